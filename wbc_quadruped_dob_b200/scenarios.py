@@ -1,0 +1,238 @@
+"""Deterministic synthetic inputs for the batched WBC control cycle.
+
+Stands in for the reference's Gazebo / ROS / TOWR layers (L5-L3): robot states, desired CoM and
+swing-foot trajectory samples, contact modes, contact-sensor forces, pushes and terrain frames.
+All arrays are SoA: shape [k, n] float64 (component-major), `mode` is int32 [n].
+
+Randomness: numpy Philox, keyed by (seed, block) with blocks of 4096 instances, so instance i gets
+the same numbers whatever the batch size or the number of ranks that shard the batch.
+
+DoF order (canonical, tools/gen_model.py): [roll BL, BR, FL, FR, BL pitch, BL knee, BR pitch,
+BR knee, FL pitch, FL knee, FR pitch, FR knee].  Stacked foot order: BR, BL, FL, FR (main.cpp:674-686).
+"""
+import numpy as np
+
+BLOCK = 4096
+MODE_STANCE, MODE_SWING_BR_FL, MODE_SWING_BL_FR = 0, 1, 2
+TOTAL_MASS = 21.261
+
+# nominal stand (main.cpp:1977-1988, 2001), canonical DoF order
+Q_NOMINAL = np.array([0.000488, 0.000624, -3.2e-05, -0.000513,
+                      -0.88425, -1.60390, 0.88620, 1.60326,
+                      -0.88481, -1.60396, 0.88635, 1.60361])
+BASE_Z_NOMINAL = 0.430159
+# controller joint limits (main.cpp:612-613)
+QMIN = np.array([-1.75, -1.75, -1.75, -1.75, -1.58, -2.62, -3.15, -0.02, -1.58, -2.62, -3.15, -0.02])
+QMAX = np.array([1.75, 1.75, 1.75, 1.75, 3.15, 0.02, 1.58, 2.62, 3.15, 0.02, 1.58, 2.62])
+
+# leg geometry (urdf:180-325 etc.), legs BL, BR, FL, FR
+_HIP_XYZ = np.array([[-0.088, -0.2875, 0.0], [0.088, -0.2875, 0.0], [-0.088, 0.2875, 0.0], [0.088, 0.2875, 0.0]])
+_ROLL_AXIS = np.array([[0, -1.0, 0], [0, -1.0, 0], [0, 1.0, 0], [0, 1.0, 0]])
+_PITCH_XYZ = np.array([[-0.09875, 0, 0], [0.09875, 0, 0], [-0.09875, 0, 0], [0.09875, 0, 0]])
+_PITCH_AXIS = np.array([[-1.0, 0, 0], [1.0, 0, 0], [-1.0, 0, 0], [1.0, 0, 0]])
+_KNEE_XYZ = np.array([0.0, 0.0, -0.315])
+_KNEE_AXIS = np.array([[1.0, 0, 0], [-1.0, 0, 0], [1.0, 0, 0], [-1.0, 0, 0]])
+_FOOT_XYZ = np.array([-2.059009593607686e-05, -0.016585135985853, -0.321099633029770])
+_LINK_M = np.array([0.836, 1.851, 0.302, 0.001])
+_LINK_COM = [np.array([[-0.0074, 0, 0], [0.0074, 0, 0], [-0.0074, 0, 0], [0.0074, 0, 0]]),
+             np.array([[-0.0418, 0, -0.0517], [0.0418, 0, -0.0517], [-0.0418, 0, -0.0517], [0.0418, 0, -0.0517]]),
+             np.tile(np.array([0, -0.029, -0.1439]), (4, 1))]
+_FOOT_LEG = [1, 0, 2, 3]   # stacked foot -> leg
+
+
+def _rot_axis(axis, th):
+    """Rodrigues rotation, axis [3], th [n] -> [n,3,3]."""
+    a = np.asarray(axis, dtype=np.float64)
+    K = np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]])
+    s, c = np.sin(th)[:, None, None], np.cos(th)[:, None, None]
+    return np.eye(3)[None] + s * K[None] + (1 - c) * (K @ K)[None]
+
+
+def rpy_to_rot(rpy):
+    """Fixed-axis XYZ (tf getRPY convention, main.cpp:436-446): R = Rz(yaw) Ry(pitch) Rx(roll). rpy [3,n] -> [n,3,3]."""
+    r, p, y = rpy
+    return _rot_axis([0, 0, 1], y) @ _rot_axis([0, 1, 0], p) @ _rot_axis([1, 0, 0], r)
+
+
+def forward_kinematics(base_pos, base_rot, q):
+    """Positions only (numpy, vectorised): returns (com [n,3], foot_pos [n,4,3] stacked BR,BL,FL,FR).
+
+    base_pos [3,n], base_rot [9,n] row-major, q [12,n].  An independent restatement used to place
+    desired trajectories near the actual CoM / feet and as a cross-check in the tests.
+    """
+    n = q.shape[1]
+    R0 = base_rot.T.reshape(n, 3, 3)
+    p0 = base_pos.T
+    msum = np.full(n, 9.301)
+    com = 9.301 * p0
+    feet = np.zeros((n, 4, 3))
+    for leg in range(4):
+        R1 = R0 @ _rot_axis(_ROLL_AXIS[leg], q[leg])
+        p1 = p0 + np.einsum("nij,j->ni", R0, _HIP_XYZ[leg])
+        R2 = R1 @ _rot_axis(_PITCH_AXIS[leg], q[4 + 2 * leg])
+        p2 = p1 + np.einsum("nij,j->ni", R1, _PITCH_XYZ[leg])
+        R3 = R2 @ _rot_axis(_KNEE_AXIS[leg], q[5 + 2 * leg])
+        p3 = p2 + np.einsum("nij,j->ni", R2, _KNEE_XYZ)
+        pf = p3 + np.einsum("nij,j->ni", R3, _FOOT_XYZ)
+        for m, R, p, c in ((_LINK_M[0], R1, p1, _LINK_COM[0][leg]), (_LINK_M[1], R2, p2, _LINK_COM[1][leg]),
+                           (_LINK_M[2], R3, p3, _LINK_COM[2][leg]), (_LINK_M[3], R3, pf, np.zeros(3))):
+            com = com + m * (p + np.einsum("nij,j->ni", R, c))
+            msum = msum + m
+        feet[:, _FOOT_LEG.index(leg), :] = pf
+    return com / msum[:, None], feet
+
+
+def _rng(seed, block, stream):
+    return np.random.Generator(np.random.Philox(key=[int(seed) & 0xFFFFFFFFFFFFFFFF, (int(block) << 8) | int(stream)]))
+
+
+def _block(seed, blk, cnt, mode_mix, pushes, terrain):
+    g = lambda s: _rng(seed, blk, s)
+    n = cnt
+    sc = {}
+    xy = g(0).uniform(-1.0, 1.0, (2, n))
+    xy[xy == 0.0] = 0.25                                    # never the all-zero base position (main.cpp:584-588)
+    z = g(1).uniform(0.36, 0.44, (1, n))
+    sc["base_pos"] = np.vstack([xy, z])
+    rpy = g(2).normal(0.0, 0.05, (3, n))
+    sc["base_rpy"] = rpy
+    R = rpy_to_rot(rpy)
+    sc["base_rot"] = np.ascontiguousarray(R.reshape(n, 9).T)
+    sc["base_vel"] = g(3).normal(0.0, 0.1, (6, n))
+    q = Q_NOMINAL[:, None] + g(4).normal(0.0, 0.05, (12, n))
+    sc["q"] = np.clip(q, QMIN[:, None], QMAX[:, None])
+    sc["dq"] = g(5).normal(0.0, 0.5, (12, n))
+    com, feet = forward_kinematics(sc["base_pos"], sc["base_rot"], sc["q"])
+    sc["com_des_pos"] = np.vstack([com.T + g(6).normal(0.0, 0.02, (3, n)), rpy + g(7).normal(0.0, 0.02, (3, n))])
+    sc["com_des_vel"] = g(8).normal(0.0, 0.05, (6, n))
+    sc["com_des_acc"] = g(9).normal(0.0, 0.5, (6, n))
+    u = g(10).uniform(0.0, 1.0, n)
+    mode = np.full(n, MODE_STANCE, dtype=np.int32)
+    mode[u >= mode_mix[0]] = MODE_SWING_BR_FL
+    mode[u >= mode_mix[0] + mode_mix[1]] = MODE_SWING_BL_FR
+    sc["mode"] = mode
+    # contact-sensor forces (sensor frame), stacked BR,BL,FL,FR
+    ff = np.zeros((12, n))
+    fz = TOTAL_MASS * 9.81 / 4.0 * g(11).uniform(0.7, 1.3, (4, n))
+    fxy = g(12).normal(0.0, 5.0, (8, n))
+    for f in range(4):
+        ff[3 * f + 0], ff[3 * f + 1], ff[3 * f + 2] = fxy[2 * f], fxy[2 * f + 1], fz[f]
+    if pushes:
+        # force_plugin case-4/5 law (fp.cpp:203-310): Fx = +-(5 + U{0..19}), Fy = +-(5 + U{0..9}) on one leg
+        gp = g(13)
+        leg = gp.integers(0, 4, n)
+        fx = (5.0 + gp.integers(0, 20, n)) * gp.choice([-1.0, 1.0], n)
+        fy = (5.0 + gp.integers(0, 10, n)) * gp.choice([-1.0, 1.0], n)
+        idx = np.arange(n)
+        ff[3 * leg + 0, idx] += fx
+        ff[3 * leg + 1, idx] += fy
+    sc["foot_force"] = ff
+    # swing-foot references: the two swing feet in Jsw row order (mode 1: BR,FL = stacked 0,2; mode 2: BL,FR = 1,3)
+    first = np.where(mode == MODE_SWING_BL_FR, 1, 0)
+    second = np.where(mode == MODE_SWING_BL_FR, 3, 2)
+    idx = np.arange(n)
+    swp = np.hstack([feet[idx, first, :], feet[idx, second, :]]).T        # [6,n]
+    arc = np.zeros((6, n))
+    arc[2] = arc[5] = 0.06 * g(14).uniform(0.0, 1.0, n)                    # up to the 6 cm apex
+    sc["sw_des_pos"] = swp + arc + g(15).normal(0.0, 0.01, (6, n))
+    sc["sw_des_vel"] = g(16).normal(0.0, 0.2, (6, n))
+    sc["sw_des_acc"] = g(17).normal(0.0, 2.0, (6, n))
+    sc["obs_yd"] = g(18).normal(0.0, 0.5, (6, n))
+    sc["obs_yw"] = g(19).normal(0.0, 0.1, (6, n))
+    if terrain:
+        gt = g(20)
+        tr = np.zeros((40, n))
+        for f in range(4):
+            # unit normal uniform on the <=15 deg cap, tangents by Gram-Schmidt from x / y, mu in U(0.4, 0.8)
+            cosmin = np.cos(np.deg2rad(15.0))
+            ct = gt.uniform(cosmin, 1.0, n)
+            st = np.sqrt(1.0 - ct * ct)
+            ph = gt.uniform(0.0, 2 * np.pi, n)
+            nrm = np.vstack([st * np.cos(ph), st * np.sin(ph), ct])
+            t1 = np.array([1.0, 0, 0])[:, None] - nrm * nrm[0]
+            t1 /= np.linalg.norm(t1, axis=0)
+            t2 = np.cross(nrm.T, t1.T).T
+            tr[10 * f + 0:10 * f + 3] = nrm
+            tr[10 * f + 3:10 * f + 6] = t1
+            tr[10 * f + 6:10 * f + 9] = t2
+            tr[10 * f + 9] = gt.uniform(0.4, 0.8, n)
+        sc["terrain"] = tr
+    return sc
+
+
+# BASELINE.json configs -> (mode mix stance/swingA/swingB, pushes, terrain, seed)
+CONFIGS = {
+    "standing_4096": dict(n=4096, mode_mix=(1.0, 0.0, 0.0), pushes=False, terrain=False, seed=1),
+    "trot_65536": dict(n=65536, mode_mix=(0.25, 0.375, 0.375), pushes=True, terrain=False, seed=2),
+    "mixed_terrain_1m": dict(n=1048576, mode_mix=(0.4, 0.3, 0.3), pushes=True, terrain=True, seed=3),
+}
+
+
+def make(n, mode_mix=(1.0, 0.0, 0.0), pushes=False, terrain=False, seed=1, start=0):
+    """Instances [start, start+n) of the infinite per-seed instance stream."""
+    if n <= 0:
+        sc = _block(seed, 0, 1, mode_mix, pushes, terrain)
+        return {k: v[..., :0] for k, v in sc.items()}
+    parts = []
+    b0, b1 = start // BLOCK, (start + n - 1) // BLOCK
+    for blk in range(b0, b1 + 1):
+        sc = _block(seed, blk, BLOCK, mode_mix, pushes, terrain)
+        lo = max(start, blk * BLOCK) - blk * BLOCK
+        hi = min(start + n, (blk + 1) * BLOCK) - blk * BLOCK
+        parts.append({k: v[..., lo:hi] for k, v in sc.items()})
+    return {k: np.ascontiguousarray(np.concatenate([p[k] for p in parts], axis=-1)) for k in parts[0]}
+
+
+def make_config(name, n=None, start=0):
+    cfg = dict(CONFIGS[name])
+    n_cfg = cfg.pop("n")
+    return make(n if n is not None else n_cfg, start=start, **cfg)
+
+
+def trot_replay(cycles_per_phase=46, seed=0x0D06B07):
+    """Config 1: ONE DogBot replaying 4 gait phases (stance, swing{BR,FL}, stance, swing{BL,FR}) of a
+    synthetic trot.  Returns a scenario whose instance index is the cycle index;
+    observer state must be chained by the caller (cycle k+1 uses the state produced by cycle k)."""
+    n = 4 * cycles_per_phase
+    t = np.arange(n) * 0.0025
+    sc = {}
+    sway = 0.02 * np.sin(2 * np.pi * 1.0 * t)
+    sc["base_pos"] = np.vstack([0.3 + sway, -0.2 + 0.5 * sway, np.full(n, BASE_Z_NOMINAL)])
+    rpy = np.vstack([0.01 * np.sin(2 * np.pi * 1.5 * t), 0.01 * np.cos(2 * np.pi * 1.2 * t), 0.05 * np.ones(n)])
+    sc["base_rpy"] = rpy
+    sc["base_rot"] = np.ascontiguousarray(rpy_to_rot(rpy).reshape(n, 9).T)
+    dsway = 0.02 * 2 * np.pi * np.cos(2 * np.pi * t)
+    sc["base_vel"] = np.vstack([dsway, 0.5 * dsway, np.zeros(n), 0.01 * 2 * np.pi * 1.5 * np.cos(2 * np.pi * 1.5 * t),
+                                -0.01 * 2 * np.pi * 1.2 * np.sin(2 * np.pi * 1.2 * t), np.zeros(n)])
+    ph = np.linspace(0, 2 * np.pi, 12, endpoint=False)[:, None]
+    sc["q"] = np.clip(Q_NOMINAL[:, None] + 0.1 * np.sin(2 * np.pi * 2.0 * t[None, :] + ph), QMIN[:, None], QMAX[:, None])
+    sc["dq"] = 0.1 * 2 * np.pi * 2.0 * np.cos(2 * np.pi * 2.0 * t[None, :] + ph)
+    com, feet = forward_kinematics(sc["base_pos"], sc["base_rot"], sc["q"])
+    # desired CoM: cubic Hermite from the initial CoM to +4 cm in x over 0.5 s (mimics main.cpp:925-940)
+    s = np.clip(t / 0.5, 0, 1)
+    hp, hv, ha = 3 * s ** 2 - 2 * s ** 3, (6 * s - 6 * s ** 2) / 0.5, (6 - 12 * s) / 0.25
+    p0 = np.array([com[0, 0], com[0, 1], 0.4])
+    des = np.zeros((6, n)); dv = np.zeros((6, n)); da = np.zeros((6, n))
+    des[0:3] = p0[:, None]; des[0] += 0.04 * hp; dv[0] = 0.04 * hv; da[0] = 0.04 * ha
+    des[5] = rpy[2]
+    sc["com_des_pos"], sc["com_des_vel"], sc["com_des_acc"] = des, dv, da
+    mode = np.repeat(np.array([MODE_STANCE, MODE_SWING_BR_FL, MODE_STANCE, MODE_SWING_BL_FR], dtype=np.int32),
+                     cycles_per_phase)
+    sc["mode"] = mode
+    rng = _rng(seed, 0, 0)
+    ff = np.zeros((12, n))
+    for f in range(4):
+        ff[3 * f + 2] = TOTAL_MASS * 9.81 / 4.0 * (1.0 + 0.1 * np.sin(2 * np.pi * 3 * t + f))
+        ff[3 * f + 0] = 2.0 * np.sin(2 * np.pi * 2 * t + f)
+        ff[3 * f + 1] = 2.0 * np.cos(2 * np.pi * 2 * t + f)
+    sc["foot_force"] = ff + rng.normal(0, 0.1, (12, n))
+    first = np.where(mode == MODE_SWING_BL_FR, 1, 0)
+    second = np.where(mode == MODE_SWING_BL_FR, 3, 2)
+    idx = np.arange(n)
+    swp = np.hstack([feet[idx, first, :], feet[idx, second, :]]).T
+    phase_t = (np.arange(n) % cycles_per_phase) / cycles_per_phase
+    arc = np.zeros((6, n)); arc[2] = arc[5] = 0.06 * np.sin(np.pi * phase_t) ** 2
+    sc["sw_des_pos"] = swp + arc
+    sc["sw_des_vel"] = np.zeros((6, n)); sc["sw_des_acc"] = np.zeros((6, n))
+    sc["obs_yd"] = np.zeros((6, n)); sc["obs_yw"] = np.zeros((6, n))
+    return sc
