@@ -1,0 +1,165 @@
+/* wbc_b200.h -- C ABI of the B200-native batched whole-body-control cycle.
+ *
+ * Drop-in boundary for the per-control-cycle hot path of prisma-lab/WBC-quadruped-DOB's
+ * dogbot_controller (reference paths are relative to /root/reference/dogbot_controller/src):
+ *
+ *   reference interface                                   replaced by
+ *   ----------------------------------------------------  ---------------------------------------
+ *   DOGCTRL::update(world_H_base, jointPos, jointVel,     wbc_cycle()  (state in: wbc_inputs)
+ *       baseVel, gravity)            client/main.cpp:63, 572-660
+ *   DOGCTRL::estimate()              client/main.cpp:692-725     wbc_cycle()  (w out; yd/yw state kept in the ctx,
+ *                                                                wbc_get/set_observer_state)
+ *   stance / swing QP assembly + tau client/main.cpp:984-1127,   wbc_cycle()  (tau out)
+ *                                    1163-1397
+ *   OPT::OPT(30,86,82), setQ, setc,  lopt.h:5-36,                wbc_qp_solve()  (dense Q, c, L in; x out)
+ *   setL_stance/_swing, opt_stance/  lopt.cpp:4-154
+ *   opt_swing
+ *
+ * Conventions
+ *   - plain C, no exceptions; every entry point returns 0 on success or a negative WBC_E* code, and
+ *     wbc_last_error() returns a message for the calling thread's last failure;
+ *   - all batched arrays are SoA "component-major": element k of instance i is at ptr[k*ld + i];
+ *   - DoF order (12): roll BL, BR, FL, FR, then (pitch, knee) of BL, BR, FL, FR -- the order of the
+ *     controller's qmin/qmax tables (main.cpp:612-613); torques use the same order;
+ *   - stacked foot order (forces, terrain, contact Jacobian rows): BR, BL, FL, FR (main.cpp:674-686);
+ *   - a ctx is bound to one GPU; calls on one ctx must be serialised by the caller, different ctxs
+ *     are independent (one ctx per GPU / per rank);
+ *   - there is no CPU fallback: every call fails with WBC_ENODEV when no sm_100 device is usable.
+ */
+#ifndef WBC_B200_H
+#define WBC_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WBC_OK 0
+#define WBC_EINVAL (-1)     /* bad argument */
+#define WBC_ENODEV (-2)     /* no usable CUDA device */
+#define WBC_ECUDA (-3)      /* CUDA runtime error (see wbc_last_error) */
+#define WBC_ENOMEM (-4)
+
+/* contact modes: which feet swing */
+#define WBC_MODE_STANCE 0        /* main.cpp:979-1148, 1516-1675 */
+#define WBC_MODE_SWING_BR_FL 1   /* main.cpp:1155-1424 */
+#define WBC_MODE_SWING_BL_FR 2   /* main.cpp:1703-1949 */
+
+/* wbc_cycle / wbc_qp_solve flags */
+#define WBC_HOST_PTRS 0u         /* in/out pointers are host memory: H2D + D2H copies are part of the call */
+#define WBC_DEVICE_PTRS 1u       /* in/out pointers are device memory on the ctx's GPU: launch only */
+#define WBC_NO_SYNC 2u           /* (device pointers only) return after enqueueing on the stream */
+
+typedef struct wbc_ctx wbc_ctx;
+
+/* Gains, limits and solver settings; wbc_default_params() fills the reference's literals. */
+typedef struct wbc_params {
+    double kcom, dcom;        /* 2500, 50          main.cpp:1019-1020 */
+    double q1_weight;         /* 50                main.cpp:997       */
+    double slack_weight;      /* 1e8               main.cpp:1187      */
+    double mu;                /* 0.6               main.cpp:1062      */
+    double tau_max;           /* 60                main.cpp:1090-1091 */
+    double joint_dt;          /* 0.025             main.cpp:1098      */
+    double kp_sw, kd_sw;      /* 300, 20           main.cpp:1371-1373 */
+    double g_acc;             /* 9.81              main.cpp:702, 1016 */
+    double obs_gain;          /* 10                main.cpp:708       */
+    double obs_dt;            /* 0.0025            main.cpp:715       */
+    double gravity[3];        /* (0,0,-9.8)        main.cpp:855       */
+    double qp_epsx, qp_rho;   /* 1e-2, 1e4         lopt.cpp:101, 138  */
+    int qp_outerits;          /* 5                 lopt.cpp:101, 138  */
+    int observer_enabled;     /* 1: call estimate() at main.cpp:1029/1220/1569/1767 (reference ships 0) */
+    int fix_swing_rhs;        /* 0: keep the reference's zero swing-equality rhs (main.cpp:1238-1241) */
+    int reserved;
+} wbc_params;
+
+/* One control cycle's inputs for n instances (what update() receives plus the members it reads). */
+typedef struct wbc_inputs {
+    const double* base_pos;     /* [3]  base position, world                          main.cpp:440-446 */
+    const double* base_rot;     /* [9]  world_R_base row-major (_world_H_base block)  main.cpp:447-451 */
+    const double* base_rpy;     /* [3]  roll pitch yaw (_base_pos[3:6])               main.cpp:596     */
+    const double* base_vel;     /* [6]  linear, angular velocity, world (MIXED)       main.cpp:453     */
+    const double* q;            /* [12] joint positions                               main.cpp:388-433 */
+    const double* dq;           /* [12] joint velocities                                               */
+    const double* com_des_pos;  /* [6]  desired CoM pose sample                       main.cpp:1005-1010 */
+    const double* com_des_vel;  /* [6]                                                                  */
+    const double* com_des_acc;  /* [6]                                                                  */
+    const double* sw_des_pos;   /* [6]  two swing feet, Jsw row order                 main.cpp:1333-1368 */
+    const double* sw_des_vel;   /* [6]                                                                  */
+    const double* sw_des_acc;   /* [6]                                                                  */
+    const double* foot_force;   /* [12] contact-sensor forces, foot frames            main.cpp:794-834 */
+    const double* terrain;      /* [40] per foot n(3) t1(3) t2(3) mu(1); NULL = flat  main.cpp:1062-1078 */
+    const int* mode;            /* [1]  WBC_MODE_*                                                      */
+    long ld;                    /* leading dimension (>= n) of every array above                       */
+} wbc_inputs;
+
+typedef struct wbc_outputs {
+    double* tau;        /* [12] joint torques                               main.cpp:1126, 1396 */
+    double* w;          /* [6]  estimated disturbance wrench w[0]           main.cpp:718        */
+    double* x;          /* [30] QP solution, may be NULL                    lopt.cpp:108-110    */
+    double* qp_obj;     /* [1]  0.5 x'Qx + c'x, may be NULL                                     */
+    int* status;        /* [1]  0 ok; <0 solver failure (the reference swallows these, lopt.cpp:114), may be NULL */
+    int* qp_info;       /* [8]  ncholesky, outer its, QQP calls, working set, max KKT dim, flags, 0, 0; may be NULL */
+    double* qp_flops;   /* [1]  instrumented algorithmic flop count of the solve, may be NULL */
+    long ld;
+} wbc_outputs;
+
+/* Intermediates of update() for stage-by-stage validation (all may be NULL individually). */
+typedef struct wbc_debug {
+    double* M;            /* [324] getFreeFloatingMassMatrix        main.cpp:620 */
+    double* h;            /* [18]  generalizedBiasForces            main.cpp:622 */
+    double* g;            /* [18]  generalizedGravityForces         main.cpp:628 */
+    double* Jac_lin;      /* [216] linear rows of Jac               main.cpp:632, 727-737 */
+    double* Jdqd_lin;     /* [12]  linear rows of Jdqd              main.cpp:634 */
+    double* com;          /* [3] */
+    double* com_vel;      /* [3] */
+    double* Mcom_b;       /* [36]  MassMatrixCOM[0:6,0:6]           main.cpp:645 */
+    double* Mcom_j;       /* [144] MassMatrixCOM[6:18,6:18] */
+    double* hcom;         /* [18]  BiasCOM                          main.cpp:648 */
+    double* gcom;         /* [18]  GravMatrixCOM                    main.cpp:651 */
+    double* Jcom_lin;     /* [216] JacCOM_lin                       main.cpp:655 */
+    double* Jdqdcom_lin;  /* [12]  JdqdCOM_lin                      main.cpp:659 */
+    double* foot_pos;     /* [12] */
+    double* foot_vel;     /* [12] */
+    double* Fgrf;         /* [12]                                   main.cpp:1022-1026 */
+    double* Wcom_des;     /* [6]                                    main.cpp:1032 */
+    long ld;
+} wbc_debug;
+
+void wbc_default_params(wbc_params* p);
+const char* wbc_last_error(void);
+const char* wbc_version(void);
+
+/* ctx lifetime.  max_batch bounds n of every later call; device is the CUDA ordinal. */
+int wbc_create(wbc_ctx** out, int device, int max_batch, const wbc_params* params);
+int wbc_destroy(wbc_ctx* ctx);
+int wbc_set_params(wbc_ctx* ctx, const wbc_params* params);
+
+/* Observer state yd, yw (main.cpp:243, 721-724): SoA [6][ld], host pointers.  The ctx zero-initialises it. */
+int wbc_set_observer_state(wbc_ctx* ctx, int n, const double* yd, const double* yw, long ld);
+int wbc_get_observer_state(wbc_ctx* ctx, int n, double* yd, double* yw, long ld);
+
+/* One control cycle for n instances: update() -> Fgrf -> estimate() -> QP assembly -> solve -> tau.
+ * `cuda_stream` is a cudaStream_t (NULL = the ctx's own stream). */
+int wbc_cycle(wbc_ctx* ctx, int n, const wbc_inputs* in, const wbc_outputs* out, void* cuda_stream, unsigned flags);
+
+/* update() only, with intermediates dumped (does not touch the observer state). */
+int wbc_debug_update(wbc_ctx* ctx, int n, const wbc_inputs* in, const wbc_debug* dbg, unsigned flags);
+
+/* The OPT operator (lopt.h:5-36): n dense QPs of the controller's shape, instance-major:
+ *   Q [n][30*30] row-major (lower triangle used, opt.cpp:4962), c [n][30], L [n][nrows*31] row-major,
+ *   first neq rows "=", the rest "<=" (lopt.cpp:35-66); x [n][30].  nrows <= 86.
+ *   info [n][8] and flops [n] may be NULL. */
+int wbc_qp_solve(wbc_ctx* ctx, int n, const double* Q, const double* c, const double* L, int nrows, int neq, double* x,
+                 int* status, int* info, double* flops, void* cuda_stream, unsigned flags);
+
+/* Device-side timing of the last wbc_cycle on this ctx (CUDA events on the launching stream), ms. */
+int wbc_last_timing(wbc_ctx* ctx, float* front_ms, float* solve_ms);
+/* Number of kernels launched by the last wbc_cycle / wbc_qp_solve. */
+int wbc_last_launches(wbc_ctx* ctx);
+
+/* FP64 DFMA peak microbenchmark (roofline denominator): returns achieved FLOP/s on the ctx's device. */
+int wbc_measure_dfma_peak(wbc_ctx* ctx, double* flops_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
