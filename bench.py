@@ -1,0 +1,274 @@
+#!/usr/bin/env python3
+"""bench.py -- WBC control-cycle solves/s on N B200s (one process per GPU), see DESIGN.md "Measurement".
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+
+One "step" = one full control cycle (update -> Fgrf -> estimate -> QP assembly -> DENSE-AUL solve -> tau) over one
+batch of synthetic DogBot instances.  At N=1 the workload is BASELINE.json configs[1] (4096 standing instances);
+with N ranks every rank runs its own shard of N x that batch (weak scaling, no data-path collective; one NCCL
+all-reduce of a 7-double statistics vector at the end).
+
+  value     solves/s, inputs and outputs resident in HBM (device pointers through the C ABI), CUDA-event timed
+  e2e       solves/s through the reference-facing call with HOST buffers: H2D + kernels + D2H inside the timed region
+  roofline  the solve kernel: instrumented algorithmic FP64 flops / CUDA-event time vs the DFMA peak measured in
+            the same process; HBM figures beside it (the path is FP64-pipe/latency bound, not HBM bound)
+  cpu_baseline  the CPU oracle (C restatement + the reference's own ALGLIB) on all host cores, same inputs
+
+`--impl reference` times that CPU path alone (rank 0 only).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from wbc_quadruped_dob_b200 import scenarios as S           # noqa: E402
+from wbc_quadruped_dob_b200 import sharding                 # noqa: E402
+
+METRIC = "wbc_control_cycle_solves_per_sec"
+UNIT = "solves/s"
+FRONT_FLOPS = 32.0e3      # dynamics + CoM transform + observer + assembly per instance
+IN_BYTES = 8 * 93 + 4     # algorithmic input bytes per instance (flat ground)
+OUT_BYTES = 8 * 18        # tau + w
+
+
+def workload_cfg(name):
+    cfg = dict(S.CONFIGS[name])
+    return cfg
+
+
+def cpu_reference_run(sc, steps, warmup, sample, cores):
+    """The reference's CPU path: oracle restatement of main.cpp's cycle + the reference's own ALGLIB (oracle/_ref)."""
+    from oracle import oracle_py as op
+    op.build(ref=True)
+    kind = "reference" if op.have_ref() else "port"
+    if not op.have_ref():
+        raise SystemExit("oracle/_ref/libref_alglib_qp.so is missing: build it where /root/reference exists")
+    sub = {k: (np.ascontiguousarray(v[..., :sample]) if isinstance(v, np.ndarray) else v) for k, v in sc.items()}
+    times = []
+    for it in range(warmup + steps):
+        _, secs = op.run_cycle_batch(sub, nthreads=cores)
+        if it >= warmup:
+            times.append(secs)
+    return kind, float(np.sum(times)), times
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU during the timed region (NVML, else nvidia-smi)."""
+
+    def __init__(self, index, period=0.05):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nvml = None
+
+    def run(self):
+        names = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+                 0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+                 0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+        while not self._stop_evt.is_set():
+            try:
+                if self.nvml is not None:
+                    self.samples.append(self.nvml.nvmlDeviceGetClockInfo(self.h, self.nvml.NVML_CLOCK_SM))
+                    try:
+                        r = self.nvml.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                    except Exception:
+                        r = self.nvml.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    for bit, nm in names.items():
+                        if r & bit and nm != "gpu_idle":
+                            self.reasons.add(nm)
+                else:
+                    import subprocess
+                    o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=clocks.sm,clocks.max.sm",
+                                        "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                    a, b = o.strip().split(",")
+                    self.samples.append(int(a)); self.max_mhz = int(b)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="standing_4096", choices=sorted(S.CONFIGS))
+    ap.add_argument("--per-gpu", type=int, default=None, help="instances per GPU (default: the workload's own size, 1M config: /8)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cfg = workload_cfg(args.workload)
+    n_cfg = cfg.pop("n")
+    per_gpu = args.per_gpu or (n_cfg // 8 if args.workload == "mixed_terrain_1m" else n_cfg)
+    cores = os.cpu_count() or 1
+    config = {"workload": "%s: %d DogBot instances per GPU x %d GPU(s), 18-DoF, mode mix %s, pushes=%s, terrain=%s, seed %d" % (
+        args.workload, per_gpu, world, cfg["mode_mix"], cfg["pushes"], cfg["terrain"], cfg["seed"]),
+        "instances_per_gpu": per_gpu, "global_batch": per_gpu * world, "parallelism": "shard%d" % world,
+        "l2": "flushed between timed steps (256 MiB write)", "solver": "DENSE-AUL/QQP restatement, reference settings (1e-2, 1e4, 5)"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        sc = S.make(per_gpu, start=0, **cfg)
+        sample = per_gpu if (cores >= 16 or per_gpu <= 1024) else 1024
+        sample = min(sample, 4096)
+        kind, tot, times = cpu_reference_run(sc, args.steps, args.warmup, sample, cores)
+        val = sample * args.steps / tot
+        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind,
+                                 "sample": "first %d instances of the workload per step, all %d host threads" % (sample, cores)},
+                "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from wbc_quadruped_dob_b200 import api
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the CUDA path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    lo, hi = sharding.shard_range(per_gpu * world, rank, world)
+    n = hi - lo
+    sc = S.make(n, start=lo, **cfg)
+    batch = api.WbcBatch(max_batch=n, device=local_rank)
+    batch.set_observer_state(sc["obs_yd"], sc["obs_yw"])
+    dev_in = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in sc.items() if isinstance(v, np.ndarray)}
+    dev_out = {"tau": torch.zeros(12, n, dtype=torch.float64, device=dev), "w": torch.zeros(6, n, dtype=torch.float64, device=dev)}
+    stat_out = dict(dev_out)
+    stat_out.update(status=torch.zeros(n, dtype=torch.int32, device=dev), qp_info=torch.zeros(8, n, dtype=torch.int32, device=dev),
+                    qp_flops=torch.zeros(n, dtype=torch.float64, device=dev))
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream()
+    sp = stream.cuda_stream
+
+    def step(outs):
+        batch.cycle_device(dev_in, outs, n, n, stream=sp, sync=False)
+
+    for it in range(args.warmup):
+        step(stat_out if it == args.warmup - 1 else dev_out)
+    torch.cuda.synchronize()
+    status = stat_out["status"].cpu().numpy()
+    qp_info = stat_out["qp_info"].cpu().numpy()
+    qp_flops = stat_out["qp_flops"].cpu().numpy()
+    dfma_peak = batch.measure_dfma_peak()
+
+    # ---- timed region: K steps, device-resident, one CUDA-event pair per step on the launching stream
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t_wall0 = time.perf_counter()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    solve_ms, front_ms = [], []
+    for it in range(args.steps):
+        flush.fill_(it & 0xFF)                     # evict L2 between timed steps
+        ev[it][0].record(stream)
+        step(dev_out)
+        ev[it][1].record(stream)
+        f, s_ = batch.last_timing()                # waits for this step's last event
+        front_ms.append(f); solve_ms.append(s_)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t_wall = time.perf_counter() - t_wall0
+    step_ms = np.array([a.elapsed_time(b) for a, b in ev])
+    tot_ms = float(step_ms.sum())
+    launches = batch.last_launches() * args.steps
+
+    # ---- e2e: host buffers through the C ABI (H2D + kernels + D2H inside the timed region)
+    e2e_steps = args.steps
+    for _ in range(2):
+        batch.cycle(sc, want=())
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        out_host = batch.cycle(sc, want=())
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()
+    assert np.isfinite(out_host["tau"]).all()
+
+    # ---- max over ranks, statistics gather (the only collective)
+    if world > 1:
+        t = torch.tensor([tot_ms, e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        tot_ms, e2e_s = t.tolist()
+    stats = sharding.gather_stats(sharding.local_stats(n, status, qp_info, qp_flops, ms=tot_ms / args.steps), device=dev)
+    total_inst = per_gpu * world
+    value = total_inst * args.steps / (tot_ms * 1e-3)
+    e2e_val = total_inst * e2e_steps / e2e_s
+
+    if rank == 0:
+        solve_avg_ms = float(np.mean(solve_ms))
+        flops_launch = float(qp_flops.sum())
+        achieved = flops_launch / (solve_avg_ms * 1e-3) / 1e12
+        peak = dfma_peak / 1e12
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        hbm_ach = n * (IN_BYTES + OUT_BYTES) / (float(np.mean(step_ms)) * 1e-3) / 1e9
+        roofline = {"bound": "fp64", "kernel": "wbc_solve_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                    "frac": achieved / peak, "traffic": None,
+                    "peak_source": "own DFMA microbenchmark in this process (MEASURED_PEAKS.json has no FP64 figure)",
+                    "flops_per_solve": flops_launch / n, "kernel_ms": solve_avg_ms, "front_kernel_ms": float(np.mean(front_ms)),
+                    "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
+                            "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": tot_ms / args.steps, "p50_ms": float(np.median(step_ms)), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks,
+                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": n * IN_BYTES, "d2h_bytes_per_step": n * OUT_BYTES},
+                "gpu_launches": launches, "roofline": roofline,
+                "stats": {"solver_failures": stats["solver_failures"], "mean_ncholesky": stats["sum_ncholesky"] / total_inst,
+                          "mean_outer_its": stats["sum_outer_its"] / total_inst, "max_kkt_dim": stats["max_kkt_dim"],
+                          "wall_s_timed_region": t_wall}}
+        if world == 1 and not args.no_cpu_baseline:
+            kind, tot, _ = cpu_reference_run(sc, 1, 0, min(n, 4096), cores)
+            line["cpu_baseline"] = {"value": min(n, 4096) / tot, "unit": UNIT, "cores": cores, "kind": kind,
+                                    "sample": "one pass over the first %d instances of the workload, all %d host threads" % (min(n, 4096), cores)}
+        print(json.dumps(line))
+    batch.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

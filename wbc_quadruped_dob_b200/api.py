@@ -1,0 +1,302 @@
+"""Host-side mirror of the reference controller's per-cycle interface, on top of the C ABI.
+
+    reference (dogbot_controller/src)                         here
+    --------------------------------------------------------  ----------------------------------------
+    DOGCTRL::update(...) + estimate() + QP + tau              WbcBatch.cycle(inputs) -> tau, w, x, ...
+        client/main.cpp:572-660, 692-725, 984-1127, 1163-1397
+    OPT(30, 86, 82); setQ; setc; setL_stance; opt_stance      OPT(...).setQ(...).setc(...).setL_stance(...).opt_stance()
+        lopt.h:5-36, lopt.cpp:4-154
+
+Everything numeric happens inside libwbc_b200.so (hand-written sm_100a CUDA behind include/wbc_b200.h).
+This module only marshals pointers: numpy arrays for host buffers, torch CUDA tensors (or raw device
+pointers) for device-resident buffers.  There is no CPU fallback: loading fails loudly when the
+library is missing, and every call fails when no B200-class GPU is present.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+MODE_STANCE, MODE_SWING_BR_FL, MODE_SWING_BL_FR = 0, 1, 2
+HOST_PTRS, DEVICE_PTRS, NO_SYNC = 0, 1, 2
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+IN_FIELDS = [("base_pos", 3), ("base_rot", 9), ("base_rpy", 3), ("base_vel", 6), ("q", 12), ("dq", 12),
+             ("com_des_pos", 6), ("com_des_vel", 6), ("com_des_acc", 6),
+             ("sw_des_pos", 6), ("sw_des_vel", 6), ("sw_des_acc", 6), ("foot_force", 12), ("terrain", 40)]
+OUT_FIELDS = [("tau", 12), ("w", 6), ("x", 30), ("qp_obj", 1)]
+DEBUG_FIELDS = [("M", 324), ("h", 18), ("g", 18), ("Jac_lin", 216), ("Jdqd_lin", 12), ("com", 3), ("com_vel", 3),
+                ("Mcom_b", 36), ("Mcom_j", 144), ("hcom", 18), ("gcom", 18), ("Jcom_lin", 216), ("Jdqdcom_lin", 12),
+                ("foot_pos", 12), ("foot_vel", 12), ("Fgrf", 12), ("Wcom_des", 6)]
+
+
+class Params(C.Structure):
+    _fields_ = [(n, C.c_double) for n in
+                ("kcom", "dcom", "q1_weight", "slack_weight", "mu", "tau_max", "joint_dt", "kp_sw", "kd_sw", "g_acc",
+                 "obs_gain", "obs_dt")] + [("gravity", C.c_double * 3), ("qp_epsx", C.c_double), ("qp_rho", C.c_double),
+                                           ("qp_outerits", C.c_int), ("observer_enabled", C.c_int),
+                                           ("fix_swing_rhs", C.c_int), ("reserved", C.c_int)]
+
+
+class _Inputs(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n, _ in IN_FIELDS] + [("mode", C.c_void_p), ("ld", C.c_long)]
+
+
+class _Outputs(C.Structure):
+    _fields_ = [("tau", C.c_void_p), ("w", C.c_void_p), ("x", C.c_void_p), ("qp_obj", C.c_void_p), ("status", C.c_void_p),
+                ("qp_info", C.c_void_p), ("qp_flops", C.c_void_p), ("ld", C.c_long)]
+
+
+class _Debug(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n, _ in DEBUG_FIELDS] + [("ld", C.c_long)]
+
+
+class WbcError(RuntimeError):
+    pass
+
+
+_lib = None
+
+EXPORTS = ["wbc_default_params", "wbc_last_error", "wbc_version", "wbc_create", "wbc_destroy", "wbc_set_params",
+           "wbc_set_observer_state", "wbc_get_observer_state", "wbc_cycle", "wbc_debug_update", "wbc_qp_solve",
+           "wbc_last_timing", "wbc_last_launches", "wbc_measure_dfma_peak"]
+
+
+def lib_path():
+    return _build.LIB
+
+
+def load():
+    """dlopen libwbc_b200.so (building it in-tree first if a compiler is at hand).  Raises if impossible."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_build.LIB):
+        _build.build()
+    lib = C.CDLL(_build.LIB)
+    lib.wbc_default_params.argtypes = [C.POINTER(Params)]
+    lib.wbc_last_error.restype = C.c_char_p
+    lib.wbc_version.restype = C.c_char_p
+    lib.wbc_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.POINTER(Params)]
+    lib.wbc_destroy.argtypes = [C.c_void_p]
+    lib.wbc_set_params.argtypes = [C.c_void_p, C.POINTER(Params)]
+    lib.wbc_set_observer_state.argtypes = [C.c_void_p, C.c_int, _dp, _dp, C.c_long]
+    lib.wbc_get_observer_state.argtypes = [C.c_void_p, C.c_int, _dp, _dp, C.c_long]
+    lib.wbc_cycle.argtypes = [C.c_void_p, C.c_int, C.POINTER(_Inputs), C.POINTER(_Outputs), C.c_void_p, C.c_uint]
+    lib.wbc_debug_update.argtypes = [C.c_void_p, C.c_int, C.POINTER(_Inputs), C.POINTER(_Debug), C.c_uint]
+    lib.wbc_qp_solve.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint]
+    lib.wbc_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    lib.wbc_last_launches.argtypes = [C.c_void_p]
+    lib.wbc_measure_dfma_peak.argtypes = [C.c_void_p, _dp]
+    _lib = lib
+    return lib
+
+
+def default_params():
+    p = Params()
+    load().wbc_default_params(C.byref(p))
+    return p
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise WbcError("%s failed (%d): %s" % (what, rc, load().wbc_last_error().decode()))
+
+
+def _ptr(a):
+    """numpy array -> host pointer; torch tensor -> data_ptr(); int -> itself; None -> NULL."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):
+        return a.data_ptr()
+    return int(a)
+
+
+class WbcBatch:
+    """One ctx = one GPU.  Holds the per-instance observer state across cycles (main.cpp:243, 721-724)."""
+
+    def __init__(self, max_batch, device=0, params=None):
+        self.lib = load()
+        self.params = params or default_params()
+        self.max_batch = int(max_batch)
+        self.device = int(device)
+        h = C.c_void_p()
+        _check(self.lib.wbc_create(C.byref(h), self.device, self.max_batch, C.byref(self.params)), "wbc_create")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.wbc_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def set_params(self, params):
+        self.params = params
+        _check(self.lib.wbc_set_params(self.h, C.byref(params)), "wbc_set_params")
+
+    def set_observer_state(self, yd, yw):
+        yd = np.ascontiguousarray(yd, dtype=np.float64)
+        yw = np.ascontiguousarray(yw, dtype=np.float64)
+        n = yd.shape[1]
+        _check(self.lib.wbc_set_observer_state(self.h, n, yd.ctypes.data_as(_dp), yw.ctypes.data_as(_dp), n),
+               "wbc_set_observer_state")
+
+    def get_observer_state(self, n):
+        yd, yw = np.zeros((6, n)), np.zeros((6, n))
+        _check(self.lib.wbc_get_observer_state(self.h, n, yd.ctypes.data_as(_dp), yw.ctypes.data_as(_dp), n),
+               "wbc_get_observer_state")
+        return yd, yw
+
+    @staticmethod
+    def _inputs_struct(sc, n, keep):
+        ins = _Inputs()
+        ld = None
+        for name, k in IN_FIELDS:
+            a = sc.get(name)
+            if a is None:
+                if name != "terrain":
+                    raise WbcError("missing input array '%s'" % name)
+                setattr(ins, name, None)
+                continue
+            if isinstance(a, np.ndarray):
+                a = np.ascontiguousarray(a, dtype=np.float64)
+                keep.append(a)
+            if tuple(a.shape)[0] != k:
+                raise WbcError("input '%s' must have shape [%d, ld]" % (name, k))
+            ld = int(a.shape[1]) if ld is None else ld
+            if int(a.shape[1]) != ld:
+                raise WbcError("all inputs must share the same leading dimension")
+            setattr(ins, name, _ptr(a))
+        m = sc["mode"]
+        if isinstance(m, np.ndarray):
+            m = np.ascontiguousarray(m, dtype=np.int32)
+            keep.append(m)
+        ins.mode = _ptr(m)
+        ins.ld = ld
+        if n > ld:
+            raise WbcError("n exceeds the arrays' leading dimension")
+        return ins
+
+    def cycle(self, sc, n=None, want=("x", "qp_obj", "status", "qp_info", "qp_flops")):
+        """One control cycle on HOST (numpy) SoA inputs; returns a dict of numpy arrays [k, n]."""
+        keep = []
+        n = int(sc["mode"].shape[0]) if n is None else int(n)
+        ins = self._inputs_struct(sc, n, keep)
+        out = {"tau": np.zeros((12, n)), "w": np.zeros((6, n))}
+        if "x" in want: out["x"] = np.zeros((30, n))
+        if "qp_obj" in want: out["qp_obj"] = np.zeros(n)
+        if "status" in want: out["status"] = np.zeros(n, dtype=np.int32)
+        if "qp_info" in want: out["qp_info"] = np.zeros((8, n), dtype=np.int32)
+        if "qp_flops" in want: out["qp_flops"] = np.zeros(n)
+        o = _Outputs()
+        for k in ("tau", "w", "x", "qp_obj", "status", "qp_info", "qp_flops"):
+            setattr(o, k, _ptr(out.get(k)))
+        o.ld = max(n, 1)
+        _check(self.lib.wbc_cycle(self.h, n, C.byref(ins), C.byref(o), None, HOST_PTRS), "wbc_cycle")
+        return out
+
+    def cycle_device(self, dev_in, dev_out, n, ld, stream=None, sync=True):
+        """One control cycle on DEVICE-resident SoA buffers (dicts of torch CUDA tensors or raw pointers)."""
+        ins = _Inputs()
+        for name, _ in IN_FIELDS:
+            setattr(ins, name, _ptr(dev_in.get(name)))
+        ins.mode = _ptr(dev_in["mode"])
+        ins.ld = ld
+        o = _Outputs()
+        for k in ("tau", "w", "x", "qp_obj", "status", "qp_info", "qp_flops"):
+            setattr(o, k, _ptr(dev_out.get(k)))
+        o.ld = ld
+        flags = DEVICE_PTRS | (0 if sync else NO_SYNC)
+        _check(self.lib.wbc_cycle(self.h, n, C.byref(ins), C.byref(o), stream, flags), "wbc_cycle")
+
+    def debug_update(self, sc, n=None):
+        """update() intermediates (wbc_debug_update) for stage-by-stage validation."""
+        keep = []
+        n = int(sc["mode"].shape[0]) if n is None else int(n)
+        ins = self._inputs_struct(sc, n, keep)
+        d = _Debug()
+        out = {}
+        for name, k in DEBUG_FIELDS:
+            out[name] = np.zeros((k, n))
+            setattr(d, name, out[name].ctypes.data)
+        d.ld = n
+        _check(self.lib.wbc_debug_update(self.h, n, C.byref(ins), C.byref(d), HOST_PTRS), "wbc_debug_update")
+        return out
+
+    def qp_solve(self, Q, c, L, neq):
+        """n dense QPs, instance-major numpy arrays Q [n,30,30], c [n,30], L [n,nrows,31] (the OPT operator)."""
+        Q = np.ascontiguousarray(Q, dtype=np.float64)
+        c = np.ascontiguousarray(c, dtype=np.float64)
+        L = np.ascontiguousarray(L, dtype=np.float64)
+        n, nrows = Q.shape[0], L.shape[1]
+        x = np.zeros((n, 30))
+        status = np.zeros(n, dtype=np.int32)
+        info = np.zeros((n, 8), dtype=np.int32)
+        flops = np.zeros(n)
+        _check(self.lib.wbc_qp_solve(self.h, n, Q.ctypes.data, c.ctypes.data, L.ctypes.data, nrows, int(neq), x.ctypes.data,
+                                     status.ctypes.data, info.ctypes.data, flops.ctypes.data, None, HOST_PTRS), "wbc_qp_solve")
+        return x, status, info, flops
+
+    def last_timing(self):
+        a, b = C.c_float(0), C.c_float(0)
+        _check(self.lib.wbc_last_timing(self.h, C.byref(a), C.byref(b)), "wbc_last_timing")
+        return a.value, b.value
+
+    def last_launches(self):
+        return int(self.lib.wbc_last_launches(self.h))
+
+    def measure_dfma_peak(self):
+        v = C.c_double(0)
+        _check(self.lib.wbc_measure_dfma_peak(self.h, C.byref(v)), "wbc_measure_dfma_peak")
+        return v.value
+
+
+class OPT:
+    """Mirror of the reference's OPT class (lopt.h:5-36): same method names and argument meaning, one QP per call.
+
+    OPT(30, 86, 82) as constructed at main.cpp:266.  setQ / setc / setL_stance / setL_swing take dense arrays
+    (the reference takes Eigen matrices by value); opt_stance / opt_swing return x (the reference fills a
+    caller-allocated VectorXd and silently leaves it untouched on failure, lopt.cpp:114-116 -- here a failure
+    raises WbcError instead).
+    """
+
+    def __init__(self, control_variables=30, stance_constraint=86, swing_constraint=82, batch=None):
+        if control_variables != 30 or stance_constraint != 86 or swing_constraint != 82:
+            raise WbcError("OPT is specialised to the controller's shapes OPT(30, 86, 82) (main.cpp:266)")
+        self._own = batch is None
+        self._b = batch or WbcBatch(1)
+        self._Q = self._c = self._Ls = self._Lw = None
+
+    def setQ(self, Q_):
+        self._Q = np.array(Q_, dtype=np.float64).reshape(1, 30, 30)
+
+    def setc(self, c_):
+        self._c = np.array(c_, dtype=np.float64).reshape(1, 30)
+
+    def setL_stance(self, L_stance):
+        self._Ls = np.array(L_stance, dtype=np.float64).reshape(1, 86, 31)
+
+    def setL_swing(self, L_swing):
+        self._Lw = np.array(L_swing, dtype=np.float64).reshape(1, 82, 31)
+
+    def _solve(self, L, neq):
+        if self._Q is None or self._c is None or L is None:
+            raise WbcError("OPT: setQ, setc and setL_* must be called before opt_*")
+        x, status, _, _ = self._b.qp_solve(self._Q, self._c, L, neq)
+        if status[0] != 0:
+            raise WbcError("OPT: QP solver failed with status %d" % status[0])
+        return x[0]
+
+    def opt_stance(self):
+        return self._solve(self._Ls, 18)     # first 18 rows are equalities (lopt.cpp:40-47)
+
+    def opt_swing(self):
+        return self._solve(self._Lw, 12)     # first 12 rows are equalities (lopt.cpp:57-64)

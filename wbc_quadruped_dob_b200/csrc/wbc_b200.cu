@@ -143,7 +143,14 @@ __global__ void __launch_bounds__(256) wbc_dense_qp_kernel(Params P, int n, cons
         Stats st;
         solve_denseaul(ex, w, cfg, Q + (long)i * 900, 1, c + (long)i * 30, 1, L + (long)i * nrows * 31, 1, nrows, neq,
                        x + (long)i * 30, 1, st);
-        if (ex.lane() == 0) write_info(st, i, n, status, info, flops);
+        if (ex.lane() == 0) {   // instance-major info [n][8] on this path
+            write_info(st, i, n, status, nullptr, flops);
+            if (info) {
+                int* q = info + (long)i * 8;
+                q[0] = st.ncholesky; q[1] = st.outer_its; q[2] = st.qqp_calls; q[3] = st.nicwork; q[4] = st.kkt_dim_max;
+                q[5] = st.flags; q[6] = 0; q[7] = 0;
+            }
+        }
         __syncwarp();
     }
 }
@@ -413,7 +420,8 @@ int wbc_cycle(wbc_ctx* c, int n, const wbc_inputs* in, const wbc_outputs* out, v
     c->launches = 2;
     if (!dev_ptrs) {
         // one D2H of the packed result block, then scatter into the caller's SoA arrays
-        const size_t nd = (size_t)kOutDoubles * n;
+        // packed layout: tau 12 | w 6 | x 30 | obj 1 | flops 1 -- copy only the prefix the caller asked for
+        const size_t nd = (size_t)((out->qp_flops) ? 50 : (out->qp_obj ? 49 : (out->x ? 48 : 18))) * n;
         CU(cudaMemcpyAsync(c->h_pin, c->d_out, nd * sizeof(double), cudaMemcpyDeviceToHost, s));
         if (out->status || out->qp_info) CU(cudaMemcpyAsync(c->h_pin_i, c->d_iout, (size_t)kOutInts * n * sizeof(int), cudaMemcpyDeviceToHost, s));
         CU(cudaStreamSynchronize(s));
