@@ -171,8 +171,12 @@ def main():
     stat_out.update(status=torch.zeros(n, dtype=torch.int32, device=dev), qp_info=torch.zeros(8, n, dtype=torch.int32, device=dev),
                     qp_flops=torch.zeros(n, dtype=torch.float64, device=dev))
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    stream = torch.cuda.current_stream()
+    # a dedicated non-default stream: the C ABI treats a NULL stream as "use the ctx's own stream", and
+    # torch.cuda.Event only sees work on the stream it is recorded on -- kernels, L2 flush and events share this one
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     sp = stream.cuda_stream
+    assert sp != 0
 
     def step(outs):
         batch.cycle_device(dev_in, outs, n, n, stream=sp, sync=False)

@@ -7,6 +7,7 @@
 #include "../../wbc_quadruped_dob_b200/csrc/wbc_assemble.cuh"
 #include "../../wbc_quadruped_dob_b200/csrc/wbc_front.cuh"
 
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -66,7 +67,8 @@ int emu_cycle(const Params* P, const EmuIO* io, int n)
     std::vector<double> rec(QPREC_DOUBLES);
     HostEx ex;
     Settings cfg;
-    cfg.epsx = P->qp_epsx; cfg.rho = P->qp_rho; cfg.outerits = P->qp_outerits; cfg.kkt_mode = 0;
+    cfg.epsx = P->qp_epsx; cfg.rho = P->qp_rho; cfg.outerits = P->qp_outerits; cfg.kkt_mode = getenv("WBC_EMU_KKT") ? atoi(getenv("WBC_EMU_KKT")) : 0;
+    if (getenv("WBC_EMU_PIVTOL")) cfg.kkt_pivtol = atof(getenv("WBC_EMU_PIVTOL"));
     for (long i = 0; i < n; i++) {
         front_cycle(*P, in, st, i, rec.data(), io->w, io->ld, nullptr);
         if (io->rec) memcpy(io->rec + i * QPREC_DOUBLES, rec.data(), sizeof(double) * QPREC_DOUBLES);

@@ -40,6 +40,7 @@ struct Settings {
     double rho = 1.0e4;
     int outerits = 5;
     int kkt_mode = 0;       // 0 = literal stacked KKT least squares (opt.cpp:41803-42032); 1 = reduced
+    double kkt_pivtol = 1.0e-5;   // reduced form: relative Schur pivot below which the literal form is used
 };
 
 struct Stats {
@@ -747,6 +748,224 @@ WBC_HD void update_lagrange_multipliers(const Ex& ex, const Work& w, int nec, in
     ex.sync();
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Multiplier update, reduced form.  The stacked system above is the KKT system of the equality-
+// constrained model  min 1/2 x'Ax + b'x  s.t.  c_r'x = d_r  for r in ACT = {equalities} U {inequality
+// rows whose slack is exactly 0}; rows with a free slack get multiplier 0 (their slack-stationarity
+// row reads -nu_r = 0).  With A = LA LA' the multipliers solve the Schur-complement system
+//     (W W') nu_ACT = d_ACT + W t,   W = C_ACT LA^-T (row m: LA^-1 c_m),  t = LA^-1 b.
+// The Tikhonov term of the literal form (lambda = 1e-8 max|A_ii|) changes the result by
+// O((lambda/sigma_min(K))^2), far below the parity tolerance unless ACT is (nearly) rank deficient;
+// that case is detected by the pivots of the Schur Cholesky and handed to the literal form.
+// Returns false when the caller must fall back.
+template <class Ex>
+WBC_HD bool update_lagrange_multipliers_schur(const Ex& ex, const Work& w, int nec, int nic, Stats& st, double pivtol)
+{
+    const int ktotal = nec + nic;
+    double* LA = w.kkt;                 // [30*30] lower Cholesky factor of A
+    double* W = LA + 900;               // [ka][31]: LA^-1 c_m, and entry 30 = rhs d_m
+    int nq = NMAIN + nic + ktotal;
+    if (nq > st.kkt_dim_max) st.kkt_dim_max = nq;
+    // active list (uniform across lanes: reads shared data only)
+    int ka = 0;
+    int* act = w.isfree;                // reuse: QQP is not running
+    ex.sync();
+    for (int r = 0; r < ktotal; r++) {
+        const bool on = (r < nec) || (w.exxc[NMAIN + (r - nec)] == 0.0);
+        if (on) { if (ex.lane() == 0) act[ka] = r; ka++; }
+    }
+    ex.sync();
+    double* Sm = W + (long)ka * 31;     // [ka][ka] Schur complement, lower
+    double* tv = Sm + (long)ka * ka;    // [30] t = LA^-1 b, then [ka] solution
+    // LA = chol(A), lower, row-major; lane-per-row left-looking columns
+    for (int i = ex.lane(); i < NMAIN * NMAIN; i += Ex::NL) LA[i] = w.A[i];
+    ex.sync();
+    for (int j = 0; j < NMAIN; j++) {
+        for (int r = j + ex.lane(); r < NMAIN; r += Ex::NL) {
+            double s = LA[r * NMAIN + j];
+            for (int k = 0; k < j; k++) s -= LA[r * NMAIN + k] * LA[j * NMAIN + k];
+            LA[r * NMAIN + j] = s;
+        }
+        ex.sync();
+        const double d = sqrt(LA[j * NMAIN + j]);
+        const double rinv = 1.0 / d;
+        ex.sync();
+        for (int r = j + ex.lane(); r < NMAIN; r += Ex::NL) LA[r * NMAIN + j] = (r == j) ? d : LA[r * NMAIN + j] * rinv;
+        ex.sync();
+    }
+    // forward substitutions, one lane per right-hand side (ka rows of C and b)
+    for (int m = ex.lane(); m <= ka; m += Ex::NL) {
+        double* y = (m < ka) ? &W[m * 31] : tv;
+        const double* src = (m < ka) ? &w.C[act[m] * 31] : w.b;
+        for (int i = 0; i < NMAIN; i++) {
+            double s = src[i];
+            for (int k = 0; k < i; k++) s -= LA[i * NMAIN + k] * y[k];
+            y[i] = s / LA[i * NMAIN + i];
+        }
+        if (m < ka) y[NMAIN] = src[NMAIN];
+    }
+    ex.sync();
+    // Schur complement (lower) and right-hand side
+    for (int e = ex.lane(); e < ka * ka; e += Ex::NL) {
+        const int r = e / ka, c = e % ka;
+        if (c > r) continue;
+        double s = 0.0;
+        for (int k = 0; k < NMAIN; k++) s += W[r * 31 + k] * W[c * 31 + k];
+        Sm[r * ka + c] = s;
+    }
+    ex.sync();
+    for (int m = ex.lane(); m < ka; m += Ex::NL) {
+        double s = W[m * 31 + NMAIN];
+        for (int k = 0; k < NMAIN; k++) s += W[m * 31 + k] * tv[k];
+        w.sv0[m] = s;
+    }
+    ex.sync();
+    st.flops += 9000.0 + (double)(ka + 1) * NMAIN * NMAIN + (double)ka * ka * NMAIN + 2.0 * ka * NMAIN;
+    // delta form: rho = rhs - S nu0 (the literal system is solved for the correction to (X0, L0), and among the
+    // solutions of a rank-deficient system its Tikhonov term selects the one of least norm)
+    for (int m = ex.lane(); m < ka; m += Ex::NL) {
+        double s = 0.0;
+        for (int k = 0; k < ka; k++) s += ((k <= m) ? Sm[m * ka + k] : Sm[k * ka + m]) * w.nulcest[act[k]];
+        w.sv0[m] = w.sv0[m] - s;
+        w.qrv[m] = 0.0;
+    }
+    ex.sync();
+    double* rhs0 = w.qrv + ka;          // copy of rho for the consistency check
+    for (int m = ex.lane(); m < ka; m += Ex::NL) rhs0[m] = w.sv0[m];
+    // Cholesky of the PSD Schur complement, skipping dependent rows (relative pivot test).  Lt: [ka][ka] lower,
+    // columns compacted to the r kept pivots; keep[j] = column of row j or -1.
+    double* Lt = tv + 32;
+    int* keep = w.cstatus;
+    for (int e = ex.lane(); e < ka * ka; e += Ex::NL) Lt[e] = 0.0;
+    ex.sync();
+    int r = 0;
+    bool ambiguous = false;
+    for (int j = 0; j < ka; j++) {
+        const double d0 = Sm[j * ka + j];
+        double piv = d0;
+        for (int k = 0; k < r; k++) piv -= Lt[j * ka + k] * Lt[j * ka + k];     // redundant in every lane
+        const double ratio = piv / d0;
+        if (ratio < pivtol) {
+            if (ratio > 1.0e-3 * pivtol) ambiguous = true;
+            if (ex.lane() == 0) keep[j] = -1;
+            ex.sync();
+            continue;
+        }
+        const double d = sqrt(piv), rinv = 1.0 / d;
+        for (int i = j + ex.lane(); i < ka; i += Ex::NL) {
+            double v;
+            if (i == j) v = d;
+            else {
+                v = Sm[i * ka + j];
+                for (int k = 0; k < r; k++) v -= Lt[i * ka + k] * Lt[j * ka + k];
+                v *= rinv;
+            }
+            Lt[i * ka + r] = v;
+        }
+        if (ex.lane() == 0) keep[j] = r;
+        ex.sync();
+        r++;
+    }
+    if (ambiguous) {
+#ifdef WBC_EMU_DEBUG
+        printf("schur ambiguous ka=%d r=%d\n", ka, r);
+#endif
+        return false;
+    }
+    st.flops += (double)ka * ka * ka / 3.0 + 2.0 * ka * ka;
+    if (r == ka) {
+        // full rank: L L' delta = rho
+        for (int k = 0; k < ka; k++) {
+            const double yk = w.sv0[k] / Lt[k * ka + k];
+            ex.sync();
+            for (int i = k + ex.lane(); i < ka; i += Ex::NL) { if (i == k) w.sv0[k] = yk; else w.sv0[i] -= Lt[i * ka + k] * yk; }
+            ex.sync();
+        }
+        for (int k = ka - 1; k >= 0; k--) {
+            const double xk = w.sv0[k] / Lt[k * ka + k];
+            ex.sync();
+            for (int i = ex.lane(); i <= k; i += Ex::NL) { if (i == k) w.sv0[k] = xk; else w.sv0[i] -= Lt[k * ka + i] * xk; }
+            ex.sync();
+        }
+    } else {
+        // rank r < ka: S = Lt Lt' (ka x r), least-norm solution  delta = Lt G^-1 G^-1 Lt' rho,  G = Lt' Lt
+        double* G = Lt + (long)ka * ka;      // [r][r] lower
+        double* u = G + (long)r * r;         // [r]
+        for (int e = ex.lane(); e < r * r; e += Ex::NL) {
+            const int a = e / r, c = e % r;
+            if (c > a) continue;
+            double sacc = 0.0;
+            for (int i = 0; i < ka; i++) sacc += Lt[i * ka + a] * Lt[i * ka + c];
+            G[a * r + c] = sacc;
+        }
+        for (int a = ex.lane(); a < r; a += Ex::NL) {
+            double sacc = 0.0;
+            for (int i = 0; i < ka; i++) sacc += Lt[i * ka + a] * w.sv0[i];
+            u[a] = sacc;
+        }
+        ex.sync();
+        for (int j = 0; j < r; j++) {       // Cholesky of G (well conditioned by construction)
+            for (int i = j + ex.lane(); i < r; i += Ex::NL) {
+                double v = G[i * r + j];
+                for (int k = 0; k < j; k++) v -= G[i * r + k] * G[j * r + k];
+                G[i * r + j] = v;
+            }
+            ex.sync();
+            const double d = sqrt(G[j * r + j]), rinv = 1.0 / d;
+            ex.sync();
+            for (int i = j + ex.lane(); i < r; i += Ex::NL) G[i * r + j] = (i == j) ? d : G[i * r + j] * rinv;
+            ex.sync();
+        }
+        for (int pass = 0; pass < 2; pass++) {
+            for (int k = 0; k < r; k++) {
+                const double yk = u[k] / G[k * r + k];
+                ex.sync();
+                for (int i = k + ex.lane(); i < r; i += Ex::NL) { if (i == k) u[k] = yk; else u[i] -= G[i * r + k] * yk; }
+                ex.sync();
+            }
+            for (int k = r - 1; k >= 0; k--) {
+                const double xk = u[k] / G[k * r + k];
+                ex.sync();
+                for (int i = ex.lane(); i <= k; i += Ex::NL) { if (i == k) u[k] = xk; else u[i] -= G[k * r + i] * xk; }
+                ex.sync();
+            }
+        }
+        for (int i = ex.lane(); i < ka; i += Ex::NL) {
+            double sacc = 0.0;
+            for (int a = 0; a < r; a++) sacc += Lt[i * ka + a] * u[a];
+            w.sv0[i] = sacc;
+        }
+        ex.sync();
+        st.flops += 4.0 * ka * r * r;
+        st.flags |= 16;
+    }
+    // consistency: S delta must reproduce rho (fails only when dependent active rows carry inconsistent right-hand sides)
+    double worst = 0.0, scale = 0.0;
+    for (int m = ex.lane(); m < ka; m += Ex::NL) {
+        double sacc = 0.0;
+        for (int k = 0; k < ka; k++) sacc += ((k <= m) ? Sm[m * ka + k] : Sm[k * ka + m]) * w.sv0[k];
+        worst = fmax(worst, fabs(sacc - rhs0[m]));
+        scale = fmax(scale, fabs(W[m * 31 + NMAIN]));      // |d_m|: rho is a difference of terms of this size
+    }
+    worst = ex.maxv(worst);
+    scale = ex.maxv(scale);
+    if (worst > 1.0e-9 * (scale + 1.0)) {
+#ifdef WBC_EMU_DEBUG
+        printf("schur inconsistent ka=%d r=%d worst=%.3e scale=%.3e\n", ka, r, worst, scale);
+#endif
+        return false;
+    }
+    double* nu0 = w.qrv;                    // save nu0 before zeroing
+    for (int m = ex.lane(); m < ka; m += Ex::NL) nu0[m] = w.nulcest[act[m]];
+    ex.sync();
+    for (int i = ex.lane(); i < ktotal; i += Ex::NL) w.nulcest[i] = 0.0;
+    ex.sync();
+    for (int m = ex.lane(); m < ka; m += Ex::NL) w.nulcest[act[m]] = nu0[m] + w.sv0[m];
+    ex.sync();
+    return true;
+}
+
 // ------------------------------------------------------------------------------------------------
 // generateexmodel (opt.cpp:41594-41740): extended box-QP in [x; slacks].  Upper triangle of exa.
 template <class Ex>
@@ -960,7 +1179,10 @@ WBC_HDN void solve_denseaul(const Ex& ex, const Work& w, const Settings& cfg, co
         // multiplier estimate (41438-41439)
         for (int i = ex.lane(); i < kwork; i += Ex::NL) w.nulcest[i] = w.nulc[i];
         ex.sync();
-        update_lagrange_multipliers(ex, w, nec, nicwork, st);
+        if (!(cfg.kkt_mode == 1 && update_lagrange_multipliers_schur(ex, w, nec, nicwork, st, cfg.kkt_pivtol))) {
+            if (cfg.kkt_mode == 1) st.flags |= 8;
+            update_lagrange_multipliers(ex, w, nec, nicwork, st);
+        }
         // feasibility error and multiplier update (41444-41476): lane-per-row, summed in row order
         double feaserrprev = feaserr;
         double fe = 0.0;
