@@ -1,9 +1,9 @@
 // TEST-ONLY host emulation of the device control-cycle path: compiles the product headers
-// (wbc_front.cuh, wbc_assemble.cuh, qp_denseaul.cuh) with g++ and the single-lane `HostEx` executor so
+// (wbc_front.cuh, wbc_assemble.cuh, qp_team.cuh) with g++ and the single-lane `HostEx` executor so
 // that the device code's arithmetic and decisions can be unit-tested on a machine without a GPU
 // (`pytest -m "not gpu"`).  It is NOT linked into libwbc_b200.so and never used by bench.py or by the
 // product path; GPU parity tests call the CUDA kernels through the C ABI instead.
-#include "../../wbc_quadruped_dob_b200/csrc/qp_denseaul.cuh"
+#include "emu_work.h"
 #include "../../wbc_quadruped_dob_b200/csrc/wbc_assemble.cuh"
 #include "../../wbc_quadruped_dob_b200/csrc/wbc_front.cuh"
 
@@ -13,31 +13,6 @@
 
 using namespace wbc;
 using namespace wbcqp;
-
-struct EmuWork {
-    std::vector<double> buf;
-    std::vector<int> ibuf;
-    Work w;
-    EmuWork()
-    {
-        const int nqmax = MAXNT + MAXK;
-        size_t nd = 900 + 30 + 30 + MAXK * 31 + MAXNIC + 2 * MAXK + 2 * MAXNT + 2 * MAXNT * MAXNT + 12 * MAXNT +
-                    (size_t)kkt_doubles(nqmax) + 2 * nqmax + 2 + nqmax;
-        buf.assign(nd, 0.0);
-        ibuf.assign(MAXNIC + 2 * MAXNT, 0);
-        double* p = buf.data();
-        w.A = p; p += 900; w.b = p; p += 30; w.s = p; p += 30; w.C = p; p += MAXK * 31;
-        w.nicerr = p; p += MAXNIC; w.nulc = p; p += MAXK; w.nulcest = p; p += MAXK;
-        w.exxc = p; p += MAXNT; w.exb = p; p += MAXNT;
-        w.exa = p; p += MAXNT * MAXNT; w.z = p; p += MAXNT * MAXNT;
-        w.xc = p; p += MAXNT; w.xp = p; p += MAXNT; w.xf = p; p += MAXNT; w.gc = p; p += MAXNT;
-        w.cgc = p; p += MAXNT; w.cgp = p; p += MAXNT; w.dc = p; p += MAXNT; w.dp = p; p += MAXNT;
-        w.tmp0 = p; p += MAXNT; w.tmp1 = p; p += MAXNT; w.regdiag = p; p += MAXNT; w.bufr = p; p += MAXNT;
-        w.kkt = p; p += kkt_doubles(nqmax); w.qrv = p; p += 2 * nqmax + 2; w.sv0 = p; p += nqmax;
-        int* ip = ibuf.data();
-        w.nicnact = ip; ip += MAXNIC; w.cstatus = ip; ip += MAXNT; w.isfree = ip; ip += MAXNT;
-    }
-};
 
 extern "C" {
 
@@ -67,16 +42,17 @@ int emu_cycle(const Params* P, const EmuIO* io, int n)
     std::vector<double> rec(QPREC_DOUBLES);
     HostEx ex;
     Settings cfg;
-    cfg.epsx = P->qp_epsx; cfg.rho = P->qp_rho; cfg.outerits = P->qp_outerits; cfg.kkt_mode = getenv("WBC_EMU_KKT") ? atoi(getenv("WBC_EMU_KKT")) : 0;
+    cfg.epsx = P->qp_epsx; cfg.rho = P->qp_rho; cfg.outerits = P->qp_outerits; cfg.kkt_mode = getenv("WBC_EMU_KKT") ? atoi(getenv("WBC_EMU_KKT")) : 1;
     if (getenv("WBC_EMU_PIVTOL")) cfg.kkt_pivtol = atof(getenv("WBC_EMU_PIVTOL"));
     for (long i = 0; i < n; i++) {
         front_cycle(*P, in, st, i, rec.data(), io->w, io->ld, nullptr);
         if (io->rec) memcpy(io->rec + i * QPREC_DOUBLES, rec.data(), sizeof(double) * QPREC_DOUBLES);
         const QpShape sh = qp_shape((int)rec[QR_MODE]);
-        assemble_qp(ex, *P, rec.data(), sh, ew.w.z, ew.w.exb, ew.w.C);
+        assemble_qp(ex, *P, rec.data(), sh, ew.w.Ssh, ew.w.exb, ew.w.C);
         Stats s;
         double xs[30];
-        solve_denseaul(ex, ew.w, cfg, ew.w.z, 1, ew.w.exb, 1, ew.w.C, 1, sh.nrows, sh.neq, xs, 1, s);
+        solve_denseaul(ex, ew.w, cfg, sh.nrows, sh.neq, s);
+        memcpy(xs, ew.w.xs, sizeof(xs));
         if (s.termination != 2) memset(xs, 0, sizeof(xs));
         torque_and_objective(ex, *P, rec.data(), sh, xs, io->tau + i, io->ld, io->qp_obj ? io->qp_obj + i : nullptr);
         if (io->x) for (int k = 0; k < 30; k++) io->x[k * io->ld + i] = xs[k];

@@ -101,7 +101,7 @@ class Emu:
         self.lib.emu_cycle(C.byref(P), C.byref(io), n)
         return out
 
-    def qp_solve(self, Q, c, L, neq, epsx=1e-2, rho=1e4, outerits=5):
+    def qp_solve(self, Q, c, L, neq, epsx=1e-2, rho=1e4, outerits=5, kkt_mode=1):
         Q = np.ascontiguousarray(Q, dtype=np.float64)
         c = np.ascontiguousarray(c, dtype=np.float64)
         L = np.ascontiguousarray(L, dtype=np.float64)
@@ -109,7 +109,7 @@ class Emu:
         ist = (C.c_int * 8)()
         ds = (C.c_double * 2)()
         self.qp.emu_qp_solve(Q.ctypes.data_as(_dp), c.ctypes.data_as(_dp), L.ctypes.data_as(_dp), L.shape[0], int(neq),
-                             epsx, rho, outerits, 0, x.ctypes.data_as(_dp), ist, ds)
+                             epsx, rho, outerits, kkt_mode, x.ctypes.data_as(_dp), ist, ds)
         return x, list(ist), ds[0]
 
 

@@ -34,7 +34,8 @@ def build(force=False, verbose=False):
     if not force and not stale():
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    extra = os.environ.get("WBC_NVCC_EXTRA", "").split()      # experiments only (e.g. -DWBC_SOLVE_T=64)
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     with open(os.path.join(LIBDIR, "build.log"), "w") as f:
         f.write(" ".join(cmd) + "\n" + res.stdout)

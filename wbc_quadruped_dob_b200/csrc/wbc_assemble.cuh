@@ -5,7 +5,7 @@
 //   swing   main.cpp:1163-1389  x = [ddq_com(6) | ddq_j(12) | f_st(6) | g(6)], L 82 x 31, 12 equalities
 //   torque  main.cpp:1126, 1396 tau = Mjj ddq_j + h_j - Jst_j' f
 #pragma once
-#include "qp_denseaul.cuh"
+#include "qp_team.cuh"
 #include "wbc_types.h"
 
 namespace wbc {
@@ -156,7 +156,7 @@ WBC_HDN inline void torque_and_objective(const Ex& ex, const Params& P, const do
         // x'Qx = sum_i R_ii x_i^2 + q1 |Jst_c' f|^2 ;  c'x = -q1 (Jst_c' f) . Wcom_des
         double sq = 0.0;
         for (int k = lane; k < 30; k += Ex::NL) sq += ((sh.nst == 2 && k >= 24) ? P.slack_weight : 1.0) * x[k] * x[k];
-        sq = ex.sum(sq);
+        sq = wbcqp::allsum1(ex, sq);
         double jj = 0.0, jw = 0.0;
         for (int t = lane; t < 6; t += Ex::NL) {
             double s = 0.0;
@@ -164,8 +164,11 @@ WBC_HDN inline void torque_and_objective(const Ex& ex, const Params& P, const do
             jj += s * s;
             jw += s * Wc[t];
         }
-        jj = ex.sum(jj);
-        jw = ex.sum(jw);
+        {
+            double r2[2] = {jj, jw};
+            ex.template allred<2, 0>(r2, r2);
+            jj = r2[0]; jw = r2[1];
+        }
         if (lane == 0) *obj_out = 0.5 * (sq + P.q1_weight * jj) - P.q1_weight * jw;
     }
     ex.sync();

@@ -2,9 +2,10 @@
 //
 // Two kernels per cycle, no intermediate dense QP ever reaches HBM:
 //   wbc_front_kernel   thread-per-instance: update() + Fgrf + estimate() + Wcom_des -> 4.2 KB QP record
-//   wbc_solve_kernel   warp-per-instance, persistent warps pulling instances from an atomic queue
-//                      (iteration counts vary 4..50 Cholesky per solve): assemble (Q,c,L) from the
-//                      record straight into the warp's scratch, DENSE-AUL/QQP solve, torque map.
+//   wbc_solve_kernel   CTA-per-instance (a team of SOLVE_T threads, 4 CTAs per SM), persistent CTAs pulling
+//                      instances from an atomic queue (iteration counts vary 4..50 Cholesky per solve):
+//                      assemble (Q,c,L) from the record straight into shared memory, DENSE-AUL/QQP solve with
+//                      everything hot in shared memory (qp_team.cuh), torque map.
 // There is no CPU fallback anywhere in this file.
 #include <cuda_runtime.h>
 #include <stdio.h>
@@ -13,7 +14,7 @@
 #include <new>
 
 #include "../../include/wbc_b200.h"
-#include "qp_denseaul.cuh"
+#include "qp_team.cuh"
 #include "wbc_assemble.cuh"
 #include "wbc_front.cuh"
 #include "wbc_types.h"
@@ -23,52 +24,62 @@ using namespace wbcqp;
 
 static_assert(sizeof(wbc_params) == sizeof(wbc::Params), "wbc_params and wbc::Params must have identical layout");
 
-// ------------------------------------------------------------------------------------------------
-// per-warp scratch layout (doubles)
-namespace scratch {
-constexpr int NQMAX = MAXNT + MAXK;
-constexpr long OFF_A = 0;
-constexpr long OFF_B = OFF_A + 900;
-constexpr long OFF_S = OFF_B + 32;
-constexpr long OFF_C = OFF_S + 32;
-constexpr long OFF_NICERR = OFF_C + MAXK * 31;
-constexpr long OFF_NULC = OFF_NICERR + MAXNIC;
-constexpr long OFF_NULCEST = OFF_NULC + MAXK;
-constexpr long OFF_EXXC = OFF_NULCEST + MAXK;
-constexpr long OFF_EXB = OFF_EXXC + MAXNT;
-constexpr long OFF_VEC = OFF_EXB + MAXNT;                 // 12 vectors of MAXNT
-constexpr long OFF_QRV = OFF_VEC + 12 * MAXNT;
-constexpr long OFF_SV0 = OFF_QRV + 2 * NQMAX + 2;
-constexpr long OFF_X = OFF_SV0 + NQMAX;                   // 32: solution
-constexpr long OFF_INT = OFF_X + 32;                      // ints: nicnact[MAXNIC], cstatus[MAXNT], isfree[MAXNT]
-constexpr long INT_DOUBLES = (MAXNIC + 2 * MAXNT + 1) / 2 + 1;
-constexpr long OFF_EXA = ((OFF_INT + INT_DOUBLES + 15) / 16) * 16;
-constexpr long OFF_Z = OFF_EXA + (long)MAXNT * MAXNT;
-constexpr long OFF_KKT = OFF_Z + (long)MAXNT * MAXNT;
-constexpr long TOTAL = ((OFF_KKT + 2L * NQMAX * (NQMAX + 1) + 15) / 16) * 16;
-}  // namespace scratch
+#ifndef WBC_SOLVE_T
+#define WBC_SOLVE_T 128
+#endif
+constexpr int SOLVE_T = WBC_SOLVE_T;          // threads per team (= per CTA)
+constexpr int SOLVE_CTAS_PER_SM = 4;
 
-__device__ __forceinline__ Work carve_work(double* p)
+// ------------------------------------------------------------------------------------------------
+// per-team storage layout (doubles)
+namespace gscr {      // global scratch
+constexpr int NQMAX = MAXNT + MAXK;
+constexpr long OFF_SA = 0;
+constexpr long OFF_SGL = 944;
+constexpr long OFF_VGL = OFF_SGL + ((long)MAXNT * LDG + 15) / 16 * 16;
+constexpr long OFF_QRV = OFF_VGL + (long)NVEC * VLG;
+constexpr long OFF_SV0 = OFF_QRV + 2 * NQMAX + 4;
+constexpr long OFF_KKT = ((OFF_SV0 + NQMAX + 15) / 16) * 16;
+constexpr long TOTAL = ((OFF_KKT + 2L * NQMAX * (NQMAX + 1) + 15) / 16) * 16;
+}  // namespace gscr
+namespace sscr {      // shared memory
+constexpr int OFF_S = 0;
+constexpr int OFF_V = OFF_S + S_DOUBLES;
+constexpr int OFF_C = OFF_V + NVEC * NCAP;
+constexpr int OFF_LARINV = OFF_C + MAXK * 31;
+constexpr int OFF_LADIAG = OFF_LARINV + 32;
+constexpr int OFF_B = OFF_LADIAG + 32;
+constexpr int OFF_SC = OFF_B + 32;
+constexpr int OFF_NICERR = OFF_SC + 32;
+constexpr int OFF_NULC = OFF_NICERR + MAXNIC;
+constexpr int OFF_NULCEST = OFF_NULC + MAXK;
+constexpr int OFF_EXXC = OFF_NULCEST + MAXK;
+constexpr int OFF_EXB = OFF_EXXC + 104;
+constexpr int OFF_XS = OFF_EXB + 104;
+constexpr int OFF_RED = OFF_XS + 32;
+constexpr int OFF_INT = OFF_RED + 128;        // ints: nicnact[72], cstatus[104], isfree[104], iscr[8]
+constexpr int TOTAL = OFF_INT + (72 + 104 + 104 + 8) / 2;
+constexpr int BYTES = TOTAL * 8;
+}  // namespace sscr
+
+__device__ __forceinline__ Work carve_work(double* sm, double* gl)
 {
     Work w;
-    w.A = p + scratch::OFF_A; w.b = p + scratch::OFF_B; w.s = p + scratch::OFF_S; w.C = p + scratch::OFF_C;
-    w.nicerr = p + scratch::OFF_NICERR; w.nulc = p + scratch::OFF_NULC; w.nulcest = p + scratch::OFF_NULCEST;
-    w.exxc = p + scratch::OFF_EXXC; w.exb = p + scratch::OFF_EXB;
-    double* v = p + scratch::OFF_VEC;
-    w.xc = v; w.xp = v + MAXNT; w.xf = v + 2 * MAXNT; w.gc = v + 3 * MAXNT; w.cgc = v + 4 * MAXNT; w.cgp = v + 5 * MAXNT;
-    w.dc = v + 6 * MAXNT; w.dp = v + 7 * MAXNT; w.tmp0 = v + 8 * MAXNT; w.tmp1 = v + 9 * MAXNT; w.regdiag = v + 10 * MAXNT;
-    w.bufr = v + 11 * MAXNT;
-    w.qrv = p + scratch::OFF_QRV; w.sv0 = p + scratch::OFF_SV0;
-    int* ip = reinterpret_cast<int*>(p + scratch::OFF_INT);
-    w.nicnact = ip; w.cstatus = ip + MAXNIC; w.isfree = ip + MAXNIC + MAXNT;
-    w.exa = p + scratch::OFF_EXA; w.z = p + scratch::OFF_Z; w.kkt = p + scratch::OFF_KKT;
+    w.SA = gl + gscr::OFF_SA; w.Sgl = gl + gscr::OFF_SGL; w.vgl = gl + gscr::OFF_VGL; w.qrv = gl + gscr::OFF_QRV;
+    w.sv0 = gl + gscr::OFF_SV0; w.kkt = gl + gscr::OFF_KKT;
+    w.Ssh = sm + sscr::OFF_S; w.vsh = sm + sscr::OFF_V; w.C = sm + sscr::OFF_C; w.larinv = sm + sscr::OFF_LARINV;
+    w.ladiag = sm + sscr::OFF_LADIAG; w.b = sm + sscr::OFF_B; w.s = sm + sscr::OFF_SC; w.nicerr = sm + sscr::OFF_NICERR;
+    w.nulc = sm + sscr::OFF_NULC; w.nulcest = sm + sscr::OFF_NULCEST; w.exxc = sm + sscr::OFF_EXXC; w.exb = sm + sscr::OFF_EXB;
+    w.xs = sm + sscr::OFF_XS;
+    int* ip = reinterpret_cast<int*>(sm + sscr::OFF_INT);
+    w.nicnact = ip; w.cstatus = ip + 72; w.isfree = ip + 72 + 104; w.iscr = ip + 72 + 104 + 104;
     return w;
 }
 
 // ------------------------------------------------------------------------------------------------
 // kernels
-__global__ void __launch_bounds__(128) wbc_front_kernel(Params P, DevInputs in, FrontState st, int n, double* __restrict__ recs,
-                                                        double* __restrict__ w_out, long w_ld, DevDebug dbg, int has_dbg)
+__global__ void __launch_bounds__(64) wbc_front_kernel(Params P, DevInputs in, FrontState st, int n, double* __restrict__ recs,
+                                                       double* __restrict__ w_out, long w_ld, DevDebug dbg, int has_dbg)
 {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -90,59 +101,70 @@ __device__ __forceinline__ void write_info(const Stats& st, long i, long ld, int
     if (flops) flops[i] = st.flops;
 }
 
-__global__ void __launch_bounds__(256) wbc_solve_kernel(Params P, int n, const double* __restrict__ recs, SolveOut out,
-                                                        double* __restrict__ scratch_base, int* __restrict__ queue)
+__device__ __forceinline__ int next_instance(int* queue, int* slot)
 {
-    const WarpEx ex;
-    const int warps_per_block = blockDim.x >> 5;
-    const long wslot = (long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
-    const Work w = carve_work(scratch_base + wslot * scratch::TOTAL);
-    double* xs = scratch_base + wslot * scratch::TOTAL + scratch::OFF_X;
+    if (threadIdx.x == 0) *slot = atomicAdd(queue, 1);
+    __syncthreads();
+    const int i = *slot;
+    __syncthreads();
+    return i;
+}
+
+__global__ void __launch_bounds__(SOLVE_T, SOLVE_CTAS_PER_SM)
+wbc_solve_kernel(Params P, int n, const double* __restrict__ recs, SolveOut out, double* __restrict__ scratch_base, int* __restrict__ queue)
+{
+    extern __shared__ __align__(16) double sm[];
+    __shared__ int s_next;
+    const Work w = carve_work(sm, scratch_base + (long)blockIdx.x * gscr::TOTAL);
+    TeamEx<SOLVE_T> ex;
+    ex.red = sm + sscr::OFF_RED; ex.par = 0;
     Settings cfg;
-    cfg.epsx = P.qp_epsx; cfg.rho = P.qp_rho; cfg.outerits = P.qp_outerits; cfg.kkt_mode = 0;
+    cfg.epsx = P.qp_epsx; cfg.rho = P.qp_rho; cfg.outerits = P.qp_outerits; cfg.kkt_mode = P.reserved == 1 ? 0 : 1;
     for (;;) {
-        int i = 0;
-        if (ex.lane() == 0) i = atomicAdd(queue, 1);
-        i = __shfl_sync(0xffffffffu, i, 0);
+        const int i = next_instance(queue, &s_next);
         if (i >= n) break;
         const double* rec = recs + (long)i * QPREC_DOUBLES;
         const QpShape sh = qp_shape((int)rec[QR_MODE]);
-        // Q -> w.z, c -> w.exb, L -> w.C (scaled in place by the solver)
-        assemble_qp(ex, P, rec, sh, w.z, w.exb, w.C);
+        // Q -> w.Ssh[0..900), c -> w.exb, L -> w.C (scaled in place by the solver)
+        assemble_qp(ex, P, rec, sh, w.Ssh, w.exb, w.C);
         Stats st;
-        solve_denseaul(ex, w, cfg, w.z, 1, w.exb, 1, w.C, 1, sh.nrows, sh.neq, xs, 1, st);
+        solve_denseaul(ex, w, cfg, sh.nrows, sh.neq, st);
         if (st.termination != 2) {
-            for (int k = ex.lane(); k < 30; k += 32) xs[k] = 0.0;
-            __syncwarp();
+            for (int k = ex.lane(); k < 30; k += SOLVE_T) w.xs[k] = 0.0;
+            ex.sync();
         }
-        torque_and_objective(ex, P, rec, sh, xs, out.tau + i, out.ld, out.qp_obj ? out.qp_obj + i : nullptr);
+        torque_and_objective(ex, P, rec, sh, w.xs, out.tau + i, out.ld, out.qp_obj ? out.qp_obj + i : nullptr);
         if (out.x)
-            for (int k = ex.lane(); k < 30; k += 32) out.x[(long)k * out.ld + i] = xs[k];
+            for (int k = ex.lane(); k < 30; k += SOLVE_T) out.x[(long)k * out.ld + i] = w.xs[k];
         if (ex.lane() == 0) write_info(st, i, out.ld, out.status, out.qp_info, out.qp_flops);
-        __syncwarp();
+        ex.sync();
     }
 }
 
 // OPT-operator path: dense, instance-major (Q [n][900], c [n][30], L [n][nrows*31], x [n][30]).
-__global__ void __launch_bounds__(256) wbc_dense_qp_kernel(Params P, int n, const double* __restrict__ Q, const double* __restrict__ c,
-                                                           const double* __restrict__ L, int nrows, int neq, double* __restrict__ x,
-                                                           int* status, int* info, double* flops, double* __restrict__ scratch_base,
-                                                           int* __restrict__ queue)
+__global__ void __launch_bounds__(SOLVE_T, SOLVE_CTAS_PER_SM)
+wbc_dense_qp_kernel(Params P, int n, const double* __restrict__ Q, const double* __restrict__ c, const double* __restrict__ L, int nrows,
+                    int neq, double* __restrict__ x, int* status, int* info, double* flops, double* __restrict__ scratch_base,
+                    int* __restrict__ queue)
 {
-    const WarpEx ex;
-    const int warps_per_block = blockDim.x >> 5;
-    const long wslot = (long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
-    const Work w = carve_work(scratch_base + wslot * scratch::TOTAL);
+    extern __shared__ __align__(16) double sm[];
+    __shared__ int s_next;
+    const Work w = carve_work(sm, scratch_base + (long)blockIdx.x * gscr::TOTAL);
+    TeamEx<SOLVE_T> ex;
+    ex.red = sm + sscr::OFF_RED; ex.par = 0;
     Settings cfg;
-    cfg.epsx = P.qp_epsx; cfg.rho = P.qp_rho; cfg.outerits = P.qp_outerits; cfg.kkt_mode = 0;
+    cfg.epsx = P.qp_epsx; cfg.rho = P.qp_rho; cfg.outerits = P.qp_outerits; cfg.kkt_mode = P.reserved == 1 ? 0 : 1;
     for (;;) {
-        int i = 0;
-        if (ex.lane() == 0) i = atomicAdd(queue, 1);
-        i = __shfl_sync(0xffffffffu, i, 0);
+        const int i = next_instance(queue, &s_next);
         if (i >= n) break;
+        for (int k = ex.lane(); k < 900; k += SOLVE_T) w.Ssh[k] = Q[(long)i * 900 + k];
+        for (int k = ex.lane(); k < 30; k += SOLVE_T) w.exb[k] = c[(long)i * 30 + k];
+        for (int k = ex.lane(); k < nrows * 31; k += SOLVE_T) w.C[k] = L[(long)i * nrows * 31 + k];
+        ex.sync();
         Stats st;
-        solve_denseaul(ex, w, cfg, Q + (long)i * 900, 1, c + (long)i * 30, 1, L + (long)i * nrows * 31, 1, nrows, neq,
-                       x + (long)i * 30, 1, st);
+        solve_denseaul(ex, w, cfg, nrows, neq, st);
+        if (st.termination == 2)
+            for (int k = ex.lane(); k < 30; k += SOLVE_T) x[(long)i * 30 + k] = w.xs[k];
         if (ex.lane() == 0) {   // instance-major info [n][8] on this path
             write_info(st, i, n, status, nullptr, flops);
             if (info) {
@@ -151,7 +173,7 @@ __global__ void __launch_bounds__(256) wbc_dense_qp_kernel(Params P, int n, cons
                 q[5] = st.flags; q[6] = 0; q[7] = 0;
             }
         }
-        __syncwarp();
+        ex.sync();
     }
 }
 
@@ -202,7 +224,7 @@ struct wbc_ctx {
     double* yd;          // [6][max_batch]
     double* yw;
     double* w_dev;       // [6][max_batch] (when the caller passes no w)
-    double* scratch;     // [nwarps][scratch::TOTAL]
+    double* scratch;     // [nblocks][gscr::TOTAL]
     int* queue;          // work-queue counter
     int nblocks, threads;   // solver launch shape
     // staging for WBC_HOST_PTRS
@@ -269,9 +291,9 @@ int wbc_create(wbc_ctx** out, int device, int max_batch, const wbc_params* param
     wbc_default_params(&def);
     memcpy(&c->params, params ? params : &def, sizeof(Params));
     const size_t nb = (size_t)max_batch;
-    c->threads = 256;
-    c->nblocks = c->sm_count * 2;
-    const long nwarps = (long)c->nblocks * (c->threads / 32);
+    c->threads = SOLVE_T;
+    c->nblocks = c->sm_count * SOLVE_CTAS_PER_SM;
+    const long nteams = c->nblocks;
     cudaError_t e = cudaSuccess;
 #define TRY(call) if (e == cudaSuccess) e = (call)
     TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -280,7 +302,7 @@ int wbc_create(wbc_ctx** out, int device, int max_batch, const wbc_params* param
     TRY(cudaMalloc(&c->yd, nb * 6 * sizeof(double)));
     TRY(cudaMalloc(&c->yw, nb * 6 * sizeof(double)));
     TRY(cudaMalloc(&c->w_dev, nb * 6 * sizeof(double)));
-    TRY(cudaMalloc(&c->scratch, (size_t)nwarps * scratch::TOTAL * sizeof(double)));
+    TRY(cudaMalloc(&c->scratch, (size_t)nteams * gscr::TOTAL * sizeof(double)));
     TRY(cudaMalloc(&c->queue, 64));
     TRY(cudaMalloc(&c->d_in, nb * (kInDoublesNoTerrain + 40) * sizeof(double)));
     TRY(cudaMalloc(&c->d_out, nb * kOutDoubles * sizeof(double)));
@@ -290,7 +312,9 @@ int wbc_create(wbc_ctx** out, int device, int max_batch, const wbc_params* param
     TRY(cudaMallocHost(&c->h_pin_i, nb * kOutInts * sizeof(int)));
     TRY(cudaMemset(c->yd, 0, nb * 6 * sizeof(double)));
     TRY(cudaMemset(c->yw, 0, nb * 6 * sizeof(double)));
-    TRY(cudaMemset(c->scratch, 0, (size_t)nwarps * scratch::TOTAL * sizeof(double)));
+    TRY(cudaMemset(c->scratch, 0, (size_t)nteams * gscr::TOTAL * sizeof(double)));
+    TRY(cudaFuncSetAttribute(wbc_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sscr::BYTES));
+    TRY(cudaFuncSetAttribute(wbc_dense_qp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sscr::BYTES));
 #undef TRY
     if (e != cudaSuccess) {
         fail(e == cudaErrorMemoryAllocation ? WBC_ENOMEM : WBC_ECUDA, "wbc_create: %s", cudaGetErrorString(e));
@@ -328,6 +352,13 @@ int wbc_get_observer_state(wbc_ctx* c, int n, double* yd, double* yw, long ld)
     CU(cudaMemcpy2D(yd, (size_t)ld * 8, c->yd, (size_t)c->max_batch * 8, (size_t)n * 8, 6, cudaMemcpyDeviceToHost));
     CU(cudaMemcpy2D(yw, (size_t)ld * 8, c->yw, (size_t)c->max_batch * 8, (size_t)n * 8, 6, cudaMemcpyDeviceToHost));
     return WBC_OK;
+}
+
+// Front kernel block size: small batches use small blocks so that every SM gets work.
+static int front_threads(const wbc_ctx* c, int n)
+{
+    if (n >= c->sm_count * 64 * 4) return 64;
+    return 32;
 }
 
 static int check_inputs(const wbc_inputs* in, int n)
@@ -408,13 +439,11 @@ int wbc_cycle(wbc_ctx* c, int n, const wbc_inputs* in, const wbc_outputs* out, v
     memset(&nodbg, 0, sizeof(nodbg));
     CU(cudaMemsetAsync(c->queue, 0, sizeof(int), s));
     CU(cudaEventRecord(c->ev0, s));
-    wbc_front_kernel<<<(n + 127) / 128, 128, 0, s>>>(c->params, din, st, n, c->recs, w_ptr, w_ld, nodbg, 0);
+    const int fthreads = front_threads(c, n);
+    wbc_front_kernel<<<(n + fthreads - 1) / fthreads, fthreads, 0, s>>>(c->params, din, st, n, c->recs, w_ptr, w_ld, nodbg, 0);
     CU(cudaEventRecord(c->ev1, s));
-    const int nwarps_needed = n;
-    int nblocks = c->nblocks;
-    const int wpb = c->threads / 32;
-    if ((long)nblocks * wpb > nwarps_needed) nblocks = (nwarps_needed + wpb - 1) / wpb;
-    wbc_solve_kernel<<<nblocks, c->threads, 0, s>>>(c->params, n, c->recs, so, c->scratch, c->queue);
+    const int nblocks = n < c->nblocks ? n : c->nblocks;
+    wbc_solve_kernel<<<nblocks, c->threads, sscr::BYTES, s>>>(c->params, n, c->recs, so, c->scratch, c->queue);
     CU(cudaEventRecord(c->ev2, s));
     CU(cudaGetLastError());
     c->launches = 2;
@@ -486,7 +515,8 @@ int wbc_debug_update(wbc_ctx* c, int n, const wbc_inputs* in, const wbc_debug* d
     cudaMemsetAsync(ytmp, 0, (size_t)12 * n * sizeof(double), s);
     FrontState st;
     st.yd = ytmp; st.yw = ytmp + 6L * n; st.ld = n;
-    wbc_front_kernel<<<(n + 127) / 128, 128, 0, s>>>(c->params, din, st, n, c->recs, c->w_dev, c->max_batch, dd, 1);
+    const int fthreads = front_threads(c, n);
+    wbc_front_kernel<<<(n + fthreads - 1) / fthreads, fthreads, 0, s>>>(c->params, din, st, n, c->recs, c->w_dev, c->max_batch, dd, 1);
     e = cudaStreamSynchronize(s);
     if (e == cudaSuccess) e = cudaGetLastError();
     off = 0;
@@ -538,12 +568,10 @@ int wbc_qp_solve(wbc_ctx* c, int n, const double* Q, const double* cvec, const d
         dinfo = info ? ip + n : nullptr;
     }
     CU(cudaMemsetAsync(c->queue, 0, sizeof(int), s));
-    int nblocks = c->nblocks;
-    const int wpb = c->threads / 32;
-    if ((long)nblocks * wpb > n) nblocks = (n + wpb - 1) / wpb;
+    const int nblocks = n < c->nblocks ? n : c->nblocks;
     CU(cudaEventRecord(c->ev0, s));
     CU(cudaEventRecord(c->ev1, s));
-    wbc_dense_qp_kernel<<<nblocks, c->threads, 0, s>>>(c->params, n, dQ, dc, dL, nrows, neq, dx, dstatus, dinfo, dflops, c->scratch, c->queue);
+    wbc_dense_qp_kernel<<<nblocks, c->threads, sscr::BYTES, s>>>(c->params, n, dQ, dc, dL, nrows, neq, dx, dstatus, dinfo, dflops, c->scratch, c->queue);
     CU(cudaEventRecord(c->ev2, s));
     CU(cudaGetLastError());
     c->launches = 1;
