@@ -68,7 +68,7 @@ typedef struct wbc_params {
     int qp_outerits;          /* 5                 lopt.cpp:101, 138  */
     int observer_enabled;     /* 1: call estimate() at main.cpp:1029/1220/1569/1767 (reference ships 0) */
     int fix_swing_rhs;        /* 0: keep the reference's zero swing-equality rhs (main.cpp:1238-1241) */
-    int reserved;
+    int qp_literal_kkt;       /* 0 (default): reduced multiplier update with the literal form as fallback; 1: always the literal stacked-KKT QR (opt.cpp:41803-42032) */
 } wbc_params;
 
 /* One control cycle's inputs for n instances (what update() receives plus the members it reads). */

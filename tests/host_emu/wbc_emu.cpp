@@ -1,5 +1,5 @@
 // TEST-ONLY host emulation of the device control-cycle path: compiles the product headers
-// (wbc_front.cuh, wbc_assemble.cuh, qp_team.cuh) with g++ and the single-lane `HostEx` executor so
+// (wbc_front.cuh, wbc_assemble.cuh, qp_warp.cuh) with g++ and the single-lane `HostEx` executor so
 // that the device code's arithmetic and decisions can be unit-tested on a machine without a GPU
 // (`pytest -m "not gpu"`).  It is NOT linked into libwbc_b200.so and never used by bench.py or by the
 // product path; GPU parity tests call the CUDA kernels through the C ABI instead.
@@ -48,11 +48,11 @@ int emu_cycle(const Params* P, const EmuIO* io, int n)
         front_cycle(*P, in, st, i, rec.data(), io->w, io->ld, nullptr);
         if (io->rec) memcpy(io->rec + i * QPREC_DOUBLES, rec.data(), sizeof(double) * QPREC_DOUBLES);
         const QpShape sh = qp_shape((int)rec[QR_MODE]);
-        assemble_qp(ex, *P, rec.data(), sh, ew.w.Ssh, ew.w.exb, ew.w.C);
+        assemble_qp<LDH>(ex, *P, rec.data(), sh, W_H(ew.w), W_EXB(ew.w), W_C(ew.w));
         Stats s;
         double xs[30];
         solve_denseaul(ex, ew.w, cfg, sh.nrows, sh.neq, s);
-        memcpy(xs, ew.w.xs, sizeof(xs));
+        memcpy(xs, W_XS(ew.w), sizeof(xs));
         if (s.termination != 2) memset(xs, 0, sizeof(xs));
         torque_and_objective(ex, *P, rec.data(), sh, xs, io->tau + i, io->ld, io->qp_obj ? io->qp_obj + i : nullptr);
         if (io->x) for (int k = 0; k < 30; k++) io->x[k * io->ld + i] = xs[k];
@@ -70,7 +70,7 @@ int emu_assemble(const Params* P, const double* rec, double* Q, double* c, doubl
 {
     HostEx ex;
     const QpShape sh = qp_shape((int)rec[QR_MODE]);
-    assemble_qp(ex, *P, rec, sh, Q, c, L);
+    assemble_qp<30>(ex, *P, rec, sh, Q, c, L);
     *nrows = sh.nrows; *neq = sh.neq;
     return 0;
 }

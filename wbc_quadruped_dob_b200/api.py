@@ -39,7 +39,7 @@ class Params(C.Structure):
                 ("kcom", "dcom", "q1_weight", "slack_weight", "mu", "tau_max", "joint_dt", "kp_sw", "kd_sw", "g_acc",
                  "obs_gain", "obs_dt")] + [("gravity", C.c_double * 3), ("qp_epsx", C.c_double), ("qp_rho", C.c_double),
                                            ("qp_outerits", C.c_int), ("observer_enabled", C.c_int),
-                                           ("fix_swing_rhs", C.c_int), ("reserved", C.c_int)]
+                                           ("fix_swing_rhs", C.c_int), ("qp_literal_kkt", C.c_int)]
 
 
 class _Inputs(C.Structure):

@@ -1,0 +1,561 @@
+// Device-only fast path of the QQP inner solver (opt.cpp:29675-30566) for the shared-memory case
+// (nic <= NICCAP): same decisions and arithmetic as qqp_optimize<false> in qp_warp.cuh, re-expressed for
+// a single warp so that it issues few instructions and few branches (the warp runs almost alone on its
+// scheduler, so every taken branch and every dependent instruction is exposed latency):
+//   * every QQP vector lives in registers in a two-slot form: slot A = main variable `lane` (lanes 0..29),
+//     slot B = slack variable 30 + `lane` (lanes 0..nic-1); only vectors that are multiplied by E are
+//     mirrored to shared memory (for the broadcast reads of the products);
+//   * the products with E = [H, CI'; CI, rho I] are straight-line code over the 30 main columns, with
+//     128-bit loads of the vector, four independent accumulation chains, and no predicates on loads (out-of-
+//     range lanes read finite in-bounds values and drop the result);
+//   * the constrained-Newton factorisation handles two columns per step on the packed factor with 128-bit
+//     loads; triangular solves keep the running right-hand side in registers.
+// Included by qp_warp.cuh; uses its layout constants.
+#pragma once
+#if defined(__CUDACC__)
+
+namespace wbcqp {
+namespace fast {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ double bshfl(double v, int src) { return __shfl_sync(FULL, v, src); }
+__device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+
+// y = E x for the vector mirrored at `x` (shared, 16-byte aligned, entries >= n finite).  Returns slot A / slot B parts.
+// nic2 = nic rounded up to even; rows [nic, nic2) of CI are zero.
+__device__ __noinline__ double2 symv(const double* __restrict__ x, int nic2, double rho)
+{
+    const int l = threadIdx.x & 31;
+    const double* H = wbc_smem + sl::OFF_H + l;             // column walk of row l (H symmetric)
+    const double* Crow = wbc_smem + sl::OFF_CI + l * LDH;   // slack row l
+    const double* Ccol = wbc_smem + sl::OFF_CI + l;         // column l of the slack rows
+    double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+#pragma unroll
+    for (int j = 0; j < NMAIN; j += 2) {
+        const double2 xv = ld2(x + j);
+        a0 += H[j * LDH] * xv.x;
+        a1 += H[(j + 1) * LDH] * xv.y;
+        b0 += Crow[j] * xv.x;
+        b1 += Crow[j + 1] * xv.y;
+    }
+#pragma unroll 1
+    for (int k = 0; k < nic2; k += 2) {
+        const double2 xv = ld2(x + NMAIN + k);
+        a0 += Ccol[k * LDH] * xv.x;
+        a1 += Ccol[(k + 1) * LDH] * xv.y;
+    }
+    double2 r;
+    r.x = a0 + a1;
+    r.y = (b0 + b1) + rho * x[NMAIN + l];
+    return r;
+}
+
+// f_k = exb . t_k + 0.5 t_k . (E t_k) for the four projected points t_k = P(xc + s_k d) (opt.cpp:30582-30652).
+// xc, d, exb in two-slot registers.  Results to V_SPARE[0..3] (shared) -- every lane also returns them in f[].
+__device__ __noinline__ void eval4(double xcA, double xcB, double dA, double dB, double exbA, double exbB, int nic, double rho, double s0,
+                                  double s1, double s2, double s3)
+{
+    const int l = threadIdx.x & 31;
+    const int nic2 = (nic + 1) & ~1;
+    double* t4 = wbc_smem + sl::OFF_V + V_T0 * VLS;          // [48][4] interleaved candidates (T0..T3 are contiguous)
+    const bool vA = l < NMAIN, vB = l < nic;
+    double tA[4], tB[4];
+    const double s[4] = {s0, s1, s2, s3};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        tA[k] = (s[k] != 0.0) ? xcA + s[k] * dA : xcA;
+        double v = (s[k] != 0.0) ? xcB + s[k] * dB : xcB;
+        if (v < 0.0) v = 0.0;
+        tB[k] = vB ? v : 0.0;
+        if (!vA) tA[k] = 0.0;
+    }
+    if (vA) {
+        *reinterpret_cast<double2*>(t4 + l * 4) = make_double2(tA[0], tA[1]);
+        *reinterpret_cast<double2*>(t4 + l * 4 + 2) = make_double2(tA[2], tA[3]);
+    }
+    if (l < nic2) {      // includes the zero pad entry when nic is odd
+        *reinterpret_cast<double2*>(t4 + (NMAIN + l) * 4) = make_double2(tB[0], tB[1]);
+        *reinterpret_cast<double2*>(t4 + (NMAIN + l) * 4 + 2) = make_double2(tB[2], tB[3]);
+    }
+    __syncwarp();
+    const double* H = wbc_smem + sl::OFF_H + l;
+    const double* Crow = wbc_smem + sl::OFF_CI + l * LDH;
+    const double* Ccol = wbc_smem + sl::OFF_CI + l;
+    double a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
+#pragma unroll 6
+    for (int j = 0; j < NMAIN; j++) {
+        const double2 t01 = ld2(t4 + j * 4), t23 = ld2(t4 + j * 4 + 2);
+        const double h = H[j * LDH], c = Crow[j];
+        a[0] += h * t01.x; a[1] += h * t01.y; a[2] += h * t23.x; a[3] += h * t23.y;
+        b[0] += c * t01.x; b[1] += c * t01.y; b[2] += c * t23.x; b[3] += c * t23.y;
+    }
+#pragma unroll 1
+    for (int k = 0; k < nic2; k++) {
+        const double2 t01 = ld2(t4 + (NMAIN + k) * 4), t23 = ld2(t4 + (NMAIN + k) * 4 + 2);
+        const double c = Ccol[k * LDH];
+        a[0] += c * t01.x; a[1] += c * t01.y; a[2] += c * t23.x; a[3] += c * t23.y;
+    }
+    double r8[8];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const double eb = b[k] + rho * tB[k];
+        r8[k] = exbA * tA[k] + exbB * tB[k];                 // tA / tB are zero on invalid lanes
+        r8[4 + k] = tA[k] * a[k] + tB[k] * eb;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) r8[k] += __shfl_xor_sync(FULL, r8[k], o);
+    }
+    __syncwarp();
+    if (l < 4) wbc_smem[sl::OFF_V + V_SPARE * VLS + l] = (l == 0 ? r8[0] + 0.5 * r8[4] : l == 1 ? r8[1] + 0.5 * r8[5] : l == 2 ? r8[2] + 0.5 * r8[6] : r8[3] + 0.5 * r8[7]);
+    __syncwarp();
+}
+
+// Cholesky of the masked, regularised E into the packed factor (see chol_cols in qp_warp.cuh for the layout),
+// two columns per step.  Row c of the factor is owned by lane c & 31 (slot c >> 5).  diagA / diagB: the diagonal
+// E_ii + regulariser (1 for a fixed variable) in two-slot form; freeB: slack variable 30 + lane is free.
+// Returns false on a non-positive pivot.
+__device__ __noinline__ bool chol_build(int n, double diagA, double diagB, int freeB)
+{
+    const int l = threadIdx.x & 31;
+    double* Z = wbc_smem + sl::OFF_Z;
+    double* zd = wbc_smem + sl::OFF_V + V_ZD * VLS;
+    double* zrinv = wbc_smem + sl::OFF_V + V_ZRINV * VLS;
+    const double* H = wbc_smem + sl::OFF_H;
+    const double* CI = wbc_smem + sl::OFF_CI;
+    // rows: c0 = l, c1 = l + 32.  a(k, c) for a main column k < 30:
+    //   c < 30: H[k][c];  c >= 30: free(c) * CI[c-30][k]
+    const int c0 = l, c1 = l + 32;
+    const double* src0 = (c0 < NMAIN) ? H + c0 : CI + (c0 - NMAIN) * LDH;
+    const int str0 = (c0 < NMAIN) ? LDH : 1;
+    const double* src1 = CI + (c1 - NMAIN) * LDH;
+    // the free flags and diagonals of rows c0 / c1 come from the two-slot registers of other lanes
+    const int f30 = __shfl_sync(FULL, freeB, 0), f31 = __shfl_sync(FULL, freeB, 1);
+    const int fB1 = __shfl_sync(FULL, freeB, (l + 2) & 31);           // slack index of row c1 = l + 2
+    const double m0 = (c0 < NMAIN) ? 1.0 : ((c0 == NMAIN ? f30 : f31) ? 1.0 : 0.0);
+    const double m1 = (c1 < n && fB1) ? 1.0 : 0.0;
+    const double dg30 = bshfl(diagB, 0), dg31 = bshfl(diagB, 1);
+    const double dgB1 = bshfl(diagB, (l + 2) & 31);
+    const double dg0 = (c0 < NMAIN) ? diagA : (c0 == NMAIN ? dg30 : dg31);
+    const double dg1 = dgB1;
+    double* r0 = Z + zoff(c0);
+    double* r1 = Z + zoff(c1 < n ? c1 : 0);
+    const bool has1 = n > 32;
+    for (int k = 0; k < n; k += 2) {
+        const bool two = (k + 1 < n);
+        const double* rk = Z + zoff(k);
+        const double* rk1 = Z + zoff(two ? k + 1 : k);
+        // dots over m < k (k even: whole pairs)
+        double p00 = 0.0, p01 = 0.0, p10 = 0.0, p11 = 0.0;     // [slot][column]
+        double q00 = 0.0, q01 = 0.0, q10 = 0.0, q11 = 0.0;
+#pragma unroll 2
+        for (int m = 0; m < k; m += 2) {
+            const double2 zk = ld2(rk + m), zk1 = ld2(rk1 + m);
+            const double2 z0 = ld2(r0 + m);
+            p00 += z0.x * zk.x; q00 += z0.y * zk.y;
+            p01 += z0.x * zk1.x; q01 += z0.y * zk1.y;
+            if (has1) {
+                const double2 z1 = ld2(r1 + m);
+                p10 += z1.x * zk.x; q10 += z1.y * zk.y;
+                p11 += z1.x * zk1.x; q11 += z1.y * zk1.y;
+            }
+        }
+        // matrix entries of the two columns
+        double a00, a01, a10, a11;
+        if (k < NMAIN) {        // k even, so k + 1 < 30 too
+            a00 = src0[k * str0] * m0; a01 = src0[(k + 1) * str0] * m0;
+            a10 = has1 ? src1[k] * m1 : 0.0; a11 = has1 ? src1[k + 1] * m1 : 0.0;
+        } else { a00 = a01 = a10 = a11 = 0.0; }
+        if (c0 == k) a00 = dg0;
+        if (c0 == k + 1) a01 = dg0;
+        if (c1 == k) a10 = dg1;
+        if (c1 == k + 1) a11 = dg1;
+        double v00 = a00 - (p00 + q00), v01 = a01 - (p01 + q01);
+        double v10 = a10 - (p10 + q10), v11 = a11 - (p11 + q11);
+        // column k
+        const double piv0 = bshfl((k < 32) ? v00 : v10, k & 31);
+        if (!(piv0 > 0.0)) return false;
+        const double ri0 = rsqrt(piv0);
+        const double z0k = v00 * ri0, z1k = v10 * ri0;          // meaningful for rows c > k
+        if (c0 > k && c0 < n) r0[k] = z0k;
+        if (has1 && c1 > k && c1 < n) r1[k] = z1k;
+        if (l == 0) { zd[k] = piv0 * ri0; zrinv[k] = ri0; }
+        if (two) {
+            // column k + 1: subtract the contribution of column k
+            const double zk1k = bshfl(((k + 1) < 32) ? z0k : z1k, (k + 1) & 31);
+            v01 -= z0k * zk1k;
+            v11 -= z1k * zk1k;
+            const double piv1 = bshfl(((k + 1) < 32) ? v01 : v11, (k + 1) & 31);
+            if (!(piv1 > 0.0)) return false;
+            const double ri1 = rsqrt(piv1);
+            if (c0 > k + 1 && c0 < n) r0[k + 1] = v01 * ri1;
+            if (has1 && c1 > k + 1 && c1 < n) r1[k + 1] = v11 * ri1;
+            if (l == 0) { zd[k + 1] = piv1 * ri1; zrinv[k + 1] = ri1; }
+        }
+        __syncwarp();
+    }
+    return true;
+}
+
+// Solve U'U x = rhs with the packed factor; rhs and result in shared memory at `x` (index = variable).
+__device__ __noinline__ void tri_solve(double* x, int n)
+{
+    const int l = threadIdx.x & 31;
+    const double* Z = wbc_smem + sl::OFF_Z;
+    const double* zrinv = wbc_smem + sl::OFF_V + V_ZRINV * VLS;
+    const int c0 = l, c1 = l + 32;
+    const double* r0 = Z + zoff(c0);
+    const double* r1 = Z + zoff(c1 < n ? c1 : 0);
+    double x0 = (c0 < n) ? x[c0] : 0.0, x1 = (c1 < n) ? x[c1] : 0.0;
+    double y0 = 0.0, y1 = 0.0;
+    // forward: U' y = rhs, column oriented
+#pragma unroll 2
+    for (int k = 0; k < n; k++) {
+        const double yk = bshfl((k < 32) ? x0 : x1, k & 31) * zrinv[k];
+        if (c0 == k) y0 = yk;
+        if (c1 == k) y1 = yk;
+        if (c0 > k && c0 < n) x0 -= r0[k] * yk;
+        if (c1 > k && c1 < n) x1 -= r1[k] * yk;
+    }
+    // backward: U x = y
+#pragma unroll 2
+    for (int k = n - 1; k >= 0; k--) {
+        const double xk = bshfl((k < 32) ? y0 : y1, k & 31) * zrinv[k];
+        const double* rk = Z + zoff(k);
+        if (c0 == k) y0 = xk;
+        if (c1 == k) y1 = xk;
+        if (c0 < k) y0 -= rk[c0] * xk;
+        if (c1 < k) y1 -= rk[c1] * xk;
+    }
+    __syncwarp();
+    if (c0 < n) x[c0] = y0;
+    if (c1 < n) x[c1] = y1;
+    __syncwarp();
+}
+
+__device__ __noinline__ void givens_fix(int n, int k)
+{
+    givens_fix_regs<2>(WarpEx(), wbc_smem + sl::OFF_Z, wbc_smem + sl::OFF_V + V_ZD * VLS, wbc_smem + sl::OFF_V + V_ZRINV * VLS, n, k);
+}
+
+__device__ __forceinline__ void red3(double& a, double& b, double& c)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(FULL, a, o);
+        b += __shfl_xor_sync(FULL, b, o);
+        c += __shfl_xor_sync(FULL, c, o);
+    }
+}
+__device__ __forceinline__ double red1(double a)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(FULL, a, o);
+    return a;
+}
+
+// qqpsolver_quadraticmodel (opt.cpp:30753-30821) on two-slot registers.  d is mirrored at V_DC.  Returns the packed sign
+// estimates (see estimateparabolicmodel); d1, d2 by reference (inlined).
+__device__ __forceinline__ int quadratic_model(double dA, double dB, double gA, double gB, double xcA, double xcB, int nic2, double rho,
+                                               double absasum, double absasum2, double mb, double& d1, double& d2)
+{
+    const double2 ed = symv(wbc_smem + sl::OFF_V + V_DC * VLS, nic2, rho);
+    double s0 = dA * ed.x + dB * ed.y;       // invalid lanes carry d = 0
+    double s1 = dA * gA + dB * gB;
+    double m0 = fmax(fabs(xcA), fabs(xcB)), m1 = fmax(fabs(dA), fabs(dB));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s0 += __shfl_xor_sync(FULL, s0, o);
+        s1 += __shfl_xor_sync(FULL, s1, o);
+        m0 = fmax(m0, __shfl_xor_sync(FULL, m0, o));
+        m1 = fmax(m1, __shfl_xor_sync(FULL, m1, o));
+    }
+    d2 = 0.5 * s0; d1 = s1;
+    return estimateparabolicmodel(absasum, absasum2, m0, mb, m1, d1, d2);
+}
+
+// sasexploredirection (opt.cpp:27433-27528) on slot B registers (see sas_explore_direction in qp_warp.cuh).
+__device__ __forceinline__ void explore(double xcB, double dB, bool candB, double& stpmax, int& cidx)
+{
+    const int l = threadIdx.x & 31;
+    double best = BIGSTEP;
+    int bi = 0x7fffffff;
+    if (candB && dB < 0.0) {
+        best = safeminposrv(xcB - 0.0, -dB, BIGSTEP);
+        if (best < BIGSTEP) bi = NMAIN + l; else bi = 0x7fffffff;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(FULL, best, o);
+        const int oi = __shfl_xor_sync(FULL, bi, o);
+        if (ov < best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    stpmax = best;
+    cidx = (best < BIGSTEP) ? bi : -1;
+}
+
+// qqpsolver_findbeststepandmove (opt.cpp:30882-31003) + sasmoveto (27574-27723) on two-slot registers.
+// csB: cstatus of slot B (updated).  Mirrors the new point to V_XC.
+__device__ __forceinline__ void best_step_and_move(double& xcA, double& xcB, int& csB, double dA, double dB, double exbA, double exbB, int nic,
+                                                   double rho, double stp, bool needact, int cidx, double cval, double a0, double a1, double a2,
+                                                   int addcnt)
+{
+    const int l = threadIdx.x & 31;
+    double stpbest = stp;
+    if (addcnt > 0) {
+        eval4(xcA, xcB, dA, dB, exbA, exbB, nic, rho, stp, a0, addcnt > 1 ? a1 : a0, addcnt > 2 ? a2 : a0);
+        const double* f = wbc_smem + sl::OFF_V + V_SPARE * VLS;
+        const double2 f01 = ld2(f), f23 = ld2(f + 2);
+        double fbest = f01.x;
+        if (a0 > stp && f01.y < fbest) { fbest = f01.y; stpbest = a0; }
+        if (addcnt > 1 && a1 > stp && f23.x < fbest) { fbest = f23.x; stpbest = a1; }
+        if (addcnt > 2 && a2 > stp && f23.y < fbest) { fbest = f23.y; stpbest = a2; }
+    }
+    xcA = xcA + stpbest * dA;
+    {
+        const double old = xcB;
+        double v = old + stpbest * dB;
+        if (v < 0.0) v = 0.0;
+        if (needact && (NMAIN + l) == cidx) { v = cval; csB = 1; }
+        if (v <= 0.0 && v != old) { v = 0.0; csB = 1; }
+        xcB = (l < nic) ? v : 0.0;
+    }
+    double* xs = wbc_smem + sl::OFF_V + V_XC * VLS;
+    if (l < NMAIN) xs[l] = xcA;
+    if (l < ((nic + 1) & ~1)) xs[NMAIN + l] = xcB;
+    __syncwarp();
+}
+
+// One QQP solve from the point exxc (in/out) on the model (H, CI, rho, exb).  Returns the QQP termination type.
+__device__ __noinline__ int qqp_optimize_fast(const Work w, int nic, double rho, double epsx, int maxouterits, int* ncholesky, double* flops_io)
+{
+    const int l = threadIdx.x & 31;
+    const int n = NMAIN + nic;
+    const int nic2 = (nic + 1) & ~1;
+    const bool vA = l < NMAIN, vB = l < nic;
+    double flops = 0.0;
+    int nchol = 0, nfree = 0, cnmodelage = 0;
+    double* sxc = wbc_smem + sl::OFF_V + V_XC * VLS;
+    double* sdc = wbc_smem + sl::OFF_V + V_DC * VLS;
+    double* exb = wbc_smem + sl::OFF_EXB;
+    double* exxc = wbc_smem + sl::OFF_EXXC;
+    const double* H = wbc_smem + sl::OFF_H;
+    const double* CI = wbc_smem + sl::OFF_CI;
+    // settings: qqploaddefaults (opt.cpp:29533-29547) + overrides (41318-41323)
+    const int cgminits = 5;
+    int cgmaxits = (int)(1 + 0.33 * n + 0.5);
+    if (cgmaxits < cgminits) cgmaxits = cgminits;
+    const int cnmaxupdates = (int)(1 + 0.1 * n + 0.5);
+    (void)w;
+
+    const double exbA = vA ? exb[l] : 0.0, exbB = vB ? exb[NMAIN + l] : 0.0;
+    double xcA, xcB;
+    int csB = -1;
+    // |A| statistics (opt.cpp:29893-29915, with its k = (i==v ? 1 : 2) quirk) over the upper triangle of E; max|b|;
+    // start point clipped to the bounds (29979-29998) and sasstartoptimization (27377-27399)
+    double absasum, absasum2, mb;
+    {
+        double s1 = 0.0, s2 = 0.0;
+        if (vA) {
+            for (int j = l; j < NMAIN; j++) {
+                const double v = H[l * LDH + j], vv = fabs(v);
+                const double k = ((double)l == v) ? 1.0 : 2.0;
+                s1 += vv * k; s2 += vv * vv * k;
+            }
+            for (int kk = 0; kk < nic; kk++) {
+                const double v = CI[kk * LDH + l], vv = fabs(v);
+                const double k = ((double)l == v) ? 1.0 : 2.0;
+                s1 += vv * k; s2 += vv * vv * k;
+            }
+        }
+        if (vB) {
+            const double v = rho, vv = fabs(v);
+            const double k = ((double)(NMAIN + l) == v) ? 1.0 : 2.0;
+            s1 += vv * k; s2 += vv * vv * k;
+        }
+        double m1 = fmax(fabs(exbA), fabs(exbB));
+        xcA = vA ? exxc[l] : 0.0;
+        xcB = 0.0;
+        if (vB) {
+            double v = exxc[NMAIN + l];
+            if (v <= 0.0) { v = 0.0; csB = 0; }
+            xcB = v;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s1 += __shfl_xor_sync(FULL, s1, o);
+            s2 += __shfl_xor_sync(FULL, s2, o);
+            m1 = fmax(m1, __shfl_xor_sync(FULL, m1, o));
+        }
+        absasum = s1; absasum2 = s2; mb = m1;
+        if (vA) sxc[l] = xcA;
+        if (l < nic2) sxc[NMAIN + l] = xcB;
+        if (l < nic2) sdc[NMAIN + l] = 0.0;
+        __syncwarp();
+    }
+    int term = 0;
+    int cgmax = cgminits;
+    int outerits = 0;
+    double xpA = 0.0, xpB = 0.0;
+    for (;;) {
+        if (maxouterits > 0 && outerits >= maxouterits) { term = 5; break; }
+        if (outerits > 0) {
+            // epsx stopping test (30137-30149)
+            const double ta = xpA - xcA, tb = xpB - xcB;
+            const double v = red1(ta * ta + tb * tb);
+            if (sqrt(v) <= epsx) { term = 2; break; }
+        }
+        outerits++;
+        xpA = xcA; xpB = xcB;
+        double cgpA = 0.0, cgpB = 0.0, dpA = 0.0, dpB = 0.0;
+        for (int cgcnt = 0; cgcnt <= cgmax - 1; cgcnt++) {
+            const double2 ex = symv(sxc, nic2, rho);                            // targetgradient
+            const double gA = vA ? ex.x + exbA : 0.0, gB = vB ? ex.y + exbB : 0.0;
+            flops += 2.0 * n * n;
+            // sasreactivateconstraints (28992-29047), constrained gradient, CG coefficients (30199-30221)
+            const bool atb = vB && xcB == 0.0;
+            const bool act = atb && gB >= 0.0;
+            csB = act ? 1 : -1;
+            const double cgA = gA, cgB = act ? 0.0 : gB;
+            double v = cgA * cgA + cgB * cgB, vv = cgpA * cgpA + cgpB * cgpB, bf = (atb && dpB != 0.0) ? 1.0 : 0.0;
+            red3(v, vv, bf);
+            if (sqrt(v) <= 0.0) { term = 4; break; }
+            const bool brst = (bf != 0.0) || (vv == 0.0) || (cgcnt % 50 == 0);
+            const double beta = brst ? 0.0 : v / vv;
+            const double dA = vA ? -cgA + beta * dpA : 0.0;
+            const double dB = (vB && !act) ? -cgB + beta * dpB : 0.0;
+            if (vA) sdc[l] = dA;
+            if (vB) sdc[NMAIN + l] = dB;
+            __syncwarp();
+            double stpmax; int cidx;
+            explore(xcB, dB, vB && csB <= 0, stpmax, cidx);
+            double d1, d2;
+            const int code = quadratic_model(dA, dB, gA, gB, xcA, xcB, nic2, rho, absasum, absasum2, mb, d1, d2);
+            const int d1est = (code >> 2) - 1, d2est = (code & 3) - 1;
+            flops += 2.0 * n * n;
+            if (d1 == 0.0 && d2 == 0.0) { term = 4; break; }
+            if (d1est >= 0) { term = 7; break; }
+            if (d2est <= 0 && cidx < 0) { term = -4; break; }
+            double stp, a0 = 0.0, a1 = 0.0, a2 = 0.0; bool needact; int stpcnt;
+            if (d2est > 0) {
+                const double fullstp = -d1 / (2 * d2);
+                needact = fullstp >= stpmax;
+                if (needact) { stp = stpmax; a0 = stpmax * 4; a1 = fullstp; a2 = fullstp / 4; stpcnt = 3; }
+                else { stp = fullstp; stpcnt = 0; }
+            } else {
+                stp = stpmax; needact = true; a0 = 4 * stpmax; stpcnt = 1;
+            }
+            best_step_and_move(xcA, xcB, csB, dA, dB, exbA, exbB, nic, rho, stp, needact, cidx, 0.0, a0, a1, a2, stpcnt);
+            if (stpcnt > 0) flops += (1 + stpcnt) * 2.0 * n * n;
+            dpA = dA; dpB = dB; cgpA = cgA; cgpB = cgB;
+        }
+        if (term != 0) break;
+        cgmax = cgmaxits;
+        // constrained Newton phase (30353-30527)
+        int newtcnt = 0;
+        int freeB = 0;
+        for (;;) {
+            bool b;
+            if (newtcnt == 0) {
+                // qqpsolver_cnewtonbuild (31058-31201): free set, regularised diagonal, factorisation
+                freeB = vB ? !(xcB == 0.0) : 0;
+                nfree = NMAIN + __popc(__ballot_sync(FULL, freeB != 0));
+                cnmodelage = 0;
+                nchol++;
+                flops += (double)n * n * n / 3.0;
+                if (nfree == 0) b = false;      // cannot happen (main variables are free); kept for fidelity
+                else {
+                    double dgA = 0.0, dgB = 1.0;
+                    const unsigned fmask = __ballot_sync(FULL, freeB != 0);
+                    if (vA) {
+                        double v = 0.0;
+                        for (int j = 0; j < NMAIN; j++) v += fabs(H[j * LDH + l]);
+                        for (int k = 0; k < nic; k++)
+                            if ((fmask >> k) & 1u) v += fabs(CI[k * LDH + l]);
+                        if (v == 0.0) v = 1.0;
+                        dgA = H[l * LDH + l] + 1.0e-9 * v;
+                    }
+                    if (vB && freeB) {
+                        const double* row = CI + l * LDH;
+                        double v = 0.0;
+                        for (int i = 0; i < NMAIN; i++) v += fabs(row[i]);
+                        v += fabs(rho);
+                        if (v == 0.0) v = 1.0;
+                        dgB = rho + 1.0e-9 * v;
+                    }
+                    b = chol_build(n, dgA, dgB, freeB);
+                }
+                if (b) cgmax = cgminits;
+            } else {
+                // qqpsolver_cnewtonupdate (31314-31426)
+                const bool tofix = vB && freeB && xcB == 0.0;
+                const unsigned fixmask = __ballot_sync(FULL, tofix);
+                const int ntofix = __popc(fixmask);
+                flops += 3.0 * n * n;
+                if (ntofix == 0 || ntofix == nfree) b = false;
+                else if (cnmodelage + ntofix > cnmaxupdates) b = false;
+                else {
+                    for (int k = 0; k < nic; k++) {
+                        if (!((fixmask >> k) & 1u)) continue;
+                        givens_fix(n, NMAIN + k);
+                    }
+                    if (tofix) freeB = 0;
+                    nfree -= ntofix;
+                    cnmodelage += ntofix;
+                    b = true;
+                }
+            }
+            if (!b) break;
+            newtcnt++;
+            const double2 ex = symv(sxc, nic2, rho);
+            const double gA = vA ? ex.x + exbA : 0.0, gB = vB ? ex.y + exbB : 0.0;
+            // qqpsolver_cnewtonstep (31474-31536), epsg = 0
+            const double ngA = gA, ngB = (vB && freeB) ? gB : 0.0;
+            const double gg = red1(ngA * ngA + ngB * ngB);
+            if (sqrt(gg) <= 0.0) break;
+            if (vA) sdc[l] = -ngA;
+            if (vB) sdc[NMAIN + l] = -ngB;
+            __syncwarp();
+            tri_solve(sdc, n);
+            const double dA = vA ? sdc[l] : 0.0, dB = vB ? sdc[NMAIN + l] : 0.0;
+            double d1, d2;
+            const int code = quadratic_model(dA, dB, gA, gB, xcA, xcB, nic2, rho, absasum, absasum2, mb, d1, d2);
+            const int d1est = (code >> 2) - 1, d2est = (code & 3) - 1;
+            flops += 6.0 * n * n;
+            if (d1est >= 0) break;
+            double stpmax; int cidx;
+            explore(xcB, dB, vB && csB <= 0, stpmax, cidx);
+            if (d2est > 0) {
+                const double fullstp = -d1 / (2 * d2);
+                const bool needact = fullstp >= stpmax;
+                double stp, a0 = 0.0, a1 = 0.0, a2 = 0.0; int stpcnt;
+                if (needact) { stp = stpmax; a0 = stpmax * 4; a1 = fullstp; a2 = fullstp / 4; stpcnt = 3; }
+                else { stp = fullstp; stpcnt = 0; }
+                best_step_and_move(xcA, xcB, csB, dA, dB, exbA, exbB, nic, rho, stp, needact, cidx, 0.0, a0, a1, a2, stpcnt);
+                if (stpcnt > 0) flops += (1 + stpcnt) * 2.0 * n * n;
+            } else {
+                if (cidx < 0) { term = -4; break; }
+                if (stpmax == 0.0) { cgmax = cgmaxits; break; }
+                // f(x) vs f(x + stpmax d) (30493-30503)
+                eval4(xcA, xcB, dA, dB, exbA, exbB, nic, rho, 0.0, stpmax, stpmax, stpmax);
+                const double2 f01 = ld2(wbc_smem + sl::OFF_V + V_SPARE * VLS);
+                if (f01.y >= f01.x) { cgmax = cgmaxits; break; }
+                best_step_and_move(xcA, xcB, csB, dA, dB, exbA, exbB, nic, rho, stpmax, true, cidx, 0.0, stpmax * 4, 1.00, 0.25, 3);
+                flops += 12.0 * n * n;
+            }
+        }
+        if (term != 0) break;
+    }
+    // unpack (30546-30565)
+    if (vA) exxc[l] = xcA;
+    if (vB) exxc[NMAIN + l] = (xcB < 0.0 || xcB == 0.0) ? 0.0 : xcB;
+    __syncwarp();
+    *ncholesky += nchol;
+    *flops_io += flops;
+    return term;
+}
+
+}  // namespace fast
+}  // namespace wbcqp
+#endif

@@ -5,7 +5,7 @@
 //   swing   main.cpp:1163-1389  x = [ddq_com(6) | ddq_j(12) | f_st(6) | g(6)], L 82 x 31, 12 equalities
 //   torque  main.cpp:1126, 1396 tau = Mjj ddq_j + h_j - Jst_j' f
 #pragma once
-#include "qp_team.cuh"
+#include "qp_warp.cuh"
 #include "wbc_types.h"
 
 namespace wbc {
@@ -33,8 +33,8 @@ WBC_HD QpShape qp_shape(int mode)
     return s;
 }
 
-// Q: 30x30 row-major, c: 30, L: nrows x 31 row-major (dense, zero-filled here).
-template <class Ex>
+// Q: 30x30 row-major with leading dimension LDQ, c: 30, L: nrows x 31 row-major (dense, zero-filled here).
+template <int LDQ, class Ex>
 WBC_HDN inline void assemble_qp(const Ex& ex, const Params& P, const double* rec, const QpShape& sh, double* Q, double* c,
                                 double* L)
 {
@@ -49,7 +49,7 @@ WBC_HDN inline void assemble_qp(const Ex& ex, const Params& P, const double* rec
     const double* Jd = rec + QR_JDQD;
     const double* Wc = rec + QR_WCOM;
     const int nf = 3 * sh.nst;                 // force variables
-    for (int k = lane; k < 900; k += Ex::NL) Q[k] = 0.0;
+    for (int k = lane; k < 30 * LDQ; k += Ex::NL) Q[k] = 0.0;
     for (int k = lane; k < 30; k += Ex::NL) c[k] = 0.0;
     for (int k = lane; k < sh.nrows * 31; k += Ex::NL) L[k] = 0.0;
     ex.sync();
@@ -59,11 +59,11 @@ WBC_HDN inline void assemble_qp(const Ex& ex, const Params& P, const double* rec
         const int ra = sh.strow[a / 3] + a % 3, rb = sh.strow[b / 3] + b % 3;
         double s = 0.0;
         for (int t = 0; t < 6; t++) s += Jc[ra * 6 + t] * P.q1_weight * Jc[rb * 6 + t];
-        Q[(18 + a) * 30 + 18 + b] = s + (a == b ? 1.0 : 0.0);
+        Q[(18 + a) * LDQ + 18 + b] = s + (a == b ? 1.0 : 0.0);
     }
-    for (int k = lane; k < 18; k += Ex::NL) Q[k * 30 + k] = 1.0;
+    for (int k = lane; k < 18; k += Ex::NL) Q[k * LDQ + k] = 1.0;
     if (sh.nst == 2)
-        for (int k = 24 + lane; k < 30; k += Ex::NL) Q[k * 30 + k] = P.slack_weight;      // main.cpp:1187-1189
+        for (int k = 24 + lane; k < 30; k += Ex::NL) Q[k * LDQ + k] = P.slack_weight;      // main.cpp:1187-1189
     // c = -T_s' Q1 Wcom_des   (main.cpp:1033, 1224)
     for (int a = lane; a < nf; a += Ex::NL) {
         const int ra = sh.strow[a / 3] + a % 3;
@@ -156,7 +156,7 @@ WBC_HDN inline void torque_and_objective(const Ex& ex, const Params& P, const do
         // x'Qx = sum_i R_ii x_i^2 + q1 |Jst_c' f|^2 ;  c'x = -q1 (Jst_c' f) . Wcom_des
         double sq = 0.0;
         for (int k = lane; k < 30; k += Ex::NL) sq += ((sh.nst == 2 && k >= 24) ? P.slack_weight : 1.0) * x[k] * x[k];
-        sq = wbcqp::allsum1(ex, sq);
+        sq = wbcqp::red_sum1(ex, sq);
         double jj = 0.0, jw = 0.0;
         for (int t = lane; t < 6; t += Ex::NL) {
             double s = 0.0;
@@ -166,7 +166,7 @@ WBC_HDN inline void torque_and_objective(const Ex& ex, const Params& P, const do
         }
         {
             double r2[2] = {jj, jw};
-            ex.template allred<2, 0>(r2, r2);
+            wbcqp::red_sum<2>(ex, r2);
             jj = r2[0]; jw = r2[1];
         }
         if (lane == 0) *obj_out = 0.5 * (sq + P.q1_weight * jj) - P.q1_weight * jw;

@@ -2,10 +2,10 @@
 //
 // Two kernels per cycle, no intermediate dense QP ever reaches HBM:
 //   wbc_front_kernel   thread-per-instance: update() + Fgrf + estimate() + Wcom_des -> 4.2 KB QP record
-//   wbc_solve_kernel   CTA-per-instance (a team of SOLVE_T threads, 4 CTAs per SM), persistent CTAs pulling
-//                      instances from an atomic queue (iteration counts vary 4..50 Cholesky per solve):
-//                      assemble (Q,c,L) from the record straight into shared memory, DENSE-AUL/QQP solve with
-//                      everything hot in shared memory (qp_team.cuh), torque map.
+//   wbc_solve_kernel   warp-per-instance, one warp per CTA, SOLVE_CTAS_PER_SM resident CTAs per SM (shared-memory
+//                      bound), persistent warps pulling instances from an atomic queue (iteration counts vary
+//                      4..50 Cholesky per solve): assemble (Q,c,L) from the record, DENSE-AUL/QQP solve with the
+//                      hot state in shared memory (qp_warp.cuh), torque map.
 // There is no CPU fallback anywhere in this file.
 #include <cuda_runtime.h>
 #include <stdio.h>
@@ -14,7 +14,7 @@
 #include <new>
 
 #include "../../include/wbc_b200.h"
-#include "qp_team.cuh"
+#include "qp_warp.cuh"
 #include "wbc_assemble.cuh"
 #include "wbc_front.cuh"
 #include "wbc_types.h"
@@ -24,57 +24,8 @@ using namespace wbcqp;
 
 static_assert(sizeof(wbc_params) == sizeof(wbc::Params), "wbc_params and wbc::Params must have identical layout");
 
-#ifndef WBC_SOLVE_T
-#define WBC_SOLVE_T 128
-#endif
-constexpr int SOLVE_T = WBC_SOLVE_T;          // threads per team (= per CTA)
-constexpr int SOLVE_CTAS_PER_SM = 4;
-
-// ------------------------------------------------------------------------------------------------
-// per-team storage layout (doubles)
-namespace gscr {      // global scratch
-constexpr int NQMAX = MAXNT + MAXK;
-constexpr long OFF_SA = 0;
-constexpr long OFF_SGL = 944;
-constexpr long OFF_VGL = OFF_SGL + ((long)MAXNT * LDG + 15) / 16 * 16;
-constexpr long OFF_QRV = OFF_VGL + (long)NVEC * VLG;
-constexpr long OFF_SV0 = OFF_QRV + 2 * NQMAX + 4;
-constexpr long OFF_KKT = ((OFF_SV0 + NQMAX + 15) / 16) * 16;
-constexpr long TOTAL = ((OFF_KKT + 2L * NQMAX * (NQMAX + 1) + 15) / 16) * 16;
-}  // namespace gscr
-namespace sscr {      // shared memory
-constexpr int OFF_S = 0;
-constexpr int OFF_V = OFF_S + S_DOUBLES;
-constexpr int OFF_C = OFF_V + NVEC * NCAP;
-constexpr int OFF_LARINV = OFF_C + MAXK * 31;
-constexpr int OFF_LADIAG = OFF_LARINV + 32;
-constexpr int OFF_B = OFF_LADIAG + 32;
-constexpr int OFF_SC = OFF_B + 32;
-constexpr int OFF_NICERR = OFF_SC + 32;
-constexpr int OFF_NULC = OFF_NICERR + MAXNIC;
-constexpr int OFF_NULCEST = OFF_NULC + MAXK;
-constexpr int OFF_EXXC = OFF_NULCEST + MAXK;
-constexpr int OFF_EXB = OFF_EXXC + 104;
-constexpr int OFF_XS = OFF_EXB + 104;
-constexpr int OFF_RED = OFF_XS + 32;
-constexpr int OFF_INT = OFF_RED + 128;        // ints: nicnact[72], cstatus[104], isfree[104], iscr[8]
-constexpr int TOTAL = OFF_INT + (72 + 104 + 104 + 8) / 2;
-constexpr int BYTES = TOTAL * 8;
-}  // namespace sscr
-
-__device__ __forceinline__ Work carve_work(double* sm, double* gl)
-{
-    Work w;
-    w.SA = gl + gscr::OFF_SA; w.Sgl = gl + gscr::OFF_SGL; w.vgl = gl + gscr::OFF_VGL; w.qrv = gl + gscr::OFF_QRV;
-    w.sv0 = gl + gscr::OFF_SV0; w.kkt = gl + gscr::OFF_KKT;
-    w.Ssh = sm + sscr::OFF_S; w.vsh = sm + sscr::OFF_V; w.C = sm + sscr::OFF_C; w.larinv = sm + sscr::OFF_LARINV;
-    w.ladiag = sm + sscr::OFF_LADIAG; w.b = sm + sscr::OFF_B; w.s = sm + sscr::OFF_SC; w.nicerr = sm + sscr::OFF_NICERR;
-    w.nulc = sm + sscr::OFF_NULC; w.nulcest = sm + sscr::OFF_NULCEST; w.exxc = sm + sscr::OFF_EXXC; w.exb = sm + sscr::OFF_EXB;
-    w.xs = sm + sscr::OFF_XS;
-    int* ip = reinterpret_cast<int*>(sm + sscr::OFF_INT);
-    w.nicnact = ip; w.cstatus = ip + 72; w.isfree = ip + 72 + 104; w.iscr = ip + 72 + 104 + 104;
-    return w;
-}
+constexpr int SOLVE_T = 32;                   // one warp per instance, one warp per CTA
+constexpr int SOLVE_CTAS_PER_SM = (227 * 1024) / (sl::BYTES + 1024);
 
 // ------------------------------------------------------------------------------------------------
 // kernels
@@ -101,70 +52,74 @@ __device__ __forceinline__ void write_info(const Stats& st, long i, long ld, int
     if (flops) flops[i] = st.flops;
 }
 
-__device__ __forceinline__ int next_instance(int* queue, int* slot)
+__device__ __forceinline__ int next_instance(int* queue)
 {
-    if (threadIdx.x == 0) *slot = atomicAdd(queue, 1);
-    __syncthreads();
-    const int i = *slot;
-    __syncthreads();
-    return i;
+    int i = 0;
+    if ((threadIdx.x & 31) == 0) i = atomicAdd(queue, 1);
+    return __shfl_sync(0xffffffffu, i, 0);
 }
 
-__global__ void __launch_bounds__(SOLVE_T, SOLVE_CTAS_PER_SM)
-wbc_solve_kernel(Params P, int n, const double* __restrict__ recs, SolveOut out, double* __restrict__ scratch_base, int* __restrict__ queue)
+__global__ void __launch_bounds__(SOLVE_T) wbc_solve_kernel(Params P, int n, const double* __restrict__ recs, SolveOut out,
+                                                            double* __restrict__ scratch_base, int* __restrict__ queue)
 {
-    extern __shared__ __align__(16) double sm[];
-    __shared__ int s_next;
-    const Work w = carve_work(sm, scratch_base + (long)blockIdx.x * gscr::TOTAL);
-    TeamEx<SOLVE_T> ex;
-    ex.red = sm + sscr::OFF_RED; ex.par = 0;
+    Work w;
+    w.g = scratch_base + (long)blockIdx.x * gl::TOTAL;
+    w.sm = nullptr;
+    const WarpEx ex;
     Settings cfg;
-    cfg.epsx = P.qp_epsx; cfg.rho = P.qp_rho; cfg.outerits = P.qp_outerits; cfg.kkt_mode = P.reserved == 1 ? 0 : 1;
+    cfg.epsx = P.qp_epsx; cfg.rho = P.qp_rho; cfg.outerits = P.qp_outerits; cfg.kkt_mode = P.qp_literal_kkt ? 0 : 1;
+    // every value later read from shared memory is finite (out-of-range lanes read neighbours and drop the result)
+    for (int k = ex.lane(); k < sl::TOTAL; k += SOLVE_T) WBC_SM(w)[k] = 0.0;
+    ex.sync();
     for (;;) {
-        const int i = next_instance(queue, &s_next);
+        const int i = next_instance(queue);
         if (i >= n) break;
         const double* rec = recs + (long)i * QPREC_DOUBLES;
         const QpShape sh = qp_shape((int)rec[QR_MODE]);
-        // Q -> w.Ssh[0..900), c -> w.exb, L -> w.C (scaled in place by the solver)
-        assemble_qp(ex, P, rec, sh, w.Ssh, w.exb, w.C);
+        // Q -> H array (ld 31), c -> exb, L -> the warp's global C array (scaled in place by the solver)
+        assemble_qp<LDH>(ex, P, rec, sh, W_H(w), W_EXB(w), W_C(w));
         Stats st;
         solve_denseaul(ex, w, cfg, sh.nrows, sh.neq, st);
+        double* xs = W_XS(w);
         if (st.termination != 2) {
-            for (int k = ex.lane(); k < 30; k += SOLVE_T) w.xs[k] = 0.0;
+            for (int k = ex.lane(); k < 30; k += SOLVE_T) xs[k] = 0.0;
             ex.sync();
         }
-        torque_and_objective(ex, P, rec, sh, w.xs, out.tau + i, out.ld, out.qp_obj ? out.qp_obj + i : nullptr);
+        torque_and_objective(ex, P, rec, sh, xs, out.tau + i, out.ld, out.qp_obj ? out.qp_obj + i : nullptr);
         if (out.x)
-            for (int k = ex.lane(); k < 30; k += SOLVE_T) out.x[(long)k * out.ld + i] = w.xs[k];
+            for (int k = ex.lane(); k < 30; k += SOLVE_T) out.x[(long)k * out.ld + i] = xs[k];
         if (ex.lane() == 0) write_info(st, i, out.ld, out.status, out.qp_info, out.qp_flops);
         ex.sync();
     }
 }
 
 // OPT-operator path: dense, instance-major (Q [n][900], c [n][30], L [n][nrows*31], x [n][30]).
-__global__ void __launch_bounds__(SOLVE_T, SOLVE_CTAS_PER_SM)
-wbc_dense_qp_kernel(Params P, int n, const double* __restrict__ Q, const double* __restrict__ c, const double* __restrict__ L, int nrows,
-                    int neq, double* __restrict__ x, int* status, int* info, double* flops, double* __restrict__ scratch_base,
-                    int* __restrict__ queue)
+__global__ void __launch_bounds__(SOLVE_T) wbc_dense_qp_kernel(Params P, int n, const double* __restrict__ Q, const double* __restrict__ c,
+                                                               const double* __restrict__ L, int nrows, int neq, double* __restrict__ x,
+                                                               int* status, int* info, double* flops, double* __restrict__ scratch_base,
+                                                               int* __restrict__ queue)
 {
-    extern __shared__ __align__(16) double sm[];
-    __shared__ int s_next;
-    const Work w = carve_work(sm, scratch_base + (long)blockIdx.x * gscr::TOTAL);
-    TeamEx<SOLVE_T> ex;
-    ex.red = sm + sscr::OFF_RED; ex.par = 0;
+    Work w;
+    w.g = scratch_base + (long)blockIdx.x * gl::TOTAL;
+    w.sm = nullptr;
+    const WarpEx ex;
     Settings cfg;
-    cfg.epsx = P.qp_epsx; cfg.rho = P.qp_rho; cfg.outerits = P.qp_outerits; cfg.kkt_mode = P.reserved == 1 ? 0 : 1;
+    cfg.epsx = P.qp_epsx; cfg.rho = P.qp_rho; cfg.outerits = P.qp_outerits; cfg.kkt_mode = P.qp_literal_kkt ? 0 : 1;
+    // every value later read from shared memory is finite (out-of-range lanes read neighbours and drop the result)
+    for (int k = ex.lane(); k < sl::TOTAL; k += SOLVE_T) WBC_SM(w)[k] = 0.0;
+    ex.sync();
     for (;;) {
-        const int i = next_instance(queue, &s_next);
+        const int i = next_instance(queue);
         if (i >= n) break;
-        for (int k = ex.lane(); k < 900; k += SOLVE_T) w.Ssh[k] = Q[(long)i * 900 + k];
-        for (int k = ex.lane(); k < 30; k += SOLVE_T) w.exb[k] = c[(long)i * 30 + k];
-        for (int k = ex.lane(); k < nrows * 31; k += SOLVE_T) w.C[k] = L[(long)i * nrows * 31 + k];
+        double* H = W_H(w);
+        for (int k = ex.lane(); k < 900; k += SOLVE_T) H[(k / 30) * LDH + (k % 30)] = Q[(long)i * 900 + k];
+        for (int k = ex.lane(); k < 30; k += SOLVE_T) W_EXB(w)[k] = c[(long)i * 30 + k];
+        for (int k = ex.lane(); k < nrows * 31; k += SOLVE_T) W_C(w)[k] = L[(long)i * nrows * 31 + k];
         ex.sync();
         Stats st;
         solve_denseaul(ex, w, cfg, nrows, neq, st);
         if (st.termination == 2)
-            for (int k = ex.lane(); k < 30; k += SOLVE_T) x[(long)i * 30 + k] = w.xs[k];
+            for (int k = ex.lane(); k < 30; k += SOLVE_T) x[(long)i * 30 + k] = W_XS(w)[k];
         if (ex.lane() == 0) {   // instance-major info [n][8] on this path
             write_info(st, i, n, status, nullptr, flops);
             if (info) {
@@ -224,7 +179,7 @@ struct wbc_ctx {
     double* yd;          // [6][max_batch]
     double* yw;
     double* w_dev;       // [6][max_batch] (when the caller passes no w)
-    double* scratch;     // [nblocks][gscr::TOTAL]
+    double* scratch;     // [nblocks][gl::TOTAL]
     int* queue;          // work-queue counter
     int nblocks, threads;   // solver launch shape
     // staging for WBC_HOST_PTRS
@@ -250,7 +205,7 @@ void wbc_default_params(wbc_params* p)
     p->joint_dt = 0.025; p->kp_sw = 300.0; p->kd_sw = 20.0; p->g_acc = 9.81; p->obs_gain = 10.0; p->obs_dt = 0.0025;
     p->gravity[0] = 0.0; p->gravity[1] = 0.0; p->gravity[2] = -9.8;
     p->qp_epsx = 1.0e-2; p->qp_rho = 1.0e4; p->qp_outerits = 5;
-    p->observer_enabled = 1; p->fix_swing_rhs = 0; p->reserved = 0;
+    p->observer_enabled = 1; p->fix_swing_rhs = 0; p->qp_literal_kkt = 0;
 }
 
 const char* wbc_last_error(void) { return g_err; }
@@ -302,7 +257,7 @@ int wbc_create(wbc_ctx** out, int device, int max_batch, const wbc_params* param
     TRY(cudaMalloc(&c->yd, nb * 6 * sizeof(double)));
     TRY(cudaMalloc(&c->yw, nb * 6 * sizeof(double)));
     TRY(cudaMalloc(&c->w_dev, nb * 6 * sizeof(double)));
-    TRY(cudaMalloc(&c->scratch, (size_t)nteams * gscr::TOTAL * sizeof(double)));
+    TRY(cudaMalloc(&c->scratch, (size_t)nteams * gl::TOTAL * sizeof(double)));
     TRY(cudaMalloc(&c->queue, 64));
     TRY(cudaMalloc(&c->d_in, nb * (kInDoublesNoTerrain + 40) * sizeof(double)));
     TRY(cudaMalloc(&c->d_out, nb * kOutDoubles * sizeof(double)));
@@ -312,9 +267,11 @@ int wbc_create(wbc_ctx** out, int device, int max_batch, const wbc_params* param
     TRY(cudaMallocHost(&c->h_pin_i, nb * kOutInts * sizeof(int)));
     TRY(cudaMemset(c->yd, 0, nb * 6 * sizeof(double)));
     TRY(cudaMemset(c->yw, 0, nb * 6 * sizeof(double)));
-    TRY(cudaMemset(c->scratch, 0, (size_t)nteams * gscr::TOTAL * sizeof(double)));
-    TRY(cudaFuncSetAttribute(wbc_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sscr::BYTES));
-    TRY(cudaFuncSetAttribute(wbc_dense_qp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sscr::BYTES));
+    TRY(cudaMemset(c->scratch, 0, (size_t)nteams * gl::TOTAL * sizeof(double)));
+    TRY(cudaFuncSetAttribute(wbc_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sl::BYTES));
+    TRY(cudaFuncSetAttribute(wbc_dense_qp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sl::BYTES));
+    TRY(cudaFuncSetAttribute(wbc_solve_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    TRY(cudaFuncSetAttribute(wbc_dense_qp_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 #undef TRY
     if (e != cudaSuccess) {
         fail(e == cudaErrorMemoryAllocation ? WBC_ENOMEM : WBC_ECUDA, "wbc_create: %s", cudaGetErrorString(e));
@@ -443,7 +400,7 @@ int wbc_cycle(wbc_ctx* c, int n, const wbc_inputs* in, const wbc_outputs* out, v
     wbc_front_kernel<<<(n + fthreads - 1) / fthreads, fthreads, 0, s>>>(c->params, din, st, n, c->recs, w_ptr, w_ld, nodbg, 0);
     CU(cudaEventRecord(c->ev1, s));
     const int nblocks = n < c->nblocks ? n : c->nblocks;
-    wbc_solve_kernel<<<nblocks, c->threads, sscr::BYTES, s>>>(c->params, n, c->recs, so, c->scratch, c->queue);
+    wbc_solve_kernel<<<nblocks, c->threads, sl::BYTES, s>>>(c->params, n, c->recs, so, c->scratch, c->queue);
     CU(cudaEventRecord(c->ev2, s));
     CU(cudaGetLastError());
     c->launches = 2;
@@ -571,7 +528,7 @@ int wbc_qp_solve(wbc_ctx* c, int n, const double* Q, const double* cvec, const d
     const int nblocks = n < c->nblocks ? n : c->nblocks;
     CU(cudaEventRecord(c->ev0, s));
     CU(cudaEventRecord(c->ev1, s));
-    wbc_dense_qp_kernel<<<nblocks, c->threads, sscr::BYTES, s>>>(c->params, n, dQ, dc, dL, nrows, neq, dx, dstatus, dinfo, dflops, c->scratch, c->queue);
+    wbc_dense_qp_kernel<<<nblocks, c->threads, sl::BYTES, s>>>(c->params, n, dQ, dc, dL, nrows, neq, dx, dstatus, dinfo, dflops, c->scratch, c->queue);
     CU(cudaEventRecord(c->ev2, s));
     CU(cudaGetLastError());
     c->launches = 1;

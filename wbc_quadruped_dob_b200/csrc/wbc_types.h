@@ -39,7 +39,7 @@ struct Params {
     int qp_outerits;          // 5                 lopt.cpp:101
     int observer_enabled;     // north_star: 1 (the reference ships with the call commented out, main.cpp:1029)
     int fix_swing_rhs;        // 0 keeps the reference's zero swing-equality rhs (main.cpp:1238-1241)
-    int reserved;
+    int qp_literal_kkt;       // 0: reduced multiplier update, literal form as fallback; 1: literal form only (opt.cpp:41803-42032)
 };
 
 struct DevInputs {
