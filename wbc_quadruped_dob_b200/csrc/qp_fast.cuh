@@ -83,7 +83,7 @@ __device__ __noinline__ void eval4(double xcA, double xcB, double dA, double dB,
     const double* Crow = wbc_smem + sl::OFF_CI + l * LDH;
     const double* Ccol = wbc_smem + sl::OFF_CI + l;
     double a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
-#pragma unroll 6
+#pragma unroll 2
     for (int j = 0; j < NMAIN; j++) {
         const double2 t01 = ld2(t4 + j * 4), t23 = ld2(t4 + j * 4 + 2);
         const double h = H[j * LDH], c = Crow[j];
@@ -199,38 +199,50 @@ __device__ __noinline__ bool chol_build(int n, double diagA, double diagB, int f
 }
 
 // Solve U'U x = rhs with the packed factor; rhs and result in shared memory at `x` (index = variable).
+// Row c of the factor is owned by lane c & 31 (slot c >> 5).  The running right-hand side stays in registers; the
+// owner of component k never touches it again after step k, so scaling by 1/U_kk is done once at the end of each sweep.
 __device__ __noinline__ void tri_solve(double* x, int n)
 {
     const int l = threadIdx.x & 31;
     const double* Z = wbc_smem + sl::OFF_Z;
     const double* zrinv = wbc_smem + sl::OFF_V + V_ZRINV * VLS;
-    const int c0 = l, c1 = l + 32;
-    const double* r0 = Z + zoff(c0);
+    const int c1 = l + 32;
+    const double* r0 = Z + zoff(l);
     const double* r1 = Z + zoff(c1 < n ? c1 : 0);
-    double x0 = (c0 < n) ? x[c0] : 0.0, x1 = (c1 < n) ? x[c1] : 0.0;
-    double y0 = 0.0, y1 = 0.0;
+    const double zr0 = zrinv[l], zr1 = zrinv[c1 < n ? c1 : 0];
+    double x0 = x[l], x1 = (c1 < n) ? x[c1] : 0.0;          // lanes >= n (n < 32) carry finite garbage that is never broadcast
+    const int n0 = n < 32 ? n : 32;
     // forward: U' y = rhs, column oriented
 #pragma unroll 2
-    for (int k = 0; k < n; k++) {
-        const double yk = bshfl((k < 32) ? x0 : x1, k & 31) * zrinv[k];
-        if (c0 == k) y0 = yk;
-        if (c1 == k) y1 = yk;
-        if (c0 > k && c0 < n) x0 -= r0[k] * yk;
-        if (c1 > k && c1 < n) x1 -= r1[k] * yk;
+    for (int k = 0; k < n0; k++) {
+        const double yk = bshfl(x0 * zr0, k);
+        if (l > k) x0 -= r0[k] * yk;
+        x1 -= r1[k] * yk;
     }
+#pragma unroll 1
+    for (int k = 32; k < n; k++) {
+        const double yk = bshfl(x1 * zr1, k - 32);
+        if (c1 > k) x1 -= r1[k] * yk;
+    }
+    x0 *= zr0; x1 *= zr1;
     // backward: U x = y
-#pragma unroll 2
-    for (int k = n - 1; k >= 0; k--) {
-        const double xk = bshfl((k < 32) ? y0 : y1, k & 31) * zrinv[k];
+#pragma unroll 1
+    for (int k = n - 1; k >= 32; k--) {
+        const double xk = bshfl(x1 * zr1, k - 32);
         const double* rk = Z + zoff(k);
-        if (c0 == k) y0 = xk;
-        if (c1 == k) y1 = xk;
-        if (c0 < k) y0 -= rk[c0] * xk;
-        if (c1 < k) y1 -= rk[c1] * xk;
+        x0 -= rk[l] * xk;
+        if (c1 < k) x1 -= rk[c1] * xk;
     }
+#pragma unroll 2
+    for (int k = n0 - 1; k >= 0; k--) {
+        const double xk = bshfl(x0 * zr0, k);
+        const double* rk = Z + zoff(k);
+        if (l < k) x0 -= rk[l] * xk;
+    }
+    x0 *= zr0; x1 *= zr1;
     __syncwarp();
-    if (c0 < n) x[c0] = y0;
-    if (c1 < n) x[c1] = y1;
+    if (l < n) x[l] = x0;
+    if (c1 < n) x[c1] = x1;
     __syncwarp();
 }
 
@@ -256,9 +268,9 @@ __device__ __forceinline__ double red1(double a)
 }
 
 // qqpsolver_quadraticmodel (opt.cpp:30753-30821) on two-slot registers.  d is mirrored at V_DC.  Returns the packed sign
-// estimates (see estimateparabolicmodel); d1, d2 by reference (inlined).
-__device__ __forceinline__ int quadratic_model(double dA, double dB, double gA, double gB, double xcA, double xcB, int nic2, double rho,
-                                               double absasum, double absasum2, double mb, double& d1, double& d2)
+// estimates (see estimateparabolicmodel); d1, d2 are left in V_SPARE[4..5].
+__device__ __noinline__ int quadratic_model(double dA, double dB, double gA, double gB, double xcA, double xcB, int nic2, double rho,
+                                            double absasum, double absasum2, double mb)
 {
     const double2 ed = symv(wbc_smem + sl::OFF_V + V_DC * VLS, nic2, rho);
     double s0 = dA * ed.x + dB * ed.y;       // invalid lanes carry d = 0
@@ -271,12 +283,18 @@ __device__ __forceinline__ int quadratic_model(double dA, double dB, double gA, 
         m0 = fmax(m0, __shfl_xor_sync(FULL, m0, o));
         m1 = fmax(m1, __shfl_xor_sync(FULL, m1, o));
     }
-    d2 = 0.5 * s0; d1 = s1;
+    const double d2 = 0.5 * s0, d1 = s1;
+    if ((threadIdx.x & 31) == 0) {
+        wbc_smem[sl::OFF_V + V_SPARE * VLS + 4] = d1;
+        wbc_smem[sl::OFF_V + V_SPARE * VLS + 5] = d2;
+    }
+    __syncwarp();
     return estimateparabolicmodel(absasum, absasum2, m0, mb, m1, d1, d2);
 }
 
 // sasexploredirection (opt.cpp:27433-27528) on slot B registers (see sas_explore_direction in qp_warp.cuh).
-__device__ __forceinline__ void explore(double xcB, double dB, bool candB, double& stpmax, int& cidx)
+// Returns cidx (-1: no blocking bound); the step is left in V_SPARE[6].
+__device__ __noinline__ int explore(double xcB, double dB, int candB)
 {
     const int l = threadIdx.x & 31;
     double best = BIGSTEP;
@@ -291,22 +309,40 @@ __device__ __forceinline__ void explore(double xcB, double dB, bool candB, doubl
         const int oi = __shfl_xor_sync(FULL, bi, o);
         if (ov < best || (ov == best && oi < bi)) { best = ov; bi = oi; }
     }
-    stpmax = best;
-    cidx = (best < BIGSTEP) ? bi : -1;
+    if (l == 0) wbc_smem[sl::OFF_V + V_SPARE * VLS + 6] = best;
+    __syncwarp();
+    return (best < BIGSTEP) ? bi : -1;
 }
 
-// qqpsolver_findbeststepandmove (opt.cpp:30882-31003) + sasmoveto (27574-27723) on two-slot registers.
-// csB: cstatus of slot B (updated).  Mirrors the new point to V_XC.
-__device__ __forceinline__ void best_step_and_move(double& xcA, double& xcB, int& csB, double dA, double dB, double exbA, double exbB, int nic,
-                                                   double rho, double stp, bool needact, int cidx, double cval, double a0, double a1, double a2,
-                                                   int addcnt)
+// Step selection after the quadratic model (opt.cpp:30259-30302 / 30440-30487), qqpsolver_findbeststepandmove
+// (30882-31003) and sasmoveto (27574-27723) on two-slot registers; xc is read from and written back to its shared
+// mirror V_XC.  mode 0: d2est > 0 (full step unless a bound blocks); 1: non-positive curvature in the CG phase
+// (step to the bound); 2: the Newton phase's bound step with candidates {4 stpmax, 1, 0.25}.
+// Returns the new cstatus of slot B; *evals (register, uniform) gets the number of extra model evaluations.
+__device__ __noinline__ int step_and_move(double dA, double dB, double exbA, double exbB, int nic, double rho, int mode, int cidx, int csB)
 {
     const int l = threadIdx.x & 31;
+    double* xs = wbc_smem + sl::OFF_V + V_XC * VLS;
+    const double* sp = wbc_smem + sl::OFF_V + V_SPARE * VLS;
+    const double d1 = sp[4], d2 = sp[5], stpmax = sp[6];
+    double xcA = xs[l], xcB = (l < nic) ? xs[NMAIN + l] : 0.0;
+    double stp, a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    bool needact;
+    int addcnt;
+    if (mode == 0) {
+        const double fullstp = -d1 / (2 * d2);
+        needact = fullstp >= stpmax;
+        if (needact) { stp = stpmax; a0 = stpmax * 4; a1 = fullstp; a2 = fullstp * 0.25; addcnt = 3; }
+        else { stp = fullstp; addcnt = 0; }
+    } else if (mode == 1) {
+        stp = stpmax; needact = true; a0 = 4 * stpmax; addcnt = 1;
+    } else {
+        stp = stpmax; needact = true; a0 = stpmax * 4; a1 = 1.00; a2 = 0.25; addcnt = 3;
+    }
     double stpbest = stp;
     if (addcnt > 0) {
         eval4(xcA, xcB, dA, dB, exbA, exbB, nic, rho, stp, a0, addcnt > 1 ? a1 : a0, addcnt > 2 ? a2 : a0);
-        const double* f = wbc_smem + sl::OFF_V + V_SPARE * VLS;
-        const double2 f01 = ld2(f), f23 = ld2(f + 2);
+        const double2 f01 = ld2(sp), f23 = ld2(sp + 2);
         double fbest = f01.x;
         if (a0 > stp && f01.y < fbest) { fbest = f01.y; stpbest = a0; }
         if (addcnt > 1 && a1 > stp && f23.x < fbest) { fbest = f23.x; stpbest = a1; }
@@ -317,14 +353,15 @@ __device__ __forceinline__ void best_step_and_move(double& xcA, double& xcB, int
         const double old = xcB;
         double v = old + stpbest * dB;
         if (v < 0.0) v = 0.0;
-        if (needact && (NMAIN + l) == cidx) { v = cval; csB = 1; }
+        if (needact && (NMAIN + l) == cidx) { v = 0.0; csB = 1; }
         if (v <= 0.0 && v != old) { v = 0.0; csB = 1; }
         xcB = (l < nic) ? v : 0.0;
     }
-    double* xs = wbc_smem + sl::OFF_V + V_XC * VLS;
     if (l < NMAIN) xs[l] = xcA;
     if (l < ((nic + 1) & ~1)) xs[NMAIN + l] = xcB;
+    if (l == 0) wbc_smem[sl::OFF_V + V_SPARE * VLS + 7] = (double)addcnt;
     __syncwarp();
+    return csB;
 }
 
 // One QQP solve from the point exxc (in/out) on the model (H, CI, rho, exb).  Returns the QQP termination type.
@@ -338,6 +375,7 @@ __device__ __noinline__ int qqp_optimize_fast(const Work w, int nic, double rho,
     int nchol = 0, nfree = 0, cnmodelage = 0;
     double* sxc = wbc_smem + sl::OFF_V + V_XC * VLS;
     double* sdc = wbc_smem + sl::OFF_V + V_DC * VLS;
+    const double* spare = wbc_smem + sl::OFF_V + V_SPARE * VLS;
     double* exb = wbc_smem + sl::OFF_EXB;
     double* exxc = wbc_smem + sl::OFF_EXXC;
     const double* H = wbc_smem + sl::OFF_H;
@@ -420,7 +458,7 @@ __device__ __noinline__ int qqp_optimize_fast(const Work w, int nic, double rho,
             const double cgA = gA, cgB = act ? 0.0 : gB;
             double v = cgA * cgA + cgB * cgB, vv = cgpA * cgpA + cgpB * cgpB, bf = (atb && dpB != 0.0) ? 1.0 : 0.0;
             red3(v, vv, bf);
-            if (sqrt(v) <= 0.0) { term = 4; break; }
+            if (v <= 0.0) { term = 4; break; }      // sqrt(v) <= 0 with v a sum of squares
             const bool brst = (bf != 0.0) || (vv == 0.0) || (cgcnt % 50 == 0);
             const double beta = brst ? 0.0 : v / vv;
             const double dA = vA ? -cgA + beta * dpA : 0.0;
@@ -428,26 +466,17 @@ __device__ __noinline__ int qqp_optimize_fast(const Work w, int nic, double rho,
             if (vA) sdc[l] = dA;
             if (vB) sdc[NMAIN + l] = dB;
             __syncwarp();
-            double stpmax; int cidx;
-            explore(xcB, dB, vB && csB <= 0, stpmax, cidx);
-            double d1, d2;
-            const int code = quadratic_model(dA, dB, gA, gB, xcA, xcB, nic2, rho, absasum, absasum2, mb, d1, d2);
+            const int cidx = explore(xcB, dB, vB && csB <= 0);
+            const int code = quadratic_model(dA, dB, gA, gB, xcA, xcB, nic2, rho, absasum, absasum2, mb);
             const int d1est = (code >> 2) - 1, d2est = (code & 3) - 1;
+            const double d1 = spare[4], d2 = spare[5];
             flops += 2.0 * n * n;
             if (d1 == 0.0 && d2 == 0.0) { term = 4; break; }
             if (d1est >= 0) { term = 7; break; }
             if (d2est <= 0 && cidx < 0) { term = -4; break; }
-            double stp, a0 = 0.0, a1 = 0.0, a2 = 0.0; bool needact; int stpcnt;
-            if (d2est > 0) {
-                const double fullstp = -d1 / (2 * d2);
-                needact = fullstp >= stpmax;
-                if (needact) { stp = stpmax; a0 = stpmax * 4; a1 = fullstp; a2 = fullstp / 4; stpcnt = 3; }
-                else { stp = fullstp; stpcnt = 0; }
-            } else {
-                stp = stpmax; needact = true; a0 = 4 * stpmax; stpcnt = 1;
-            }
-            best_step_and_move(xcA, xcB, csB, dA, dB, exbA, exbB, nic, rho, stp, needact, cidx, 0.0, a0, a1, a2, stpcnt);
-            if (stpcnt > 0) flops += (1 + stpcnt) * 2.0 * n * n;
+            csB = step_and_move(dA, dB, exbA, exbB, nic, rho, d2est > 0 ? 0 : 1, cidx, csB);
+            xcA = vA ? sxc[l] : 0.0; xcB = vB ? sxc[NMAIN + l] : 0.0;
+            flops += spare[7] > 0.0 ? (1.0 + spare[7]) * 2.0 * n * n : 0.0;
             dpA = dA; dpB = dB; cgpA = cgA; cgpB = cgB;
         }
         if (term != 0) break;
@@ -513,37 +542,32 @@ __device__ __noinline__ int qqp_optimize_fast(const Work w, int nic, double rho,
             // qqpsolver_cnewtonstep (31474-31536), epsg = 0
             const double ngA = gA, ngB = (vB && freeB) ? gB : 0.0;
             const double gg = red1(ngA * ngA + ngB * ngB);
-            if (sqrt(gg) <= 0.0) break;
+            if (gg <= 0.0) break;
             if (vA) sdc[l] = -ngA;
             if (vB) sdc[NMAIN + l] = -ngB;
             __syncwarp();
             tri_solve(sdc, n);
             const double dA = vA ? sdc[l] : 0.0, dB = vB ? sdc[NMAIN + l] : 0.0;
-            double d1, d2;
-            const int code = quadratic_model(dA, dB, gA, gB, xcA, xcB, nic2, rho, absasum, absasum2, mb, d1, d2);
+            const int code = quadratic_model(dA, dB, gA, gB, xcA, xcB, nic2, rho, absasum, absasum2, mb);
             const int d1est = (code >> 2) - 1, d2est = (code & 3) - 1;
             flops += 6.0 * n * n;
             if (d1est >= 0) break;
-            double stpmax; int cidx;
-            explore(xcB, dB, vB && csB <= 0, stpmax, cidx);
+            const int cidx = explore(xcB, dB, vB && csB <= 0);
             if (d2est > 0) {
-                const double fullstp = -d1 / (2 * d2);
-                const bool needact = fullstp >= stpmax;
-                double stp, a0 = 0.0, a1 = 0.0, a2 = 0.0; int stpcnt;
-                if (needact) { stp = stpmax; a0 = stpmax * 4; a1 = fullstp; a2 = fullstp / 4; stpcnt = 3; }
-                else { stp = fullstp; stpcnt = 0; }
-                best_step_and_move(xcA, xcB, csB, dA, dB, exbA, exbB, nic, rho, stp, needact, cidx, 0.0, a0, a1, a2, stpcnt);
-                if (stpcnt > 0) flops += (1 + stpcnt) * 2.0 * n * n;
+                csB = step_and_move(dA, dB, exbA, exbB, nic, rho, 0, cidx, csB);
+                flops += spare[7] > 0.0 ? (1.0 + spare[7]) * 2.0 * n * n : 0.0;
             } else {
+                const double stpmax = spare[6];
                 if (cidx < 0) { term = -4; break; }
                 if (stpmax == 0.0) { cgmax = cgmaxits; break; }
                 // f(x) vs f(x + stpmax d) (30493-30503)
                 eval4(xcA, xcB, dA, dB, exbA, exbB, nic, rho, 0.0, stpmax, stpmax, stpmax);
-                const double2 f01 = ld2(wbc_smem + sl::OFF_V + V_SPARE * VLS);
+                const double2 f01 = ld2(spare);
                 if (f01.y >= f01.x) { cgmax = cgmaxits; break; }
-                best_step_and_move(xcA, xcB, csB, dA, dB, exbA, exbB, nic, rho, stpmax, true, cidx, 0.0, stpmax * 4, 1.00, 0.25, 3);
+                csB = step_and_move(dA, dB, exbA, exbB, nic, rho, 2, cidx, csB);
                 flops += 12.0 * n * n;
             }
+            xcA = vA ? sxc[l] : 0.0; xcB = vB ? sxc[NMAIN + l] : 0.0;
         }
         if (term != 0) break;
     }

@@ -61,26 +61,29 @@ constexpr double BIGSTEP = 1.0e50;     // opt.cpp:27458
 // packed lower triangle, row c holds entries (c, k), k < c, padded to an even count
 WBC_HD int zoff(int c) { return ((c * (c - 1)) >> 1) + (c >> 1); }
 
-// ---- shared-memory layout of one warp (doubles)
+// ---- shared-memory layout of one warp (doubles).  The QQP vector block comes last: the device keeps only the
+// NVEC_SM vectors its register-resident QQP (qp_fast.cuh) mirrors to memory; the generic QQP (host emulation, and the
+// device's spill mode, which uses the global copy) needs all NVEC.
+#if defined(__CUDACC__)
+constexpr int NVEC_SM = 9;
+#else
+constexpr int NVEC_SM = NVEC;
+#endif
 namespace sl {
 constexpr int OFF_H = 0;                               // [30][31]
 constexpr int OFF_CI = OFF_H + NMAIN * LDH;            // [18][31]
 constexpr int OFF_Z = OFF_CI + NICCAP * LDH;           // packed, zoff(48) = 1152
-constexpr int OFF_V = OFF_Z + 1152;                    // [16][48]
-constexpr int BIG = OFF_V;                             // H | CI | Z double as one 2640-double workspace
-constexpr int OFF_B = OFF_V + NVEC * VLS;
-constexpr int OFF_SC = OFF_B + 32;
-constexpr int OFF_LARINV = OFF_SC + 32;
-constexpr int OFF_NICERR = OFF_LARINV + 32;
-constexpr int OFF_NULC = OFF_NICERR + MAXNIC;
-constexpr int OFF_NULCEST = OFF_NULC + MAXK;
-constexpr int OFF_EXXC = OFF_NULCEST + MAXK;
+constexpr int BIG = OFF_Z + 1152;                      // H | CI | Z double as one 2640-double workspace
+constexpr int OFF_LARINV = BIG;
+constexpr int OFF_EXXC = OFF_LARINV + 32;
 constexpr int OFF_EXB = OFF_EXXC + 104;
 constexpr int OFF_XS = OFF_EXB + 104;
-constexpr int OFF_INT = OFF_XS + 32;                   // ints: nicnact[72] cstatus[104] isfree[104] iscr[8]
-constexpr int TOTAL = OFF_INT + (72 + 104 + 104 + 8) / 2;
+constexpr int OFF_INT = OFF_XS + 32;                   // ints: cstatus[104] isfree[104] iscr[8]
+constexpr int OFF_V = OFF_INT + (104 + 104 + 8) / 2;   // [NVEC_SM][48]
+constexpr int TOTAL = OFF_V + NVEC_SM * VLS;
 constexpr int BYTES = TOTAL * 8;
 static_assert(BIG == 2640, "workspace size");
+static_assert(OFF_V % 2 == 0 && OFF_Z % 2 == 0, "16-byte alignment of the vector block and the factor");
 }  // namespace sl
 // ---- global scratch layout of one warp (doubles)
 namespace gl {
@@ -88,7 +91,13 @@ constexpr int NQMAX = MAXNT + MAXK;
 constexpr long OFF_C = 0;                                        // [88][31]
 constexpr long OFF_A = OFF_C + MAXK * LDH;                       // [30][31] scaled A, full symmetric
 constexpr long OFF_LA = OFF_A + 944;                             // packed factor of A (transposed: row c = U[.][c]), zoff(30) = 450
-constexpr long OFF_CI = OFF_LA + 464;                            // spill [72][31]
+constexpr long OFF_B = OFF_LA + 464;                             // [32] scaled linear term
+constexpr long OFF_SC = OFF_B + 32;                              // [32] variable scales
+constexpr long OFF_NICERR = OFF_SC + 32;                         // [72]
+constexpr long OFF_NULC = OFF_NICERR + MAXNIC;                   // [88]
+constexpr long OFF_NULCEST = OFF_NULC + MAXK;                    // [88]
+constexpr long OFF_NICNACT = OFF_NULCEST + MAXK;                 // [72] ints
+constexpr long OFF_CI = OFF_NICNACT + 40;                        // spill [72][31]
 constexpr long OFF_Z = OFF_CI + MAXNIC * LDH + 8;                // spill packed, zoff(102) = 5202
 constexpr long OFF_V = OFF_Z + 5216;                             // spill [16][104]
 constexpr long OFF_QRV = OFF_V + NVEC * VLG;
@@ -114,19 +123,19 @@ extern __shared__ __align__(16) double wbc_smem[];
 #define W_H(w) SM_(w, sl::OFF_H)
 #define W_BIG(w) SM_(w, 0)
 #define W_VEC(w) SM_(w, sl::OFF_V)
-#define W_B(w) SM_(w, sl::OFF_B)
-#define W_SC(w) SM_(w, sl::OFF_SC)
+#define W_B(w) ((w).g + gl::OFF_B)
+#define W_SC(w) ((w).g + gl::OFF_SC)
 #define W_LARINV(w) SM_(w, sl::OFF_LARINV)
-#define W_NICERR(w) SM_(w, sl::OFF_NICERR)
-#define W_NULC(w) SM_(w, sl::OFF_NULC)
-#define W_NULCEST(w) SM_(w, sl::OFF_NULCEST)
+#define W_NICERR(w) ((w).g + gl::OFF_NICERR)
+#define W_NULC(w) ((w).g + gl::OFF_NULC)
+#define W_NULCEST(w) ((w).g + gl::OFF_NULCEST)
 #define W_EXXC(w) SM_(w, sl::OFF_EXXC)
 #define W_EXB(w) SM_(w, sl::OFF_EXB)
 #define W_XS(w) SM_(w, sl::OFF_XS)
-#define W_NICNACT(w) (reinterpret_cast<int*>(SM_(w, sl::OFF_INT)))
-#define W_CSTATUS(w) (reinterpret_cast<int*>(SM_(w, sl::OFF_INT)) + 72)
-#define W_ISFREE(w) (reinterpret_cast<int*>(SM_(w, sl::OFF_INT)) + 72 + 104)
-#define W_ISCR(w) (reinterpret_cast<int*>(SM_(w, sl::OFF_INT)) + 72 + 104 + 104)
+#define W_NICNACT(w) (reinterpret_cast<int*>((w).g + gl::OFF_NICNACT))
+#define W_CSTATUS(w) (reinterpret_cast<int*>(SM_(w, sl::OFF_INT)))
+#define W_ISFREE(w) (reinterpret_cast<int*>(SM_(w, sl::OFF_INT)) + 104)
+#define W_ISCR(w) (reinterpret_cast<int*>(SM_(w, sl::OFF_INT)) + 104 + 104)
 #define W_C(w) ((w).g + gl::OFF_C)
 #define W_A(w) ((w).g + gl::OFF_A)
 #define W_LA(w) ((w).g + gl::OFF_LA)
@@ -140,7 +149,7 @@ struct QS {
     static WBC_HD double* V(const Work& w, int k) { return (SPILL ? w.g + gl::OFF_V : SM_(w, sl::OFF_V)) + k * VL; }
 };
 // vector slots
-enum { V_ZD = 0, V_ZRINV, V_XC, V_XP, V_GC, V_CGC, V_CGP, V_DC, V_DP, V_T0, V_T1, V_T2, V_T3, V_BUFR, V_REG, V_SPARE };
+enum { V_ZD = 0, V_ZRINV, V_XC, V_DC, V_T0, V_T1, V_T2, V_T3, V_SPARE, V_XP, V_GC, V_CGC, V_CGP, V_DP, V_BUFR, V_REG };
 
 struct Settings {
     double epsx = 1.0e-2;   // lopt.cpp:101
@@ -1512,11 +1521,18 @@ WBC_HD int model_and_qqp(const Ex& ex, const Work& w, int nec, int nicwork, doub
 {
     generate_ex_model<SPILL>(ex, w, nec, nicwork, rho);
     *flops += (double)NMAIN * NMAIN * (nec + nicwork) + 4.0 * NMAIN * (nec + nicwork);
-#if defined(__CUDA_ARCH__)
-    if (!SPILL) return fast::qqp_optimize_fast(w, nicwork, rho, 0.01 * epsx, 50, ncholesky, flops);
-#endif
     return qqp_optimize<SPILL>(ex, w, nicwork, rho, 0.01 * epsx, 50, ncholesky, flops);
 }
+#if defined(__CUDACC__)
+// device, shared-memory case: the register-resident QQP (the generic one is not instantiated: its vectors do not exist there)
+__device__ __forceinline__ int model_and_qqp_dev(const WarpEx& ex, const Work& w, int nec, int nicwork, double rho, double epsx,
+                                                 int* ncholesky, double* flops)
+{
+    generate_ex_model<false>(ex, w, nec, nicwork, rho);
+    *flops += (double)NMAIN * NMAIN * (nec + nicwork) + 4.0 * NMAIN * (nec + nicwork);
+    return fast::qqp_optimize_fast(w, nicwork, rho, 0.01 * epsx, 50, ncholesky, flops);
+}
+#endif
 
 // The solver.  On entry the warp has staged the problem (see setup_problem).  Result: xs[0..30) in shared memory.
 template <class Ex>
@@ -1556,7 +1572,11 @@ WBC_HDN void solve_denseaul(const Ex& ex, const Work& w, const Settings& cfg, in
             int term;
             // shared-memory capacity: NICCAP working inequality rows, and nec + nicwork rows in the staging array
             if (nicwork > NICCAP || (nec + nicwork) * LDH > 1152) { st.flags |= 32; term = model_and_qqp<true>(ex, w, nec, nicwork, rho, epsx, &st.ncholesky, &st.flops); }
+#if defined(__CUDA_ARCH__)
+            else term = model_and_qqp_dev(ex, w, nec, nicwork, rho, epsx, &st.ncholesky, &st.flops);
+#else
             else term = model_and_qqp<false>(ex, w, nec, nicwork, rho, epsx, &st.ncholesky, &st.flops);
+#endif
             st.qqp_calls++;
             if (term == -4) st.flags |= 4;
             // violations of all inequality rows w.r.t. the main variables only (41330-41335)
