@@ -17,10 +17,32 @@
 namespace wbcqp {
 namespace fast {
 
+// Code size is a first-order cost here: ncu shows the SM instruction cache hit rate at 60 % and the GPC-level
+// instruction cache at half of its peak request rate when every warp of an SM runs a different phase of a
+// 200 KB kernel.  So loops are not unrolled unless they are the product itself, divisions / square roots /
+// reductions are shared non-inlined helpers, and maxima / arg-minima use the warp REDUX unit on the bit
+// patterns (exact for non-negative doubles).
 constexpr unsigned FULL = 0xffffffffu;
 
 __device__ __forceinline__ double bshfl(double v, int src) { return __shfl_sync(FULL, v, src); }
 __device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+__device__ __noinline__ double ddiv(double a, double b) { return a / b; }
+__device__ __noinline__ double dsqrt(double a) { return sqrt(a); }
+// warp sum, every lane gets the same bits
+__device__ __noinline__ double wsum(double v)
+{
+#pragma unroll 1
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+// warp maximum of non-negative doubles (bit patterns order like the values)
+__device__ __forceinline__ double wmax_nn(double v)
+{
+    const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+    const unsigned mh = __reduce_max_sync(FULL, hi);
+    const unsigned ml = __reduce_max_sync(FULL, hi == mh ? lo : 0u);
+    return __hiloint2double((int)mh, (int)ml);
+}
 
 // y = E x for the vector mirrored at `x` (shared, 16-byte aligned, entries >= n finite).  Returns slot A / slot B parts.
 // nic2 = nic rounded up to even; rows [nic, nic2) of CI are zero.
@@ -83,7 +105,7 @@ __device__ __noinline__ void eval4(double xcA, double xcB, double dA, double dB,
     const double* Crow = wbc_smem + sl::OFF_CI + l * LDH;
     const double* Ccol = wbc_smem + sl::OFF_CI + l;
     double a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
-#pragma unroll 2
+#pragma unroll 1
     for (int j = 0; j < NMAIN; j++) {
         const double2 t01 = ld2(t4 + j * 4), t23 = ld2(t4 + j * 4 + 2);
         const double h = H[j * LDH], c = Crow[j];
@@ -103,12 +125,16 @@ __device__ __noinline__ void eval4(double xcA, double xcB, double dA, double dB,
         r8[k] = exbA * tA[k] + exbB * tB[k];                 // tA / tB are zero on invalid lanes
         r8[4 + k] = tA[k] * a[k] + tB[k] * eb;
     }
+#pragma unroll 1
     for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
         for (int k = 0; k < 8; k++) r8[k] += __shfl_xor_sync(FULL, r8[k], o);
     }
     __syncwarp();
-    if (l < 4) wbc_smem[sl::OFF_V + V_SPARE * VLS + l] = (l == 0 ? r8[0] + 0.5 * r8[4] : l == 1 ? r8[1] + 0.5 * r8[5] : l == 2 ? r8[2] + 0.5 * r8[6] : r8[3] + 0.5 * r8[7]);
+    if (l == 0) {
+        double* f = wbc_smem + sl::OFF_V + V_SPARE * VLS;
+        f[0] = r8[0] + 0.5 * r8[4]; f[1] = r8[1] + 0.5 * r8[5]; f[2] = r8[2] + 0.5 * r8[6]; f[3] = r8[3] + 0.5 * r8[7];
+    }
     __syncwarp();
 }
 
@@ -149,7 +175,7 @@ __device__ __noinline__ bool chol_build(int n, double diagA, double diagB, int f
         // dots over m < k (k even: whole pairs)
         double p00 = 0.0, p01 = 0.0, p10 = 0.0, p11 = 0.0;     // [slot][column]
         double q00 = 0.0, q01 = 0.0, q10 = 0.0, q11 = 0.0;
-#pragma unroll 2
+#pragma unroll 1
         for (int m = 0; m < k; m += 2) {
             const double2 zk = ld2(rk + m), zk1 = ld2(rk1 + m);
             const double2 z0 = ld2(r0 + m);
@@ -213,7 +239,7 @@ __device__ __noinline__ void tri_solve(double* x, int n)
     double x0 = x[l], x1 = (c1 < n) ? x[c1] : 0.0;          // lanes >= n (n < 32) carry finite garbage that is never broadcast
     const int n0 = n < 32 ? n : 32;
     // forward: U' y = rhs, column oriented
-#pragma unroll 2
+#pragma unroll 1
     for (int k = 0; k < n0; k++) {
         const double yk = bshfl(x0 * zr0, k);
         if (l > k) x0 -= r0[k] * yk;
@@ -233,7 +259,7 @@ __device__ __noinline__ void tri_solve(double* x, int n)
         x0 -= rk[l] * xk;
         if (c1 < k) x1 -= rk[c1] * xk;
     }
-#pragma unroll 2
+#pragma unroll 1
     for (int k = n0 - 1; k >= 0; k--) {
         const double xk = bshfl(x0 * zr0, k);
         const double* rk = Z + zoff(k);
@@ -275,14 +301,12 @@ __device__ __noinline__ int quadratic_model(double dA, double dB, double gA, dou
     const double2 ed = symv(wbc_smem + sl::OFF_V + V_DC * VLS, nic2, rho);
     double s0 = dA * ed.x + dB * ed.y;       // invalid lanes carry d = 0
     double s1 = dA * gA + dB * gB;
-    double m0 = fmax(fabs(xcA), fabs(xcB)), m1 = fmax(fabs(dA), fabs(dB));
-#pragma unroll
+#pragma unroll 1
     for (int o = 16; o > 0; o >>= 1) {
         s0 += __shfl_xor_sync(FULL, s0, o);
         s1 += __shfl_xor_sync(FULL, s1, o);
-        m0 = fmax(m0, __shfl_xor_sync(FULL, m0, o));
-        m1 = fmax(m1, __shfl_xor_sync(FULL, m1, o));
     }
+    const double m0 = wmax_nn(fmax(fabs(xcA), fabs(xcB))), m1 = wmax_nn(fmax(fabs(dA), fabs(dB)));
     const double d2 = 0.5 * s0, d1 = s1;
     if ((threadIdx.x & 31) == 0) {
         wbc_smem[sl::OFF_V + V_SPARE * VLS + 4] = d1;
@@ -298,20 +322,23 @@ __device__ __noinline__ int explore(double xcB, double dB, int candB)
 {
     const int l = threadIdx.x & 31;
     double best = BIGSTEP;
-    int bi = 0x7fffffff;
     if (candB && dB < 0.0) {
-        best = safeminposrv(xcB - 0.0, -dB, BIGSTEP);
-        if (best < BIGSTEP) bi = NMAIN + l; else bi = 0x7fffffff;
+        // safeminposrv(x, y, BIGSTEP), alglibinternal.cpp:1998
+        const double y = -dB;
+        if (y >= 1.0 || xcB < BIGSTEP * y) {
+            const double r = ddiv(xcB, y);
+            if (r < best) best = r;
+        }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const double ov = __shfl_xor_sync(FULL, best, o);
-        const int oi = __shfl_xor_sync(FULL, bi, o);
-        if (ov < best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-    }
-    if (l == 0) wbc_smem[sl::OFF_V + V_SPARE * VLS + 6] = best;
+    // arg-min over non-negative doubles by bit pattern, ties to the lowest variable index
+    const unsigned hi = (unsigned)__double2hiint(best), lo = (unsigned)__double2loint(best);
+    const unsigned mh = __reduce_min_sync(FULL, hi);
+    const unsigned ml = __reduce_min_sync(FULL, hi == mh ? lo : 0xffffffffu);
+    const unsigned bi = __reduce_min_sync(FULL, (hi == mh && lo == ml) ? (unsigned)(NMAIN + l) : 0x7fffffffu);
+    const double bestall = __hiloint2double((int)mh, (int)ml);
+    if (l == 0) wbc_smem[sl::OFF_V + V_SPARE * VLS + 6] = bestall;
     __syncwarp();
-    return (best < BIGSTEP) ? bi : -1;
+    return (bestall < BIGSTEP) ? (int)bi : -1;
 }
 
 // Step selection after the quadratic model (opt.cpp:30259-30302 / 30440-30487), qqpsolver_findbeststepandmove
@@ -330,7 +357,7 @@ __device__ __noinline__ int step_and_move(double dA, double dB, double exbA, dou
     bool needact;
     int addcnt;
     if (mode == 0) {
-        const double fullstp = -d1 / (2 * d2);
+        const double fullstp = ddiv(-d1, 2 * d2);
         needact = fullstp >= stpmax;
         if (needact) { stp = stpmax; a0 = stpmax * 4; a1 = fullstp; a2 = fullstp * 0.25; addcnt = 3; }
         else { stp = fullstp; addcnt = 0; }
@@ -364,6 +391,72 @@ __device__ __noinline__ int step_and_move(double dA, double dB, double exbA, dou
     return csB;
 }
 
+// |A| statistics of E (opt.cpp:29893-29915, with its k = (i==v ? 1 : 2) quirk) over the upper triangle, and max|exb|.
+// Results in V_SPARE[8..10].
+__device__ __noinline__ void qqp_stats(int nic, double rho, double exbA, double exbB)
+{
+    const int l = threadIdx.x & 31;
+    const double* H = wbc_smem + sl::OFF_H;
+    const double* CI = wbc_smem + sl::OFF_CI;
+    double s1 = 0.0, s2 = 0.0;
+    if (l < NMAIN) {
+#pragma unroll 1
+        for (int j = l; j < NMAIN; j++) {
+            const double v = H[l * LDH + j], vv = fabs(v);
+            const double k = ((double)l == v) ? 1.0 : 2.0;
+            s1 += vv * k; s2 += vv * vv * k;
+        }
+#pragma unroll 1
+        for (int kk = 0; kk < nic; kk++) {
+            const double v = CI[kk * LDH + l], vv = fabs(v);
+            const double k = ((double)l == v) ? 1.0 : 2.0;
+            s1 += vv * k; s2 += vv * vv * k;
+        }
+    }
+    if (l < nic) {
+        const double vv = fabs(rho);
+        const double k = ((double)(NMAIN + l) == rho) ? 1.0 : 2.0;
+        s1 += vv * k; s2 += vv * vv * k;
+    }
+    s1 = wsum(s1); s2 = wsum(s2);
+    const double m1 = wmax_nn(fmax(fabs(exbA), fabs(exbB)));
+    if (l == 0) {
+        double* sp = wbc_smem + sl::OFF_V + V_SPARE * VLS;
+        sp[8] = s1; sp[9] = s2; sp[10] = m1;
+    }
+    __syncwarp();
+}
+
+// Diagonal of the constrained-Newton model with its regulariser 1e-9 * sum_j |A_ff[i][j]| over free j (opt.cpp:31150-31167),
+// in two-slot form; fixed variables get 1.  fmask: ballot of the free slack variables.
+__device__ __noinline__ double2 newton_diag(int nic, double rho, unsigned fmask)
+{
+    const int l = threadIdx.x & 31;
+    const double* H = wbc_smem + sl::OFF_H;
+    const double* CI = wbc_smem + sl::OFF_CI;
+    double2 r = make_double2(0.0, 1.0);
+    if (l < NMAIN) {
+        double v = 0.0;
+#pragma unroll 1
+        for (int j = 0; j < NMAIN; j++) v += fabs(H[j * LDH + l]);
+#pragma unroll 1
+        for (int k = 0; k < nic; k++)
+            if ((fmask >> k) & 1u) v += fabs(CI[k * LDH + l]);
+        if (v == 0.0) v = 1.0;
+        r.x = H[l * LDH + l] + 1.0e-9 * v;
+    }
+    if (l < nic && ((fmask >> l) & 1u)) {
+        const double* row = CI + l * LDH;
+        double v = 0.0;
+#pragma unroll 1
+        for (int i = 0; i < NMAIN; i++) v += fabs(row[i]);
+        v += fabs(rho);
+        if (v == 0.0) v = 1.0;
+        r.y = rho + 1.0e-9 * v;
+    }
+    return r;
+}
+
 // One QQP solve from the point exxc (in/out) on the model (H, CI, rho, exb).  Returns the QQP termination type.
 __device__ __noinline__ int qqp_optimize_fast(const Work w, int nic, double rho, double epsx, int maxouterits, int* ncholesky, double* flops_io)
 {
@@ -371,15 +464,13 @@ __device__ __noinline__ int qqp_optimize_fast(const Work w, int nic, double rho,
     const int n = NMAIN + nic;
     const int nic2 = (nic + 1) & ~1;
     const bool vA = l < NMAIN, vB = l < nic;
-    double flops = 0.0;
+    int nsymv = 0;                      // products with E (2 n^2 flops each), for the instrumented flop count
     int nchol = 0, nfree = 0, cnmodelage = 0;
     double* sxc = wbc_smem + sl::OFF_V + V_XC * VLS;
     double* sdc = wbc_smem + sl::OFF_V + V_DC * VLS;
     const double* spare = wbc_smem + sl::OFF_V + V_SPARE * VLS;
-    double* exb = wbc_smem + sl::OFF_EXB;
+    const double* exb = wbc_smem + sl::OFF_EXB;
     double* exxc = wbc_smem + sl::OFF_EXXC;
-    const double* H = wbc_smem + sl::OFF_H;
-    const double* CI = wbc_smem + sl::OFF_CI;
     // settings: qqploaddefaults (opt.cpp:29533-29547) + overrides (41318-41323)
     const int cgminits = 5;
     int cgmaxits = (int)(1 + 0.33 * n + 0.5);
@@ -388,79 +479,48 @@ __device__ __noinline__ int qqp_optimize_fast(const Work w, int nic, double rho,
     (void)w;
 
     const double exbA = vA ? exb[l] : 0.0, exbB = vB ? exb[NMAIN + l] : 0.0;
-    double xcA, xcB;
-    int csB = -1;
-    // |A| statistics (opt.cpp:29893-29915, with its k = (i==v ? 1 : 2) quirk) over the upper triangle of E; max|b|;
     // start point clipped to the bounds (29979-29998) and sasstartoptimization (27377-27399)
-    double absasum, absasum2, mb;
-    {
-        double s1 = 0.0, s2 = 0.0;
-        if (vA) {
-            for (int j = l; j < NMAIN; j++) {
-                const double v = H[l * LDH + j], vv = fabs(v);
-                const double k = ((double)l == v) ? 1.0 : 2.0;
-                s1 += vv * k; s2 += vv * vv * k;
-            }
-            for (int kk = 0; kk < nic; kk++) {
-                const double v = CI[kk * LDH + l], vv = fabs(v);
-                const double k = ((double)l == v) ? 1.0 : 2.0;
-                s1 += vv * k; s2 += vv * vv * k;
-            }
-        }
-        if (vB) {
-            const double v = rho, vv = fabs(v);
-            const double k = ((double)(NMAIN + l) == v) ? 1.0 : 2.0;
-            s1 += vv * k; s2 += vv * vv * k;
-        }
-        double m1 = fmax(fabs(exbA), fabs(exbB));
-        xcA = vA ? exxc[l] : 0.0;
-        xcB = 0.0;
-        if (vB) {
-            double v = exxc[NMAIN + l];
-            if (v <= 0.0) { v = 0.0; csB = 0; }
-            xcB = v;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            s1 += __shfl_xor_sync(FULL, s1, o);
-            s2 += __shfl_xor_sync(FULL, s2, o);
-            m1 = fmax(m1, __shfl_xor_sync(FULL, m1, o));
-        }
-        absasum = s1; absasum2 = s2; mb = m1;
-        if (vA) sxc[l] = xcA;
-        if (l < nic2) sxc[NMAIN + l] = xcB;
-        if (l < nic2) sdc[NMAIN + l] = 0.0;
-        __syncwarp();
+    double xcA = vA ? exxc[l] : 0.0, xcB = 0.0;
+    int csB = -1;
+    if (vB) {
+        double v = exxc[NMAIN + l];
+        if (v <= 0.0) { v = 0.0; csB = 0; }
+        xcB = v;
     }
+    if (vA) sxc[l] = xcA;
+    if (l < nic2) { sxc[NMAIN + l] = xcB; sdc[NMAIN + l] = 0.0; }
+    qqp_stats(nic, rho, exbA, exbB);
+    const double absasum = spare[8], absasum2 = spare[9], mb = spare[10];
     int term = 0;
     int cgmax = cgminits;
     int outerits = 0;
     double xpA = 0.0, xpB = 0.0;
+#pragma unroll 1
     for (;;) {
         if (maxouterits > 0 && outerits >= maxouterits) { term = 5; break; }
         if (outerits > 0) {
             // epsx stopping test (30137-30149)
             const double ta = xpA - xcA, tb = xpB - xcB;
-            const double v = red1(ta * ta + tb * tb);
-            if (sqrt(v) <= epsx) { term = 2; break; }
+            const double v = wsum(ta * ta + tb * tb);
+            if (dsqrt(v) <= epsx) { term = 2; break; }
         }
         outerits++;
         xpA = xcA; xpB = xcB;
         double cgpA = 0.0, cgpB = 0.0, dpA = 0.0, dpB = 0.0;
+#pragma unroll 1
         for (int cgcnt = 0; cgcnt <= cgmax - 1; cgcnt++) {
             const double2 ex = symv(sxc, nic2, rho);                            // targetgradient
             const double gA = vA ? ex.x + exbA : 0.0, gB = vB ? ex.y + exbB : 0.0;
-            flops += 2.0 * n * n;
             // sasreactivateconstraints (28992-29047), constrained gradient, CG coefficients (30199-30221)
             const bool atb = vB && xcB == 0.0;
             const bool act = atb && gB >= 0.0;
             csB = act ? 1 : -1;
             const double cgA = gA, cgB = act ? 0.0 : gB;
-            double v = cgA * cgA + cgB * cgB, vv = cgpA * cgpA + cgpB * cgpB, bf = (atb && dpB != 0.0) ? 1.0 : 0.0;
-            red3(v, vv, bf);
+            const double v = wsum(cgA * cgA + cgB * cgB), vv = wsum(cgpA * cgpA + cgpB * cgpB);
+            const bool bf = __any_sync(FULL, atb && dpB != 0.0);
             if (v <= 0.0) { term = 4; break; }      // sqrt(v) <= 0 with v a sum of squares
-            const bool brst = (bf != 0.0) || (vv == 0.0) || (cgcnt % 50 == 0);
-            const double beta = brst ? 0.0 : v / vv;
+            const bool brst = bf || (vv == 0.0) || (cgcnt % 50 == 0);
+            const double beta = brst ? 0.0 : ddiv(v, vv);
             const double dA = vA ? -cgA + beta * dpA : 0.0;
             const double dB = (vB && !act) ? -cgB + beta * dpB : 0.0;
             if (vA) sdc[l] = dA;
@@ -470,13 +530,13 @@ __device__ __noinline__ int qqp_optimize_fast(const Work w, int nic, double rho,
             const int code = quadratic_model(dA, dB, gA, gB, xcA, xcB, nic2, rho, absasum, absasum2, mb);
             const int d1est = (code >> 2) - 1, d2est = (code & 3) - 1;
             const double d1 = spare[4], d2 = spare[5];
-            flops += 2.0 * n * n;
+            nsymv += 2;
             if (d1 == 0.0 && d2 == 0.0) { term = 4; break; }
             if (d1est >= 0) { term = 7; break; }
             if (d2est <= 0 && cidx < 0) { term = -4; break; }
             csB = step_and_move(dA, dB, exbA, exbB, nic, rho, d2est > 0 ? 0 : 1, cidx, csB);
             xcA = vA ? sxc[l] : 0.0; xcB = vB ? sxc[NMAIN + l] : 0.0;
-            flops += spare[7] > 0.0 ? (1.0 + spare[7]) * 2.0 * n * n : 0.0;
+            if (spare[7] > 0.0) nsymv += 1 + (int)spare[7];
             dpA = dA; dpB = dB; cgpA = cgA; cgpB = cgB;
         }
         if (term != 0) break;
@@ -484,51 +544,31 @@ __device__ __noinline__ int qqp_optimize_fast(const Work w, int nic, double rho,
         // constrained Newton phase (30353-30527)
         int newtcnt = 0;
         int freeB = 0;
+#pragma unroll 1
         for (;;) {
             bool b;
             if (newtcnt == 0) {
                 // qqpsolver_cnewtonbuild (31058-31201): free set, regularised diagonal, factorisation
                 freeB = vB ? !(xcB == 0.0) : 0;
-                nfree = NMAIN + __popc(__ballot_sync(FULL, freeB != 0));
+                const unsigned fmask = __ballot_sync(FULL, freeB != 0);
+                nfree = NMAIN + __popc(fmask);
                 cnmodelage = 0;
                 nchol++;
-                flops += (double)n * n * n / 3.0;
-                if (nfree == 0) b = false;      // cannot happen (main variables are free); kept for fidelity
-                else {
-                    double dgA = 0.0, dgB = 1.0;
-                    const unsigned fmask = __ballot_sync(FULL, freeB != 0);
-                    if (vA) {
-                        double v = 0.0;
-                        for (int j = 0; j < NMAIN; j++) v += fabs(H[j * LDH + l]);
-                        for (int k = 0; k < nic; k++)
-                            if ((fmask >> k) & 1u) v += fabs(CI[k * LDH + l]);
-                        if (v == 0.0) v = 1.0;
-                        dgA = H[l * LDH + l] + 1.0e-9 * v;
-                    }
-                    if (vB && freeB) {
-                        const double* row = CI + l * LDH;
-                        double v = 0.0;
-                        for (int i = 0; i < NMAIN; i++) v += fabs(row[i]);
-                        v += fabs(rho);
-                        if (v == 0.0) v = 1.0;
-                        dgB = rho + 1.0e-9 * v;
-                    }
-                    b = chol_build(n, dgA, dgB, freeB);
-                }
+                const double2 dg = newton_diag(nic, rho, fmask);
+                b = chol_build(n, dg.x, dg.y, freeB);
                 if (b) cgmax = cgminits;
             } else {
                 // qqpsolver_cnewtonupdate (31314-31426)
                 const bool tofix = vB && freeB && xcB == 0.0;
                 const unsigned fixmask = __ballot_sync(FULL, tofix);
                 const int ntofix = __popc(fixmask);
-                flops += 3.0 * n * n;
+                nsymv += 2;
                 if (ntofix == 0 || ntofix == nfree) b = false;
                 else if (cnmodelage + ntofix > cnmaxupdates) b = false;
                 else {
-                    for (int k = 0; k < nic; k++) {
-                        if (!((fixmask >> k) & 1u)) continue;
-                        givens_fix(n, NMAIN + k);
-                    }
+#pragma unroll 1
+                    for (int k = 0; k < nic; k++)
+                        if ((fixmask >> k) & 1u) givens_fix(n, NMAIN + k);
                     if (tofix) freeB = 0;
                     nfree -= ntofix;
                     cnmodelage += ntofix;
@@ -541,7 +581,7 @@ __device__ __noinline__ int qqp_optimize_fast(const Work w, int nic, double rho,
             const double gA = vA ? ex.x + exbA : 0.0, gB = vB ? ex.y + exbB : 0.0;
             // qqpsolver_cnewtonstep (31474-31536), epsg = 0
             const double ngA = gA, ngB = (vB && freeB) ? gB : 0.0;
-            const double gg = red1(ngA * ngA + ngB * ngB);
+            const double gg = wsum(ngA * ngA + ngB * ngB);
             if (gg <= 0.0) break;
             if (vA) sdc[l] = -ngA;
             if (vB) sdc[NMAIN + l] = -ngB;
@@ -550,12 +590,12 @@ __device__ __noinline__ int qqp_optimize_fast(const Work w, int nic, double rho,
             const double dA = vA ? sdc[l] : 0.0, dB = vB ? sdc[NMAIN + l] : 0.0;
             const int code = quadratic_model(dA, dB, gA, gB, xcA, xcB, nic2, rho, absasum, absasum2, mb);
             const int d1est = (code >> 2) - 1, d2est = (code & 3) - 1;
-            flops += 6.0 * n * n;
+            nsymv += 3;
             if (d1est >= 0) break;
             const int cidx = explore(xcB, dB, vB && csB <= 0);
             if (d2est > 0) {
                 csB = step_and_move(dA, dB, exbA, exbB, nic, rho, 0, cidx, csB);
-                flops += spare[7] > 0.0 ? (1.0 + spare[7]) * 2.0 * n * n : 0.0;
+                if (spare[7] > 0.0) nsymv += 1 + (int)spare[7];
             } else {
                 const double stpmax = spare[6];
                 if (cidx < 0) { term = -4; break; }
@@ -565,7 +605,7 @@ __device__ __noinline__ int qqp_optimize_fast(const Work w, int nic, double rho,
                 const double2 f01 = ld2(spare);
                 if (f01.y >= f01.x) { cgmax = cgmaxits; break; }
                 csB = step_and_move(dA, dB, exbA, exbB, nic, rho, 2, cidx, csB);
-                flops += 12.0 * n * n;
+                nsymv += 6;
             }
             xcA = vA ? sxc[l] : 0.0; xcB = vB ? sxc[NMAIN + l] : 0.0;
         }
@@ -576,7 +616,7 @@ __device__ __noinline__ int qqp_optimize_fast(const Work w, int nic, double rho,
     if (vB) exxc[NMAIN + l] = (xcB < 0.0 || xcB == 0.0) ? 0.0 : xcB;
     __syncwarp();
     *ncholesky += nchol;
-    *flops_io += flops;
+    *flops_io += 2.0 * n * n * (double)nsymv + (double)nchol * ((double)n * n * n / 3.0);
     return term;
 }
 

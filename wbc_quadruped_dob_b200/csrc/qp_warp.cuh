@@ -311,10 +311,12 @@ template <bool SKIP, class Ex, class Src>
 WBC_HD bool chol_cols(const Ex& ex, double* Z, int n, double* zd, double* zrinv, int* dep, double pivtol, bool* ambiguous, const Src& src)
 {
     bool amb = false;
+#pragma unroll 1
     for (int k = 0; k < n; k++) {
         const double* rk = Z + zoff(k);
         double piv = 0.0, d0 = 0.0;
         // pass over the lanes' rows c = k + lane, k + lane + NL, ...; the pivot lane is the first of the first pass
+#pragma unroll 1
         for (int cb = k; cb < n; cb += Ex::NL) {
             const int c = cb + ex.lane();
             double acc = 0.0, a = 0.0;
@@ -323,6 +325,7 @@ WBC_HD bool chol_cols(const Ex& ex, double* Z, int n, double* zd, double* zrinv,
                 const double* rc = Z + zoff(c);
                 double s0 = 0.0, s1 = 0.0;
                 int m = 0;
+#pragma unroll 1
                 for (; m + 1 < k; m += 2) {
                     s0 += rc[m] * rk[m];
                     s1 += rc[m + 1] * rk[m + 1];
@@ -372,16 +375,20 @@ WBC_HD void tri_solve_regs(const Ex& ex, const double* Z, int n, const double* z
 {
     if (Ex::NL == 1) {
         if (forward)
+#pragma unroll 1
             for (int k = 0; k < n; k++) {
                 const double yk = x[k] * zrinv[k];
                 x[k] = yk;
+#pragma unroll 1
                 for (int i = k + 1; i < n; i++) x[i] -= Z[zoff(i) + k] * yk;
             }
         if (backward)
+#pragma unroll 1
             for (int k = n - 1; k >= 0; k--) {
                 const double xk = x[k] * zrinv[k];
                 x[k] = xk;
                 const double* rk = Z + zoff(k);
+#pragma unroll 1
                 for (int i = 0; i < k; i++) x[i] -= rk[i] * xk;
             }
         return;
@@ -396,6 +403,7 @@ WBC_HD void tri_solve_regs(const Ex& ex, const double* Z, int n, const double* z
         rows[s] = Z + zoff(i < n ? i : 0);
     }
     if (forward)
+#pragma unroll 1
         for (int k = 0; k < n; k++) {
             double v = xr[0];
 #pragma unroll
@@ -409,6 +417,7 @@ WBC_HD void tri_solve_regs(const Ex& ex, const double* Z, int n, const double* z
             }
         }
     if (backward)
+#pragma unroll 1
         for (int k = n - 1; k >= 0; k--) {
             double v = xr[0];
 #pragma unroll
@@ -670,15 +679,19 @@ WBC_HD void givens_fix_regs(const Ex& ex, double* Z, double* zd, double* zrinv, 
 {
     if (Ex::NL == 1) {
         double buf[MAXNT];
+#pragma unroll 1
         for (int j = k + 1; j < n; j++) { buf[j] = Z[zoff(j) + k]; Z[zoff(j) + k] = 0.0; }
+#pragma unroll 1
         for (int i = 0; i < k; i++) Z[zoff(k) + i] = 0.0;
         zd[k] = 1.0; zrinv[k] = 1.0;
+#pragma unroll 1
         for (int i = k + 1; i < n; i++) {
             const double bi = buf[i];
             if (bi != 0.0) {
                 double cs, sn, r;
                 generaterotation(zd[i], bi, cs, sn, r);
                 zd[i] = r; zrinv[i] = 1.0 / r; buf[i] = 0.0;
+#pragma unroll 1
                 for (int j = i + 1; j < n; j++) {
                     const double v = Z[zoff(j) + i], vv = buf[j];
                     Z[zoff(j) + i] = cs * v + sn * vv;
@@ -701,6 +714,7 @@ WBC_HD void givens_fix_regs(const Ex& ex, double* Z, double* zd, double* zrinv, 
     }
     if (l == 0) { zd[k] = 1.0; zrinv[k] = 1.0; }
     ex.sync();
+#pragma unroll 1
     for (int i = k + 1; i < n; i++) {
         double v = br[0];
 #pragma unroll
@@ -978,19 +992,26 @@ WBC_HDNI void update_lagrange_multipliers_literal(const Ex ex, const Work w, int
     double* nulcest = W_NULCEST(w);
     double flops = 0.0;
     // reference point (X0, L0) (41888-41895)
+#pragma unroll 1
     for (int i = ex.lane(); i < nq; i += Ex::NL) sv0[i] = (i < ntotal) ? exxc[i] : nulcest[i - ntotal];
+#pragma unroll 1
     for (int i = ex.lane(); i < 2 * nq * ld; i += Ex::NL) M[i] = 0.0;
     ex.sync();
     double mxdiag = 0.0;
+#pragma unroll 1
     for (int i = 0; i < NMAIN; i++) mxdiag = fmax(mxdiag, fabs(A[i * LDH + i]));
     if (mxdiag == 0.0) mxdiag = 1.0;
     const double lambdareg = 1.0e-8;
     // quadratic term and -b (41919-41927)
+#pragma unroll 1
     for (int i = 0; i < NMAIN; i++)
+#pragma unroll 1
         for (int j = ex.lane(); j <= NMAIN; j += Ex::NL)
             M[i * ld + (j < NMAIN ? j : nq)] = (j < NMAIN) ? A[i * LDH + j] : -b[i];
     // constraints (41933-41946)
+#pragma unroll 1
     for (int i = 0; i < ktotal; i++) {
+#pragma unroll 1
         for (int j = ex.lane(); j < NMAIN; j += Ex::NL) {
             const double c = -C[i * LDH + j];
             M[(ntotal + i) * ld + j] = c;
@@ -1005,24 +1026,30 @@ WBC_HDNI void update_lagrange_multipliers_literal(const Ex ex, const Work w, int
         }
     }
     // regulariser rows (41952-41959)
+#pragma unroll 1
     for (int i = ex.lane(); i < nq; i += Ex::NL) M[(nq + i) * ld + i] = lambdareg * mxdiag;
     ex.sync();
     // subtract reference point: rhs_i -= K[i,:] . sv0  (41964-41968), first nq rows only
+#pragma unroll 1
     for (int i = ex.lane(); i < nq; i += Ex::NL) {
         double s = 0.0;
+#pragma unroll 1
         for (int j = 0; j < nq; j++) s += M[i * ld + j] * sv0[j];
         M[i * ld + nq] -= s;
     }
     ex.sync();
     // active simple constraints: slack exactly zero (41973-41993)
+#pragma unroll 1
     for (int i = NMAIN; i < ntotal; i++) {
         if (exxc[i] == 0.0) {
+#pragma unroll 1
             for (int j = ex.lane(); j < 2 * nq; j += Ex::NL) M[j * ld + i] = (j == i) ? -1.0 : 0.0;
         }
     }
     ex.sync();
     flops += 2.0 * nq * nq;
     // Householder QR, M: 2nq x (nq+1) row-major.  On exit the upper triangle holds R and column nq holds Q'r.
+#pragma unroll 1
     for (int j = 0; j < nq; j++) {
         // rows involved: K rows j..nq-1 and regulariser rows nq..nq+j  -> contiguous range j..nq+j
         const int r0 = j, r1 = nq + j;   // inclusive
@@ -1030,12 +1057,14 @@ WBC_HDNI void update_lagrange_multipliers_literal(const Ex ex, const Work w, int
         // generatereflection (linalg.cpp:19116-19213) on x = M[r0..r1][j]
         const double alpha = M[r0 * ld + j];
         double mx = 0.0;
+#pragma unroll 1
         for (int r = r0 + ex.lane(); r <= r1; r += Ex::NL) { const double t = M[r * ld + j]; v[r - r0] = t; mx = fmax(mx, fabs(t)); }
         mx = red_max1(ex, mx);
         ex.sync();
         double xnorm = 0.0;
         if (mx != 0.0) {
             double s = 0.0;
+#pragma unroll 1
             for (int r = 1 + ex.lane(); r < len; r += Ex::NL) { const double t = v[r] / mx; s += t * t; }
             s = red_sum1(ex, s);
             xnorm = sqrt(s) * mx;
@@ -1048,16 +1077,20 @@ WBC_HDNI void update_lagrange_multipliers_literal(const Ex ex, const Work w, int
             if (alpha < 0.0) beta = -beta;
             tau = (beta - alpha) / beta;
             const double sc = 1.0 / (alpha - beta);
+#pragma unroll 1
             for (int r = 1 + ex.lane(); r < len; r += Ex::NL) v[r] *= sc;
             if (ex.lane() == 0) v[0] = 1.0;
         }
         ex.sync();
         if (tau != 0.0) {
             // apply H = I - tau v v' to columns j+1..nq
+#pragma unroll 1
             for (int c = j + 1 + ex.lane(); c <= nq; c += Ex::NL) {
                 double s = 0.0;
+#pragma unroll 1
                 for (int r = 0; r < len; r++) s += v[r] * M[(r0 + r) * ld + c];
                 s *= tau;
+#pragma unroll 1
                 for (int r = 0; r < len; r++) M[(r0 + r) * ld + c] -= s * v[r];
             }
             flops += 4.0 * len * (nq - j);
@@ -1066,8 +1099,10 @@ WBC_HDNI void update_lagrange_multipliers_literal(const Ex ex, const Work w, int
         ex.sync();
     }
     // back-substitution for the last ktotal unknowns (42013-42021)
+#pragma unroll 1
     for (int i = nq - 1; i >= nq - ktotal; i--) {
         double s = 0.0;
+#pragma unroll 1
         for (int jj = i + 1 + ex.lane(); jj < nq; jj += Ex::NL) s += M[i * ld + jj] * sv0[jj];
         s = red_sum1(ex, s);
         const double xi = (M[i * ld + nq] - s) / M[i * ld + i];
@@ -1076,6 +1111,7 @@ WBC_HDNI void update_lagrange_multipliers_literal(const Ex ex, const Work w, int
         ex.sync();
     }
     // sv0 is overwritten in its tail by the solution; nulcest still holds L0
+#pragma unroll 1
     for (int i = ex.lane(); i < ktotal; i += Ex::NL) nulcest[i] = nulcest[i] + sv0[ntotal + i];
     ex.sync();
     *flops_io += flops;
@@ -1117,6 +1153,7 @@ WBC_HDNI bool update_lagrange_multipliers_reduced(const Ex ex, const Work w, int
     double flops = 0.0;
     // ---- active list, in row order (ballot compaction)
     int ka = 0;
+#pragma unroll 1
     for (int base = 0; base < ktotal; base += Ex::NL) {
         const int r = base + ex.lane();
         const bool on = (r < ktotal) && ((r < nec) || (exxc[NMAIN + (r - nec)] == 0.0));
@@ -1143,17 +1180,21 @@ WBC_HDNI bool update_lagrange_multipliers_reduced(const Ex ex, const Work w, int
     double* nu0 = vv + 7 * VLS;
     {
         const double* LA = W_LA(w);
+#pragma unroll 1
         for (int i = ex.lane(); i < 450; i += Ex::NL) LAs[i] = LA[i];
     }
     ex.sync();
     // ---- forward substitutions U' y = c_m, one lane per right-hand side
+#pragma unroll 1
     for (int m = ex.lane(); m <= ka; m += Ex::NL) {
         double* y = &Wm[m * LDH];
         const double* src = (m < ka) ? &C[act[m] * LDH] : W_B(w);
+#pragma unroll 1
         for (int i = 0; i < NMAIN; i++) {
             const double* li = LAs + zoff(i);
             double s0 = src[i], s1 = 0.0;
             int k = 0;
+#pragma unroll 1
             for (; k + 1 < i; k += 2) { s0 -= li[k] * y[k]; s1 -= li[k + 1] * y[k + 1]; }
             if (k < i) s0 -= li[k] * y[k];
             y[i] = (s0 + s1) * larinv[i];
@@ -1164,24 +1205,28 @@ WBC_HDNI bool update_lagrange_multipliers_reduced(const Ex ex, const Work w, int
     ex.sync();
     // ---- Schur complement S = W W' (packed lower + diagonal vector)
     const int npairs = ka * (ka + 1) / 2;
+#pragma unroll 1
     for (int e = ex.lane(); e < npairs; e += Ex::NL) {
         int c, r;
         tri_index_lower(e, c, r);
         const double* wr = &Wm[r * LDH];
         const double* wc = &Wm[c * LDH];
         double s0 = 0.0, s1 = 0.0;
-#pragma unroll 5
+#pragma unroll 1
         for (int k = 0; k < NMAIN; k += 2) { s0 += wr[k] * wc[k]; s1 += wr[k + 1] * wc[k + 1]; }
         if (r == c) sd[r] = s0 + s1; else Sm[zoff(c) + r] = s0 + s1;
     }
     ex.sync();
     // rho = d + W t - S nu0
+#pragma unroll 1
     for (int m = ex.lane(); m < ka; m += Ex::NL) {
         const double* wm = &Wm[m * LDH];
         const double* wt = &Wm[ka * LDH];
         double sacc = wm[NMAIN];
+#pragma unroll 1
         for (int k = 0; k < NMAIN; k++) sacc += wm[k] * wt[k];
         double sn = sd[m] * nu0[m];
+#pragma unroll 1
         for (int k = 0; k < ka; k++)
             if (k != m) sn += ((k < m) ? Sm[zoff(m) + k] : Sm[zoff(k) + m]) * nu0[k];
         rho_[m] = sacc - sn;
@@ -1198,6 +1243,7 @@ WBC_HDNI bool update_lagrange_multipliers_reduced(const Ex ex, const Work w, int
     if (ambiguous) return false;
     flops += (double)ka * ka * ka / 3.0 + 2.0 * ka * ka;
     double ndep = 0.0;
+#pragma unroll 1
     for (int m = ex.lane(); m < ka; m += Ex::NL) ndep += dep[m];
     ndep = red_sum1(ex, ndep);
     if (ndep == 0.0) {
@@ -1205,6 +1251,7 @@ WBC_HDNI bool update_lagrange_multipliers_reduced(const Ex ex, const Work w, int
     } else {
         // G = Lt'Lt over the kept columns (identity on the skipped ones), u = Lt' rho.
         // Lt[i][a] = U[a][i] = Sm(i, a) (a < i), Lt[a][a] = sd[a]; skipped columns are exact zeros.
+#pragma unroll 1
         for (int e = ex.lane(); e < npairs; e += Ex::NL) {
             int c, a;
             tri_index_lower(e, c, a);            // a <= c
@@ -1212,12 +1259,15 @@ WBC_HDNI bool update_lagrange_multipliers_reduced(const Ex ex, const Work w, int
             if (dep[a] || dep[c]) sacc = (a == c) ? 1.0 : 0.0;
             else {
                 sacc = ((a == c) ? sd[c] : Sm[zoff(c) + a]) * sd[c];
+#pragma unroll 1
                 for (int i = c + 1; i < ka; i++) sacc += Sm[zoff(i) + a] * Sm[zoff(i) + c];
             }
             if (a == c) gd[a] = sacc; else G[zoff(c) + a] = sacc;
         }
+#pragma unroll 1
         for (int a = ex.lane(); a < ka; a += Ex::NL) {
             double sacc = sd[a] * rho_[a];
+#pragma unroll 1
             for (int i = a + 1; i < ka; i++) sacc += Sm[zoff(i) + a] * rho_[i];
             u1[a] = dep[a] ? 0.0 : sacc;
         }
@@ -1230,8 +1280,10 @@ WBC_HDNI bool update_lagrange_multipliers_reduced(const Ex ex, const Work w, int
         tri_solve<false>(ex, G, ka, grinv, u1, true, true);
         // consistency: Lt u1 is the projection of rho on range(S); it must reproduce rho
         double mm[2] = {0.0, 0.0};
+#pragma unroll 1
         for (int i = ex.lane(); i < ka; i += Ex::NL) {
             double sacc = sd[i] * u1[i];
+#pragma unroll 1
             for (int a = 0; a < i; a++) sacc += Sm[zoff(i) + a] * u1[a];
             mm[0] = fmax(mm[0], fabs(sacc - rho_[i]));
             mm[1] = fmax(mm[1], fabs(C[act[i] * LDH + NMAIN]));
@@ -1239,8 +1291,10 @@ WBC_HDNI bool update_lagrange_multipliers_reduced(const Ex ex, const Work w, int
         red_max<2>(ex, mm);
         if (mm[0] > 1.0e-9 * (mm[1] + 1.0)) return false;
         tri_solve<false>(ex, G, ka, grinv, u1, true, true);
+#pragma unroll 1
         for (int i = ex.lane(); i < ka; i += Ex::NL) {
             double sacc = sd[i] * u1[i];
+#pragma unroll 1
             for (int a = 0; a < i; a++) sacc += Sm[zoff(i) + a] * u1[a];
             dl[i] = sacc;
         }
@@ -1248,8 +1302,10 @@ WBC_HDNI bool update_lagrange_multipliers_reduced(const Ex ex, const Work w, int
         flops += 4.0 * ka * ka * ka / 3.0;
         *flags_io |= 16;
     }
+#pragma unroll 1
     for (int i = ex.lane(); i < ktotal; i += Ex::NL) nulcest[i] = 0.0;
     ex.sync();
+#pragma unroll 1
     for (int m = ex.lane(); m < ka; m += Ex::NL) nulcest[act[m]] = nu0[m] + dl[m];
     ex.sync();
     *flops_io += flops;
@@ -1285,16 +1341,19 @@ WBC_HDNI void generate_ex_model(const Ex ex, const Work w, int nec, int nic, dou
     else {
         double* st = QS<false>::Z(w);
         const double* Cg = W_C(w);
+#pragma unroll 1
         for (int e = ex.lane(); e < kw * LDH; e += Ex::NL) st[e] = Cg[e];
         ex.sync();
         Cs = st;
     }
     // quadratic term, main block: A + rho * C'C
+#pragma unroll 1
     for (int e = ex.lane(); e < 465; e += Ex::NL) {
         int i, j;
         tri_index30(e, i, j);
         double s0 = 0.0, s1 = 0.0;
         int r = 0;
+#pragma unroll 1
         for (; r + 1 < kw; r += 2) {
             s0 += Cs[r * LDH + i] * Cs[r * LDH + j];
             s1 += Cs[(r + 1) * LDH + i] * Cs[(r + 1) * LDH + j];
@@ -1305,17 +1364,21 @@ WBC_HDNI void generate_ex_model(const Ex ex, const Work w, int nec, int nic, dou
         H[j * LDH + i] = v;
     }
     // slack columns (shared-memory case: a zero row pads the count to even for the two-at-a-time products)
+#pragma unroll 1
     for (int e = ex.lane(); e < nic * LDH; e += Ex::NL) {
         const int k = e / LDH, i = e - k * LDH;
         if (i < NMAIN) CI[k * LDH + i] = 0.0 + rho * Cs[(nec + k) * LDH + i];
     }
     if (!SPILL && (nic & 1))
+#pragma unroll 1
         for (int i = ex.lane(); i < LDH; i += Ex::NL) CI[nic * LDH + i] = 0.0;
     // linear term (41650-41657, 41734-41737): per element, rows in order, two updates per row
+#pragma unroll 1
     for (int i = ex.lane(); i < n; i += Ex::NL) {
         double v;
         if (i < NMAIN) {
             v = W_B(w)[i];
+#pragma unroll 1
             for (int r = 0; r < kw; r++) {
                 const double c = Cs[r * LDH + i];
                 v += c * (-rho * Cs[r * LDH + NMAIN]);
@@ -1346,14 +1409,17 @@ WBC_HDNI void update_working_set(const Ex ex, const Work w, int nec, int nictota
     double* exxc = W_EXXC(w);
     double* nulc = W_NULC(w);
     int extended = 0, added = 0;
+#pragma unroll 1
     while ((double)added < 1 + 0.20 * NMAIN && nicwork < nictotal) {
         // k = argmax_{j >= nicwork} nicerr[j], first maximum
         double bv = -1.7976931348623157e308;
         int bk = 0x7fffffff;
+#pragma unroll 1
         for (int j = nicwork + l; j < nictotal; j += Ex::NL) {
             const double v = nicerr[j];
             if (v > bv) { bv = v; bk = j; }
         }
+#pragma unroll 1
         for (int o = Ex::NL / 2; o > 0; o >>= 1) {
             const double ov = ex.shfl_xor(bv, o);
             const int ok = ex.shfl_xori(bk, o);
@@ -1363,6 +1429,7 @@ WBC_HDNI void update_working_set(const Ex ex, const Work w, int nec, int nictota
         if (!(bv > 0.0)) break;
         // swap rows nec+nicwork <-> nec+k of C, and the per-constraint bookkeeping
         if (k != nicwork) {
+#pragma unroll 1
             for (int j = l; j < LDH; j += Ex::NL) {
                 const double t = C[(nec + nicwork) * LDH + j];
                 C[(nec + nicwork) * LDH + j] = C[(nec + k) * LDH + j];
@@ -1381,11 +1448,13 @@ WBC_HDNI void update_working_set(const Ex ex, const Work w, int nec, int nictota
         extended = 1;
     }
     if (allowevict) {
+#pragma unroll 1
         for (int k = nicwork - 1; k >= 0; k--) {
             if (nicerr[k] < -0.01 && nicnact[k] <= 1) {
                 const int last = nicwork - 1;
                 ex.sync();
                 if (k != last) {
+#pragma unroll 1
                     for (int j = l; j < LDH; j += Ex::NL) {
                         const double t = C[(nec + last) * LDH + j];
                         C[(nec + last) * LDH + j] = C[(nec + k) * LDH + j];
@@ -1421,6 +1490,7 @@ WBC_HDNI int setup_problem(const Ex ex, const Work w, int nrows, int* pd_out)
     double* stage = SM_(w, sl::OFF_CI);                 // CI | Z: 1710 doubles = 55 staged rows
     constexpr int CHUNK = 55;
     double bad = 0.0;
+#pragma unroll 1
     for (int i = ex.lane(); i < NMAIN; i += Ex::NL) {
         const double d = As[i * LDH + i];
         if (d <= 0.0) bad = 1.0;
@@ -1431,6 +1501,7 @@ WBC_HDNI int setup_problem(const Ex ex, const Work w, int nrows, int* pd_out)
     if (bad != 0.0) return -9;
     // A <- S A S from the lower triangle, mirrored; Frobenius norm
     double an = 0.0;
+#pragma unroll 1
     for (int e = ex.lane(); e < 465; e += Ex::NL) {
         int i, j;
         tri_index30(e, i, j);                           // i <= j: element (j, i) of the lower triangle
@@ -1439,18 +1510,23 @@ WBC_HDNI int setup_problem(const Ex ex, const Work w, int nrows, int* pd_out)
         As[j * LDH + i] = v;
         an += (i == j) ? v * v : 2.0 * (v * v);
     }
+#pragma unroll 1
     for (int i = ex.lane(); i < NMAIN; i += Ex::NL) b[i] = W_EXB(w)[i] * sc[i];
     an = sqrt(red_sum1(ex, an));
     ex.sync();
     // constraint rows in chunks through shared memory: scale by S, normalise (42219-42314), c_r' A c_r
     double maxcac = 0.0;
+#pragma unroll 1
     for (int r0 = 0; r0 < nrows; r0 += CHUNK) {
         const int nr = (nrows - r0 < CHUNK) ? nrows - r0 : CHUNK;
+#pragma unroll 1
         for (int e = ex.lane(); e < nr * LDH; e += Ex::NL) stage[e] = C[r0 * LDH + e];
         ex.sync();
+#pragma unroll 1
         for (int r = ex.lane(); r < nr; r += Ex::NL) {
             double* row = stage + r * LDH;
             double vv = 0.0;
+#pragma unroll 1
             for (int j = 0; j < NMAIN; j++) {
                 const double v = row[j] * sc[j];
                 row[j] = v;
@@ -1460,16 +1536,19 @@ WBC_HDNI int setup_problem(const Ex ex, const Work w, int nrows, int* pd_out)
             vv = sqrt(vv);
             if (vv > 0.0) {
                 vv = 1.0 / vv;
+#pragma unroll 1
                 for (int j = 0; j < NMAIN; j++) row[j] *= vv;
                 rhs *= vv;
             }
             row[NMAIN] = rhs;
             // exact zeros of the row are skipped (they add nothing)
             double v = 0.0;
+#pragma unroll 1
             for (int j = 0; j < NMAIN; j++) {
                 const double cj = row[j];
                 if (cj == 0.0) continue;
                 double t = 0.0;
+#pragma unroll 1
                 for (int k = 0; k < NMAIN; k++) {
                     const double ck = row[k];
                     if (ck != 0.0) t += ck * As[k * LDH + j];
@@ -1479,6 +1558,7 @@ WBC_HDNI int setup_problem(const Ex ex, const Work w, int nrows, int* pd_out)
             maxcac = fmax(maxcac, fabs(v));
         }
         ex.sync();
+#pragma unroll 1
         for (int e = ex.lane(); e < nr * LDH; e += Ex::NL) C[r0 * LDH + e] = stage[e];
         ex.sync();
     }
@@ -1487,11 +1567,13 @@ WBC_HDNI int setup_problem(const Ex ex, const Work w, int nrows, int* pd_out)
     if (targetscale == 0.0) targetscale = 1.0;
     const double v = 1.0 / targetscale;
     double* Ag = W_A(w);
+#pragma unroll 1
     for (int e = ex.lane(); e < NMAIN * LDH; e += Ex::NL) {
         const double a = As[e] * v;
         As[e] = a;
         Ag[e] = a;
     }
+#pragma unroll 1
     for (int i = ex.lane(); i < NMAIN; i += Ex::NL) b[i] *= v;
     ex.sync();
     // Cholesky of A: convexity test (42474-42523); the factor is kept for the reduced multiplier update
@@ -1504,6 +1586,7 @@ WBC_HDNI int setup_problem(const Ex ex, const Work w, int nrows, int* pd_out)
     src.A = As;
     const bool pd = chol_cols<false>(ex, Zs, NMAIN, ladiag, W_LARINV(w), (int*)nullptr, 0.0, (bool*)nullptr, src);
     double* LA = W_LA(w);
+#pragma unroll 1
     for (int i = ex.lane(); i < 450; i += Ex::NL) LA[i] = Zs[i];
     ex.sync();
     *pd_out = pd ? 1 : 0;
@@ -1555,8 +1638,11 @@ WBC_HDN void solve_denseaul(const Ex& ex, const Work& w, const Settings& cfg, in
     double* nulcest = W_NULCEST(w);
     double* exxc = W_EXXC(w);
     const double* C = W_C(w);
+#pragma unroll 1
     for (int i = ex.lane(); i < nictotal; i += Ex::NL) W_NICNACT(w)[i] = (i < nicwork) ? 1 : 0;
+#pragma unroll 1
     for (int i = ex.lane(); i < nrows; i += Ex::NL) nulc[i] = 0.0;
+#pragma unroll 1
     for (int i = ex.lane(); i < NMAIN + nictotal; i += Ex::NL) exxc[i] = 0.0;
     ex.sync();
 
@@ -1565,6 +1651,7 @@ WBC_HDN void solve_denseaul(const Ex& ex, const Work& w, const Settings& cfg, in
     const double maxrho = 1.0e12, requestedfeasdecrease = 0.33;
     int goodcounter = 0, stagnationcounter = 0;
     double feaserr = 1.7976931348623157e308;   // ae_maxrealnumber
+#pragma unroll 1
     for (int outeridx = 0; outeridx < cfg.outerits; outeridx++) {
         st.outer_its++;
         bool extended;
@@ -1580,9 +1667,11 @@ WBC_HDN void solve_denseaul(const Ex& ex, const Work& w, const Settings& cfg, in
             st.qqp_calls++;
             if (term == -4) st.flags |= 4;
             // violations of all inequality rows w.r.t. the main variables only (41330-41335)
+#pragma unroll 1
             for (int i = ex.lane(); i < nictotal; i += Ex::NL) {
                 const double* row = &C[(nec + i) * LDH];
                 double v0 = 0.0, v1 = 0.0;
+#pragma unroll 1
                 for (int j = 0; j < NMAIN; j += 2) { v0 += row[j] * exxc[j]; v1 += row[j + 1] * exxc[j + 1]; }
                 nicerr[i] = (v0 + v1) - row[NMAIN];
             }
@@ -1596,6 +1685,7 @@ WBC_HDN void solve_denseaul(const Ex& ex, const Work& w, const Settings& cfg, in
 
         const int kwork = nec + nicwork;
         // multiplier estimate (41438-41439)
+#pragma unroll 1
         for (int i = ex.lane(); i < kwork; i += Ex::NL) nulcest[i] = nulc[i];
         ex.sync();
         {
@@ -1606,6 +1696,7 @@ WBC_HDN void solve_denseaul(const Ex& ex, const Work& w, const Settings& cfg, in
                 done = update_lagrange_multipliers_reduced(ex, w, nec, nicwork, cfg.kkt_pivtol, &st.flags, &st.flops);
             if (!done) {
                 st.flags |= 8;
+#pragma unroll 1
                 for (int i = ex.lane(); i < kwork; i += Ex::NL) nulcest[i] = nulc[i];
                 ex.sync();
                 update_lagrange_multipliers_literal(ex, w, nec, nicwork, &st.flops);
@@ -1614,9 +1705,11 @@ WBC_HDN void solve_denseaul(const Ex& ex, const Work& w, const Settings& cfg, in
         // feasibility error and multiplier update (41444-41476): lane-per-row, summed by the warp
         const double feaserrprev = feaserr;
         double fe = 0.0;
+#pragma unroll 1
         for (int i = ex.lane(); i < kwork; i += Ex::NL) {
             const double* row = &C[i * LDH];
             double v = 0.0, vv = 0.0;
+#pragma unroll 1
             for (int j = 0; j < NMAIN; j++) { const double c = row[j]; v += c * exxc[j]; vv += c * c; }
             if (i >= nec) { v += exxc[NMAIN + (i - nec)]; vv += 1.0; }
             v -= row[NMAIN];
@@ -1636,6 +1729,7 @@ WBC_HDN void solve_denseaul(const Ex& ex, const Work& w, const Settings& cfg, in
     }
     st.nicwork = nicwork;
     // unscale (41548-41583): x = s * xc  (+ origin 0); no box constraints on x
+#pragma unroll 1
     for (int i = ex.lane(); i < NMAIN; i += Ex::NL) W_XS(w)[i] = W_SC(w)[i] * exxc[i] + 0.0;
     ex.sync();
     st.termination = 2;
