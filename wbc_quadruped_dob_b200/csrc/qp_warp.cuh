@@ -52,7 +52,7 @@ constexpr int MAXNT = NMAIN + MAXNIC;  // extended variable count upper bound
 constexpr int NICCAP = 18;             // working inequality rows held in shared memory
 constexpr int NCAP = NMAIN + NICCAP;   // 48
 constexpr int LDH = 31;                // leading dimension of H, CI, C, A (odd: conflict-free both ways)
-constexpr int KACAP = 33;              // largest active set the reduced multiplier update handles
+constexpr int KACAP = 36;              // largest active set the reduced multiplier update handles
 constexpr int NVEC = 16;               // QQP vectors
 constexpr int VLS = 48, VLG = 104;     // vector length: shared / spill copy
 constexpr double MACHEPS = 5.0e-16;    // ae_machineepsilon (ap.cpp: 5E-16, NOT DBL_EPSILON)
@@ -1087,10 +1087,10 @@ WBC_HDNI void update_lagrange_multipliers_literal(const Ex ex, const Work w, int
 #pragma unroll 1
             for (int c = j + 1 + ex.lane(); c <= nq; c += Ex::NL) {
                 double s = 0.0;
-#pragma unroll 1
+#pragma unroll 8
                 for (int r = 0; r < len; r++) s += v[r] * M[(r0 + r) * ld + c];
                 s *= tau;
-#pragma unroll 1
+#pragma unroll 8
                 for (int r = 0; r < len; r++) M[(r0 + r) * ld + c] -= s * v[r];
             }
             flops += 4.0 * len * (nq - j);
@@ -1163,12 +1163,18 @@ WBC_HDNI bool update_lagrange_multipliers_reduced(const Ex ex, const Work w, int
         ka += ex.popc(m);
     }
     ex.sync();
-    if (ka > KACAP) return false;
+    if (ka > KACAP) {
+#ifdef WBC_EMU_DEBUG
+        printf("fallback ka=%d > KACAP\n", ka);
+#endif
+        return false;
+    }
     double* big = W_BIG(w);
-    double* Wm = big;                              // [KACAP+1][31]: U^-T c_m | d_m ; last row: t        (1054)
-    double* Sm = big + (KACAP + 1) * LDH;          // packed lower Schur complement / factor, zoff(33) = 544
-    double* G = Sm + 544;                          // packed lower, 544
-    double* LAs = G + 544;                         // packed factor of A, 450  -> 2592 <= 2640
+    double* Wm = big;                              // [KACAP+1][31]: U^-T c_m | d_m ; last row: t        (1147)
+    double* Sm = big + (KACAP + 1) * LDH + 1;      // packed lower Schur complement / factor, zoff(36) = 648
+    double* G = big;                               // packed lower, 648: overlays Wm, which is dead by then
+    double* LAs = Sm + 648;                        // packed factor of A, 450  -> 2246 <= 2640
+    static_assert((KACAP + 1) * LDH + 1 + 648 + 450 <= sl::BIG, "reduced multiplier update workspace");
     double* vv = W_VEC(w);
     double* sd = vv;
     double* srinv = vv + VLS;
@@ -1240,7 +1246,12 @@ WBC_HDNI bool update_lagrange_multipliers_reduced(const Ex ex, const Work w, int
         src.Z = Sm; src.diag = sd;
         chol_cols<true>(ex, Sm, ka, sd, srinv, dep, pivtol, &ambiguous, src);
     }
-    if (ambiguous) return false;
+    if (ambiguous) {
+#ifdef WBC_EMU_DEBUG
+        printf("fallback ambiguous ka=%d\n", ka);
+#endif
+        return false;
+    }
     flops += (double)ka * ka * ka / 3.0 + 2.0 * ka * ka;
     double ndep = 0.0;
 #pragma unroll 1
@@ -1289,7 +1300,12 @@ WBC_HDNI bool update_lagrange_multipliers_reduced(const Ex ex, const Work w, int
             mm[1] = fmax(mm[1], fabs(C[act[i] * LDH + NMAIN]));
         }
         red_max<2>(ex, mm);
-        if (mm[0] > 1.0e-9 * (mm[1] + 1.0)) return false;
+        if (mm[0] > 1.0e-9 * (mm[1] + 1.0)) {
+#ifdef WBC_EMU_DEBUG
+            printf("fallback inconsistent ka=%d worst=%.3e scale=%.3e\n", ka, mm[0], mm[1]);
+#endif
+            return false;
+        }
         tri_solve<false>(ex, G, ka, grinv, u1, true, true);
 #pragma unroll 1
         for (int i = ex.lane(); i < ka; i += Ex::NL) {
@@ -1341,7 +1357,7 @@ WBC_HDNI void generate_ex_model(const Ex ex, const Work w, int nec, int nic, dou
     else {
         double* st = QS<false>::Z(w);
         const double* Cg = W_C(w);
-#pragma unroll 1
+#pragma unroll 4
         for (int e = ex.lane(); e < kw * LDH; e += Ex::NL) st[e] = Cg[e];
         ex.sync();
         Cs = st;
@@ -1519,7 +1535,7 @@ WBC_HDNI int setup_problem(const Ex ex, const Work w, int nrows, int* pd_out)
 #pragma unroll 1
     for (int r0 = 0; r0 < nrows; r0 += CHUNK) {
         const int nr = (nrows - r0 < CHUNK) ? nrows - r0 : CHUNK;
-#pragma unroll 1
+#pragma unroll 4
         for (int e = ex.lane(); e < nr * LDH; e += Ex::NL) stage[e] = C[r0 * LDH + e];
         ex.sync();
 #pragma unroll 1
@@ -1541,28 +1557,31 @@ WBC_HDNI int setup_problem(const Ex ex, const Work w, int nrows, int* pd_out)
                 rhs *= vv;
             }
             row[NMAIN] = rhs;
-            // exact zeros of the row are skipped (they add nothing)
-            double v = 0.0;
+        }
+        ex.sync();
+        // c_r' A c_r, one row at a time across the lanes (lane = column): the zero test on c_rk is warp-uniform,
+        // so sparse rows cost their non-zero count (exact zeros add nothing)
 #pragma unroll 1
-            for (int j = 0; j < NMAIN; j++) {
+        for (int r = 0; r < nr; r++) {
+            const double* row = stage + r * LDH;
+            double part = 0.0;
+#pragma unroll 1
+            for (int j = ex.lane(); j < NMAIN; j += Ex::NL) {
                 const double cj = row[j];
-                if (cj == 0.0) continue;
                 double t = 0.0;
 #pragma unroll 1
                 for (int k = 0; k < NMAIN; k++) {
                     const double ck = row[k];
                     if (ck != 0.0) t += ck * As[k * LDH + j];
                 }
-                v += t * cj;
+                part += t * cj;
             }
-            maxcac = fmax(maxcac, fabs(v));
+            maxcac = fmax(maxcac, fabs(red_sum1(ex, part)));
         }
-        ex.sync();
-#pragma unroll 1
+#pragma unroll 4
         for (int e = ex.lane(); e < nr * LDH; e += Ex::NL) C[r0 * LDH + e] = stage[e];
         ex.sync();
     }
-    maxcac = red_max1(ex, maxcac);
     double targetscale = fmax(maxcac, an / NMAIN);
     if (targetscale == 0.0) targetscale = 1.0;
     const double v = 1.0 / targetscale;
@@ -1617,6 +1636,72 @@ __device__ __forceinline__ int model_and_qqp_dev(const WarpEx& ex, const Work& w
 }
 #endif
 
+// ------------------------------------------------------------------------------------------------
+// Row-wise products with the constraint matrix.  C lives in global memory (row-major), so rows are first copied --
+// coalesced -- into the idle factor array in shared memory, then each lane takes a row (stride 31: conflict free).
+constexpr int STAGE_ROWS = 1152 / LDH;      // 37
+template <class Ex>
+WBC_HD const double* stage_rows(const Ex& ex, const Work& w, int row0, int nr)
+{
+    double* st = SM_(w, sl::OFF_Z);
+    const double* Cg = W_C(w) + row0 * LDH;
+#pragma unroll 4
+    for (int e = ex.lane(); e < nr * LDH; e += Ex::NL) st[e] = Cg[e];
+    ex.sync();
+    return st;
+}
+// violations of all inequality rows w.r.t. the main variables only (opt.cpp:41330-41335)
+template <class Ex>
+WBC_HDNI void inequality_violations(const Ex ex, const Work w, int nec, int nictotal)
+{
+    double* nicerr = W_NICERR(w);
+    const double* exxc = W_EXXC(w);
+#pragma unroll 1
+    for (int i0 = 0; i0 < nictotal; i0 += STAGE_ROWS) {
+        const int nr = (nictotal - i0 < STAGE_ROWS) ? nictotal - i0 : STAGE_ROWS;
+        const double* st = stage_rows(ex, w, nec + i0, nr);
+#pragma unroll 1
+        for (int i = ex.lane(); i < nr; i += Ex::NL) {
+            const double* row = st + i * LDH;
+            double v0 = 0.0, v1 = 0.0;
+#pragma unroll 1
+            for (int j = 0; j < NMAIN; j += 2) { v0 += row[j] * exxc[j]; v1 += row[j + 1] * exxc[j + 1]; }
+            nicerr[i0 + i] = (v0 + v1) - row[NMAIN];
+        }
+        ex.sync();
+    }
+}
+// feasibility error over the working rows and the multiplier hand-over (opt.cpp:41444-41476); returns sum of squares
+template <class Ex>
+WBC_HDNI double feasibility_error(const Ex ex, const Work w, int nec, int kwork)
+{
+    const double* exxc = W_EXXC(w);
+    double* nulc = W_NULC(w);
+    const double* nulcest = W_NULCEST(w);
+    double fe = 0.0;
+#pragma unroll 1
+    for (int i0 = 0; i0 < kwork; i0 += STAGE_ROWS) {
+        const int nr = (kwork - i0 < STAGE_ROWS) ? kwork - i0 : STAGE_ROWS;
+        const double* st = stage_rows(ex, w, i0, nr);
+#pragma unroll 1
+        for (int ii = ex.lane(); ii < nr; ii += Ex::NL) {
+            const int i = i0 + ii;
+            const double* row = st + ii * LDH;
+            double v = 0.0, vv = 0.0;
+#pragma unroll 1
+            for (int j = 0; j < NMAIN; j++) { const double c = row[j]; v += c * exxc[j]; vv += c * c; }
+            if (i >= nec) { v += exxc[NMAIN + (i - nec)]; vv += 1.0; }
+            v -= row[NMAIN];
+            if (vv == 0.0) vv = 1.0;
+            v = v / sqrt(vv);
+            fe += v * v;
+            nulc[i] = nulcest[i];
+        }
+        ex.sync();
+    }
+    return red_sum1(ex, fe);
+}
+
 // The solver.  On entry the warp has staged the problem (see setup_problem).  Result: xs[0..30) in shared memory.
 template <class Ex>
 WBC_HDN void solve_denseaul(const Ex& ex, const Work& w, const Settings& cfg, int nrows, int neq, Stats& st)
@@ -1633,11 +1718,9 @@ WBC_HDN void solve_denseaul(const Ex& ex, const Work& w, const Settings& cfg, in
     int allowevict = 1;
     if (!pd) { nicwork = nictotal; allowevict = 0; st.flags |= 1; }
     const bool have_factor = pd != 0;
-    double* nicerr = W_NICERR(w);
     double* nulc = W_NULC(w);
     double* nulcest = W_NULCEST(w);
     double* exxc = W_EXXC(w);
-    const double* C = W_C(w);
 #pragma unroll 1
     for (int i = ex.lane(); i < nictotal; i += Ex::NL) W_NICNACT(w)[i] = (i < nicwork) ? 1 : 0;
 #pragma unroll 1
@@ -1666,16 +1749,7 @@ WBC_HDN void solve_denseaul(const Ex& ex, const Work& w, const Settings& cfg, in
 #endif
             st.qqp_calls++;
             if (term == -4) st.flags |= 4;
-            // violations of all inequality rows w.r.t. the main variables only (41330-41335)
-#pragma unroll 1
-            for (int i = ex.lane(); i < nictotal; i += Ex::NL) {
-                const double* row = &C[(nec + i) * LDH];
-                double v0 = 0.0, v1 = 0.0;
-#pragma unroll 1
-                for (int j = 0; j < NMAIN; j += 2) { v0 += row[j] * exxc[j]; v1 += row[j + 1] * exxc[j + 1]; }
-                nicerr[i] = (v0 + v1) - row[NMAIN];
-            }
-            ex.sync();
+            inequality_violations(ex, w, nec, nictotal);
             st.flops += 2.0 * nictotal * NMAIN;
             update_working_set(ex, w, nec, nictotal, nicwork, allowevict);
             nicwork = W_ISCR(w)[1];
@@ -1702,23 +1776,8 @@ WBC_HDN void solve_denseaul(const Ex& ex, const Work& w, const Settings& cfg, in
                 update_lagrange_multipliers_literal(ex, w, nec, nicwork, &st.flops);
             }
         }
-        // feasibility error and multiplier update (41444-41476): lane-per-row, summed by the warp
         const double feaserrprev = feaserr;
-        double fe = 0.0;
-#pragma unroll 1
-        for (int i = ex.lane(); i < kwork; i += Ex::NL) {
-            const double* row = &C[i * LDH];
-            double v = 0.0, vv = 0.0;
-#pragma unroll 1
-            for (int j = 0; j < NMAIN; j++) { const double c = row[j]; v += c * exxc[j]; vv += c * c; }
-            if (i >= nec) { v += exxc[NMAIN + (i - nec)]; vv += 1.0; }
-            v -= row[NMAIN];
-            if (vv == 0.0) vv = 1.0;
-            v = v / sqrt(vv);
-            fe += v * v;
-            nulc[i] = nulcest[i];
-        }
-        feaserr = sqrt(red_sum1(ex, fe));
+        feaserr = sqrt(feasibility_error(ex, w, nec, kwork));
         ex.sync();
         st.flops += 4.0 * kwork * NMAIN;
         if (feaserr < epsx) goodcounter++; else goodcounter = 0;
