@@ -67,8 +67,9 @@ private:
 class OPT {
 public:
     OPT(int control_variables, int stance_constraint, int swing_constraint, int device = 0)
-        : ctx_(1, device), Q_(900, 0.0), c_(30, 0.0), Ls_(86 * 31, 0.0), Lw_(82 * 31, 0.0), swallow_failures(false), last_status(0)
+        : swallow_failures(false), last_status(0), ctx_(1, device), Q_(900, 0.0), c_(30, 0.0), Ls_(86 * 31, 0.0), Lw_(82 * 31, 0.0)
     {
+        for (int i = 0; i < 8; i++) last_info[i] = 0;
         if (control_variables != 30 || stance_constraint != 86 || swing_constraint != 82)
             throw Error(WBC_EINVAL, "OPT is specialised to the controller's shapes OPT(30, 86, 82) (main.cpp:266)");
     }
