@@ -39,7 +39,13 @@ IN_BYTES = 8 * 93 + 4     # algorithmic input bytes per instance (flat ground)
 OUT_BYTES = 8 * 18        # tau + w
 
 
+SWEEP = "push_sweep"          # BASELINE config 5: closed-loop disturbance-rejection sweep, fixed 262144-instance grid
+SWEEP_TOTAL = S.SWEEP_DIRECTIONS * len(S.SWEEP_MAGNITUDES) * len(S.SWEEP_GAINS) * S.SWEEP_STATES
+
+
 def workload_cfg(name):
+    if name == SWEEP:
+        return dict(n=SWEEP_TOTAL, mode_mix=(1.0, 0.0, 0.0), pushes="grid 16 directions x 8 magnitudes (5..80 N)", terrain=False, seed=4)
     cfg = dict(S.CONFIGS[name])
     return cfg
 
@@ -116,7 +122,7 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="standing_4096", choices=sorted(S.CONFIGS))
+    ap.add_argument("--workload", default="standing_4096", choices=sorted(S.CONFIGS) + [SWEEP])
     ap.add_argument("--per-gpu", type=int, default=None, help="instances per GPU (default: the workload's own size, 1M config: /8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -126,7 +132,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     cfg = workload_cfg(args.workload)
     n_cfg = cfg.pop("n")
-    per_gpu = args.per_gpu or (n_cfg // 8 if args.workload == "mixed_terrain_1m" else n_cfg)
+    sweep = args.workload == SWEEP
+    per_gpu = args.per_gpu or (n_cfg // 8 if args.workload == "mixed_terrain_1m" else (n_cfg // world if sweep else n_cfg))
     cores = os.cpu_count() or 1
     config = {"workload": "%s: %d DogBot instances per GPU x %d GPU(s), 18-DoF, mode mix %s, pushes=%s, terrain=%s, seed %d" % (
         args.workload, per_gpu, world, cfg["mode_mix"], cfg["pushes"], cfg["terrain"], cfg["seed"]),
@@ -136,7 +143,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        sc = S.make(per_gpu, start=0, **cfg)
+        sc = S.push_sweep(n=min(per_gpu, 4096)) if sweep else S.make(per_gpu, start=0, **cfg)
         sample = per_gpu if (cores >= 16 or per_gpu <= 1024) else 1024
         sample = min(sample, 4096)
         kind, tot, times = cpu_reference_run(sc, args.steps, args.warmup, sample, cores)
@@ -162,7 +169,8 @@ def main():
 
     lo, hi = sharding.shard_range(per_gpu * world, rank, world)
     n = hi - lo
-    sc = S.make(n, start=lo, **cfg)
+    sc = S.push_sweep(n=n, start=lo) if sweep else S.make(n, start=lo, **cfg)
+    grid = sc.pop("grid", None)
     batch = api.WbcBatch(max_batch=n, device=local_rank)
     batch.set_observer_state(sc["obs_yd"], sc["obs_yw"])
     dev_in = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in sc.items() if isinstance(v, np.ndarray)}
@@ -178,8 +186,17 @@ def main():
     sp = stream.cuda_stream
     assert sp != 0
 
+    if sweep:
+        # closed loop: the plant needs the commanded forces x[18:30] every cycle; observer gain per instance
+        dev_out["x"] = torch.zeros(30, n, dtype=torch.float64, device=dev)
+        stat_out["x"] = dev_out["x"]
+        config["scaling_note"] = "fixed grid of %d instances sharded over the ranks (strong scaling); one step = one closed-loop cycle" % SWEEP_TOTAL
+
     def step(outs):
         batch.cycle_device(dev_in, outs, n, n, stream=sp, sync=False)
+        if sweep:
+            batch.plant_step(dev_in["base_pos"], dev_in["base_vel"], dev_in["push"], foot_force=dev_in["foot_force"], x=outs["x"], n=n, ld=n,
+                             stream=sp, sync=False)
 
     for it in range(args.warmup):
         step(stat_out if it == args.warmup - 1 else dev_out)
@@ -211,17 +228,34 @@ def main():
     t_wall = time.perf_counter() - t_wall0
     step_ms = np.array([a.elapsed_time(b) for a, b in ev])
     tot_ms = float(step_ms.sum())
-    launches = batch.last_launches() * args.steps
+    launches = (3 if sweep else 2) * args.steps
+    sweep_stats = None
+    if sweep:
+        # how far the observer got after warmup + steps closed-loop cycles, per gain (rank 0's shard)
+        w_now = dev_out["w"].cpu().numpy()
+        rel = np.abs(w_now - sc["push"]).max(axis=0) / np.abs(sc["push"]).max(axis=0)
+        sweep_stats = {"cycles": args.warmup + args.steps, "sim_time_s": (args.warmup + args.steps) * 0.0025,
+                       "w_rel_err_by_gain": {str(g): float(rel[sc["obs_gain"] == g].max()) for g in np.unique(sc["obs_gain"])},
+                       "max_abs_base_lin_vel": float(dev_in["base_vel"][:3].abs().max().item())}
 
     # ---- e2e: host buffers through the C ABI (H2D + kernels + D2H inside the timed region)
     e2e_steps = args.steps
+    want = ("x",) if sweep else ()
+
+    def e2e_step():
+        out = batch.cycle(sc, want=want)
+        if sweep:   # host-side rollout: the plant's H2D/D2H copies are part of the step too
+            batch.plant_step(sc["base_pos"], sc["base_vel"], sc["push"], foot_force=sc["foot_force"], x=out["x"])
+        return out
+    if sweep:
+        batch.set_observer_state(sc["obs_yd"], sc["obs_yw"])
     for _ in range(2):
-        batch.cycle(sc, want=())
+        e2e_step()
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        out_host = batch.cycle(sc, want=())
+        out_host = e2e_step()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop()
     assert np.isfinite(out_host["tau"]).all()
@@ -233,6 +267,7 @@ def main():
         tot_ms, e2e_s = t.tolist()
     stats = sharding.gather_stats(sharding.local_stats(n, status, qp_info, qp_flops, ms=tot_ms / args.steps), device=dev)
     total_inst = per_gpu * world
+    scaling = "strong" if sweep else "weak"
     value = total_inst * args.steps / (tot_ms * 1e-3)
     e2e_val = total_inst * e2e_steps / e2e_s
 
@@ -255,13 +290,16 @@ def main():
                     "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
                             "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": tot_ms / args.steps, "p50_ms": float(np.median(step_ms)), "higher_is_better": True, "scaling": "weak",
+                "ms_per_step": tot_ms / args.steps, "p50_ms": float(np.median(step_ms)), "higher_is_better": True, "scaling": scaling,
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks,
-                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": n * IN_BYTES, "d2h_bytes_per_step": n * OUT_BYTES},
+                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": n * (IN_BYTES + (8 + 57 * 8 if sweep else 0)),
+                        "d2h_bytes_per_step": n * (OUT_BYTES + (30 * 8 + 21 * 8 if sweep else 0))},
                 "gpu_launches": launches, "roofline": roofline,
                 "stats": {"solver_failures": stats["solver_failures"], "mean_ncholesky": stats["sum_ncholesky"] / total_inst,
                           "mean_outer_its": stats["sum_outer_its"] / total_inst, "max_kkt_dim": stats["max_kkt_dim"],
                           "wall_s_timed_region": t_wall}}
+        if sweep_stats:
+            line["stats"]["sweep"] = sweep_stats
         if world == 1 and not args.no_cpu_baseline:
             kind, tot, _ = cpu_reference_run(sc, 1, 0, min(n, 4096), cores)
             line["cpu_baseline"] = {"value": min(n, 4096) / tot, "unit": UNIT, "cores": cores, "kind": kind,

@@ -89,6 +89,8 @@ typedef struct wbc_inputs {
     const double* terrain;      /* [40] per foot n(3) t1(3) t2(3) mu(1); NULL = flat  main.cpp:1062-1078 */
     const int* mode;            /* [1]  WBC_MODE_*                                                      */
     long ld;                    /* leading dimension (>= n) of every array above                       */
+    const double* obs_gain;     /* [1]  per-instance observer gain k0 (main.cpp:708); NULL = params.obs_gain.
+                                        Extension for BASELINE config 5's gain sweep (the reference hard-codes 10). */
 } wbc_inputs;
 
 typedef struct wbc_outputs {
@@ -150,6 +152,20 @@ int wbc_debug_update(wbc_ctx* ctx, int n, const wbc_inputs* in, const wbc_debug*
  *   info [n][8] and flops [n] may be NULL. */
 int wbc_qp_solve(wbc_ctx* ctx, int n, const double* Q, const double* c, const double* L, int nrows, int neq, double* x,
                  int* status, int* info, double* flops, void* cuda_stream, unsigned flags);
+
+/* Synthetic plant of BASELINE config 5 (disturbance-rejection sweep).  Stands in for Gazebo + the ModelPush plugin
+ * (force_plugin/src/force_plugin.cpp:124-491), which cannot run here: a CoM momentum integrator with locked joints,
+ *     rho' = rho + T (-m g_acc e3 + Jc' Fgrf + push),  CoM_vel' = Mc^-1 rho',  T = params.obs_dt,
+ * using the momentum balance the LAST wbc_cycle on this ctx computed for the same n instances (the balance
+ * DOGCTRL::estimate() inverts, main.cpp:692-725).  Updates the base twist in place (omega' = CoM_vel'[3:6],
+ * v' = CoM_vel'[0:3] - omega' x (com - base)) and, when base_pos is not NULL, base_pos += T v'.
+ * Open loop (foot_force == NULL): Fgrf is what the last cycle measured.  Closed loop (foot_force != NULL, stance only):
+ * the ground reacts with the commanded forces f* = x[18:30] of the last cycle's QP solution `x` [30][ld], and
+ * foot_force [12][ld] is overwritten with R_foot' f* -- what the contact sensors report to the next cycle
+ * (main.cpp:794-834, 1022-1026).
+ * base_pos [3][ld], base_vel [6][ld], push [6][ld] (world wrench at the CoM); host or device pointers per flags. */
+int wbc_plant_step(wbc_ctx* ctx, int n, double* base_pos, double* base_vel, double* foot_force, const double* x, const double* push,
+                   long ld, void* cuda_stream, unsigned flags);
 
 /* Device-side timing of the last wbc_cycle on this ctx (CUDA events on the launching stream), ms. */
 int wbc_last_timing(wbc_ctx* ctx, float* front_ms, float* solve_ms);

@@ -143,7 +143,7 @@ public:
         in.q = q.data(); in.dq = dq.data(); in.com_des_pos = com_des_pos.data(); in.com_des_vel = com_des_vel.data();
         in.com_des_acc = com_des_acc.data(); in.sw_des_pos = sw_des_pos.data(); in.sw_des_vel = sw_des_vel.data();
         in.sw_des_acc = sw_des_acc.data(); in.foot_force = foot_force.data(); in.terrain = terrain.empty() ? nullptr : terrain.data();
-        in.mode = mode.data(); in.ld = n_;
+        in.mode = mode.data(); in.ld = n_; in.obs_gain = nullptr;
         wbc_outputs out;
         out.tau = tau.data(); out.w = w.data(); out.x = x.data(); out.qp_obj = qp_obj.data(); out.status = status.data();
         out.qp_info = nullptr; out.qp_flops = nullptr; out.ld = n_;

@@ -212,3 +212,45 @@ def assemble_only(sc, i, params=None, w=None, gravity=(0.0, 0.0, -9.8)):
     wv = (C.c_double * 6)(*(w if w is not None else [0.0] * 6))
     lib.wbc_oracle_assemble(C.byref(params), C.byref(arr[0]), C.byref(dyn), wv, C.byref(qp))
     return dyn, qp
+
+
+def run_cycle_batch_gains(sc, params=None, nthreads=1):
+    """run_cycle_batch for a scenario with a per-instance observer gain sc["obs_gain"] (BASELINE config 5):
+    the oracle's gain is a scalar parameter like the reference's literal (main.cpp:708), so instances are grouped."""
+    gains = sc.get("obs_gain")
+    if gains is None:
+        return run_cycle_batch(sc, params, nthreads)
+    n = sc["mode"].shape[0]
+    res, secs = None, 0.0
+    for gval in np.unique(gains):
+        idx = np.nonzero(gains == gval)[0]
+        sub = {k: (np.ascontiguousarray(v[..., idx]) if isinstance(v, np.ndarray) else v) for k, v in sc.items() if k != "obs_gain"}
+        p = default_params() if params is None else params
+        p2 = Params.from_buffer_copy(p)
+        p2.obs_gain = float(gval)
+        r, s = run_cycle_batch(sub, p2, nthreads)
+        secs += s
+        if res is None:
+            res = {k: np.zeros((n,) + v.shape[1:], dtype=v.dtype) for k, v in r.items()}
+        for k, v in r.items():
+            res[k][idx] = v
+    return res, secs
+
+
+def plant_step(sc, push, x=None, params=None, gravity=(0.0, 0.0, -9.8)):
+    """Synthetic plant of BASELINE config 5 (wbc_oracle_plant_step) on every instance; push [6][n]; x [n][30] (the
+    oracle's QP solutions) closes the loop.  Returns (base_pos [3][n], base_vel [6][n], foot_force [12][n] or None)."""
+    params = params or default_params()
+    lib = oracle_lib()
+    pd = C.POINTER(C.c_double)
+    lib.wbc_oracle_plant_step.argtypes = [C.POINTER(Params), C.POINTER(In), pd, pd, pd, pd, pd]
+    lib.wbc_oracle_plant_step.restype = None
+    n = sc["mode"].shape[0]
+    arr = to_structs(sc, gravity)
+    pos, vel, ff = np.zeros((n, 3)), np.zeros((n, 6)), np.zeros((n, 12))
+    pt = np.ascontiguousarray(np.asarray(push, dtype=np.float64).T)
+    xs = None if x is None else np.ascontiguousarray(x, dtype=np.float64)
+    for i in range(n):
+        lib.wbc_oracle_plant_step(C.byref(params), C.byref(arr[i]), _dp(pt[i]), _dp(xs[i]) if xs is not None else None, _dp(pos[i]),
+                                  _dp(vel[i]), _dp(ff[i]))
+    return np.ascontiguousarray(pos.T), np.ascontiguousarray(vel.T), (np.ascontiguousarray(ff.T) if xs is not None else None)

@@ -630,6 +630,53 @@ int wbc_oracle_cycle(const wbc_oracle_params* p, const wbc_oracle_in* in, wbc_qp
     return rc;
 }
 
+/* ------------------------------------------------------------------ synthetic plant of BASELINE config 5
+ * Not reference code: the reference's plant is Gazebo + the ModelPush plugin (force_plugin/src/force_plugin.cpp:124-491).
+ * SURVEY.md 8d row 5 defines the stand-in: a CoM momentum integrator with locked joints,
+ *     rho_{k+1} = rho_k + T (-m g_acc e3 + fc + w_true),   rho = Mcom[0:6,0:6] CoM_vel,  fc = J' Fgrf
+ * i.e. exactly the balance the observer (main.cpp:692-725) inverts, so that w -> w_true.  The new CoM_vel is
+ * mapped back to the base twist of a rigid body: omega = CoM_vel[3:6], v_base = CoM_vel[0:3] - omega x (com - base),
+ * and the base position advances by T v_base (orientation and joints stay fixed).  With x != NULL the loop is closed:
+ * Fgrf = the commanded forces x[18:30], and foot_force_out = R_foot' f* is what the sensors report next cycle. */
+void wbc_oracle_plant_step(const wbc_oracle_params* p, const wbc_oracle_in* in, const double* push, const double* x,
+                           double* base_pos_out, double* base_vel_out, double* foot_force_out)
+{
+    wbc_oracle_dyn* d = (wbc_oracle_dyn*)malloc(sizeof(wbc_oracle_dyn));
+    double Fgrf[12], Mc[36], qd[6], rhs[6];
+    wbc_oracle_update(in, d);
+    if (x) {
+        /* closed loop: the ground reacts with the commanded forces (stance layout x[18:30], main.cpp:1126) */
+        for (int r = 0; r < 12; r++) Fgrf[r] = x[18 + r];
+        for (int f = 0; f < 4; f++) {
+            double Rt[9];
+            mat_T(&d->foot_R[f * 9], Rt, 3, 3);
+            mat_mul(Rt, &Fgrf[f * 3], &foot_force_out[f * 3], 3, 3, 1);
+        }
+    } else {
+        wbc_oracle_fgrf(in, d, Fgrf);
+    }
+    for (int a = 0; a < 6; a++)
+        for (int b = 0; b < 6; b++) Mc[a * 6 + b] = d->Mcom[a * 18 + b];
+    for (int c = 0; c < 3; c++) { qd[c] = d->com_vel[c]; qd[3 + c] = in->base_vel[3 + c]; }
+    for (int a = 0; a < 6; a++) {
+        double rho = 0.0, fc = 0.0;
+        for (int b = 0; b < 6; b++) rho += Mc[a * 6 + b] * qd[b];
+        for (int r = 0; r < 12; r++) fc += d->Jcom_lin[r * 18 + a] * Fgrf[r];
+        const double dd = -DB_TOTAL_MASS * ((a == 2) ? p->g_acc : 0.0) + fc;
+        rhs[a] = rho + p->obs_dt * (dd + push[a]);
+    }
+    gj_solve(Mc, rhs, 6, 1);                                  /* CoM_vel_{k+1} */
+    double xbc[3], wx[3];
+    for (int c = 0; c < 3; c++) xbc[c] = d->com[c] - in->base_pos[c];
+    cross3(&rhs[3], xbc, wx);
+    for (int c = 0; c < 3; c++) {
+        base_vel_out[c] = rhs[c] - wx[c];
+        base_vel_out[3 + c] = rhs[3 + c];
+        base_pos_out[c] = in->base_pos[c] + p->obs_dt * base_vel_out[c];
+    }
+    free(d);
+}
+
 /* ------------------------------------------------------------------ threaded batch (CPU baseline) */
 typedef struct {
     const wbc_oracle_params* p; const wbc_oracle_in* in; wbc_oracle_out* out; wbc_qp_fn solve; int lo, hi;

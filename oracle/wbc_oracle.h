@@ -101,6 +101,11 @@ void wbc_oracle_fgrf(const wbc_oracle_in* in, const wbc_oracle_dyn* d, double* F
 void wbc_oracle_torque(const wbc_oracle_in* in, const wbc_oracle_dyn* d, const double* x, double* tau);
 int  wbc_oracle_cycle(const wbc_oracle_params* p, const wbc_oracle_in* in, wbc_qp_fn solve,
                       wbc_oracle_out* out, wbc_oracle_dyn* dyn_opt, wbc_oracle_qp* qp_opt);
+/* Synthetic plant of BASELINE config 5 (CoM momentum integrator, joints locked; see wbc_oracle.c). push = world wrench
+ * at the CoM (6); x = QP solution (30) for the closed loop or NULL; outputs the next base position (3), base twist (6)
+ * and, in closed loop, the next sensor-frame foot forces (12). */
+void wbc_oracle_plant_step(const wbc_oracle_params* p, const wbc_oracle_in* in, const double* push, const double* x,
+                           double* base_pos_out, double* base_vel_out, double* foot_force_out);
 /* n instances on nthreads host threads (disjoint contiguous ranges); returns wall seconds. */
 double wbc_oracle_batch(const wbc_oracle_params* p, const wbc_oracle_in* in, int n, int nthreads,
                         wbc_qp_fn solve, wbc_oracle_out* out);

@@ -36,7 +36,7 @@ int emu_cycle(const Params* P, const EmuIO* io, int n)
     in.base_pos = io->base_pos; in.base_rot = io->base_rot; in.base_rpy = io->base_rpy; in.base_vel = io->base_vel;
     in.q = io->q; in.dq = io->dq; in.com_des_pos = io->com_des_pos; in.com_des_vel = io->com_des_vel;
     in.com_des_acc = io->com_des_acc; in.sw_des_pos = io->sw_des_pos; in.sw_des_vel = io->sw_des_vel;
-    in.sw_des_acc = io->sw_des_acc; in.foot_force = io->foot_force; in.terrain = io->terrain; in.mode = io->mode; in.ld = io->ld;
+    in.sw_des_acc = io->sw_des_acc; in.foot_force = io->foot_force; in.terrain = io->terrain; in.mode = io->mode; in.obs_gain = nullptr; in.ld = io->ld;
     FrontState st;
     st.yd = io->yd; st.yw = io->yw; st.ld = io->ld;
     std::vector<double> rec(QPREC_DOUBLES);

@@ -43,7 +43,7 @@ class Params(C.Structure):
 
 
 class _Inputs(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n, _ in IN_FIELDS] + [("mode", C.c_void_p), ("ld", C.c_long)]
+    _fields_ = [(n, C.c_void_p) for n, _ in IN_FIELDS] + [("mode", C.c_void_p), ("ld", C.c_long), ("obs_gain", C.c_void_p)]
 
 
 class _Outputs(C.Structure):
@@ -63,7 +63,7 @@ _lib = None
 
 EXPORTS = ["wbc_default_params", "wbc_last_error", "wbc_version", "wbc_create", "wbc_destroy", "wbc_set_params",
            "wbc_set_observer_state", "wbc_get_observer_state", "wbc_cycle", "wbc_debug_update", "wbc_qp_solve",
-           "wbc_last_timing", "wbc_last_launches", "wbc_measure_dfma_peak"]
+           "wbc_plant_step", "wbc_last_timing", "wbc_last_launches", "wbc_measure_dfma_peak"]
 
 
 def lib_path():
@@ -90,6 +90,8 @@ def load():
     lib.wbc_debug_update.argtypes = [C.c_void_p, C.c_int, C.POINTER(_Inputs), C.POINTER(_Debug), C.c_uint]
     lib.wbc_qp_solve.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint]
+    lib.wbc_plant_step.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_void_p,
+                                   C.c_uint]
     lib.wbc_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     lib.wbc_last_launches.argtypes = [C.c_void_p]
     lib.wbc_measure_dfma_peak.argtypes = [C.c_void_p, _dp]
@@ -181,6 +183,13 @@ class WbcBatch:
             keep.append(m)
         ins.mode = _ptr(m)
         ins.ld = ld
+        g = sc.get("obs_gain")                       # optional per-instance observer gain [n] (config 5's sweep)
+        if g is not None:
+            g = np.ascontiguousarray(g, dtype=np.float64).reshape(-1)
+            if g.shape[0] != ld:
+                raise WbcError("obs_gain must have one entry per instance")
+            keep.append(g)
+        ins.obs_gain = _ptr(g)
         if n > ld:
             raise WbcError("n exceeds the arrays' leading dimension")
         return ins
@@ -209,6 +218,7 @@ class WbcBatch:
         for name, _ in IN_FIELDS:
             setattr(ins, name, _ptr(dev_in.get(name)))
         ins.mode = _ptr(dev_in["mode"])
+        ins.obs_gain = _ptr(dev_in.get("obs_gain"))
         ins.ld = ld
         o = _Outputs()
         for k in ("tau", "w", "x", "qp_obj", "status", "qp_info", "qp_flops"):
@@ -244,6 +254,24 @@ class WbcBatch:
         _check(self.lib.wbc_qp_solve(self.h, n, Q.ctypes.data, c.ctypes.data, L.ctypes.data, nrows, int(neq), x.ctypes.data,
                                      status.ctypes.data, info.ctypes.data, flops.ctypes.data, None, HOST_PTRS), "wbc_qp_solve")
         return x, status, info, flops
+
+    def plant_step(self, base_pos, base_vel, push, foot_force=None, x=None, n=None, ld=None, stream=None, sync=True):
+        """Synthetic plant of BASELINE config 5 (wbc_plant_step): advances base_pos [3,n] / base_vel [6,n] in place from the
+        momentum balance of the last cycle and the world push wrench `push` [6,n]; with foot_force [12,n] and the last QP
+        solution x [30,n] the loop is closed through the commanded ground-reaction forces.  numpy arrays (host), or torch
+        CUDA tensors / raw device pointers (then pass n and ld)."""
+        host = isinstance(base_vel, np.ndarray)
+        if host:
+            for a in (base_pos, base_vel, foot_force):
+                assert a is None or (a.flags.c_contiguous and a.dtype == np.float64)
+            n = int(base_vel.shape[1]); ld = n
+            push = np.ascontiguousarray(push, dtype=np.float64)
+            x = None if x is None else np.ascontiguousarray(x, dtype=np.float64)
+            flags = HOST_PTRS
+        else:
+            flags = DEVICE_PTRS | (0 if sync else NO_SYNC)
+        _check(self.lib.wbc_plant_step(self.h, int(n), _ptr(base_pos), _ptr(base_vel), _ptr(foot_force), _ptr(x), _ptr(push), int(ld),
+                                       stream, flags), "wbc_plant_step")
 
     def last_timing(self):
         a, b = C.c_float(0), C.c_float(0)

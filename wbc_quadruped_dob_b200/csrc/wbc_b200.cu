@@ -132,6 +132,65 @@ __global__ void __launch_bounds__(SOLVE_T) wbc_dense_qp_kernel(Params P, int n, 
     }
 }
 
+// Synthetic plant of BASELINE config 5 (see wbc_plant_step in wbc_b200.h): thread per instance, reads the momentum
+// balance the front kernel left in the QP record.
+__global__ void __launch_bounds__(128) wbc_plant_kernel(Params P, int n, const double* __restrict__ recs, double* base_pos, double* base_vel,
+                                                        double* foot_force, const double* __restrict__ x, const double* __restrict__ push, long ld)
+{
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double* rec = recs + i * QPREC_DOUBLES;
+    double L[36], y[6];
+    for (int k = 0; k < 36; k++) L[k] = rec[QR_MC + k];
+    if (foot_force) {
+        // closed loop: the ground reacts with the commanded forces f* = x[18:30] (stance layout, main.cpp:1126); they
+        // are what the contact sensors report next cycle, in the foot frames (Fgrf = R_foot f, main.cpp:1022-1026)
+        double f[12];
+        for (int r = 0; r < 12; r++) f[r] = x[(long)(18 + r) * ld + i];
+        for (int a = 0; a < 6; a++) {
+            double fc = 0.0;
+            for (int r = 0; r < 12; r++) fc += rec[QR_JC + r * 6 + a] * f[r];
+            y[a] = rec[QR_RHO + a] + P.obs_dt * (-dogbot::kTotalMass * (a == 2 ? P.g_acc : 0.0) + fc + push[(long)a * ld + i]);
+        }
+        for (int sf = 0; sf < 4; sf++) {
+            const double* R = rec + QR_FOOTR + 9 * sf;
+            for (int k = 0; k < 3; k++)
+                foot_force[(long)(3 * sf + k) * ld + i] = R[k] * f[3 * sf] + R[3 + k] * f[3 * sf + 1] + R[6 + k] * f[3 * sf + 2];
+        }
+    } else {
+        for (int a = 0; a < 6; a++) y[a] = rec[QR_RHO + a] + P.obs_dt * (rec[QR_DD + a] + push[(long)a * ld + i]);
+    }
+    // Mc is symmetric positive definite: Cholesky, two triangular solves
+    for (int c = 0; c < 6; c++) {
+        double d = L[c * 6 + c];
+        for (int k = 0; k < c; k++) d -= L[c * 6 + k] * L[c * 6 + k];
+        d = sqrt(d);
+        L[c * 6 + c] = d;
+        for (int r = c + 1; r < 6; r++) {
+            double v = L[r * 6 + c];
+            for (int k = 0; k < c; k++) v -= L[r * 6 + k] * L[c * 6 + k];
+            L[r * 6 + c] = v / d;
+        }
+    }
+    for (int r = 0; r < 6; r++) {
+        double v = y[r];
+        for (int k = 0; k < r; k++) v -= L[r * 6 + k] * y[k];
+        y[r] = v / L[r * 6 + r];
+    }
+    for (int r = 5; r >= 0; r--) {
+        double v = y[r];
+        for (int k = r + 1; k < 6; k++) v -= L[k * 6 + r] * y[k];
+        y[r] = v / L[r * 6 + r];
+    }
+    const double bx = rec[QR_XBC], by = rec[QR_XBC + 1], bz = rec[QR_XBC + 2];
+    const double vx = y[0] - (y[4] * bz - y[5] * by), vy = y[1] - (y[5] * bx - y[3] * bz), vz = y[2] - (y[3] * by - y[4] * bx);
+    base_vel[0 * ld + i] = vx; base_vel[1 * ld + i] = vy; base_vel[2 * ld + i] = vz;
+    base_vel[3 * ld + i] = y[3]; base_vel[4 * ld + i] = y[4]; base_vel[5 * ld + i] = y[5];
+    if (base_pos) {
+        base_pos[0 * ld + i] += P.obs_dt * vx; base_pos[1 * ld + i] += P.obs_dt * vy; base_pos[2 * ld + i] += P.obs_dt * vz;
+    }
+}
+
 // FP64 DFMA peak: 8 independent chains per thread, fully unrolled.
 __global__ void __launch_bounds__(256) wbc_dfma_peak_kernel(double* out, int iters)
 {
@@ -163,7 +222,7 @@ static int fail(int code, const char* fmt, const char* a = "", const char* b = "
 
 // field table of wbc_inputs for staging host buffers
 struct FieldDesc { int k; };
-static const int kInFieldK[14] = {3, 9, 3, 6, 12, 12, 6, 6, 6, 6, 6, 6, 12, 40};
+static const int kInFieldK[15] = {3, 9, 3, 6, 12, 12, 6, 6, 6, 6, 6, 6, 12, 40, 1};
 static const int kInDoublesNoTerrain = 3 + 9 + 3 + 6 + 12 + 12 + 6 + 6 + 6 + 6 + 6 + 6 + 12;   // 93
 static const int kOutDoubles = 12 + 6 + 30 + 1 + 1;   // tau, w, x, obj, flops
 static const int kOutInts = 1 + 8;
@@ -193,6 +252,7 @@ struct wbc_ctx {
     double* d_dense;     // dense QP staging (Q, c, L, x)
     float front_ms, solve_ms;
     int launches;
+    int last_n;          // instances of the last wbc_cycle (wbc_plant_step reads their records)
 };
 
 extern "C" {
@@ -259,11 +319,11 @@ int wbc_create(wbc_ctx** out, int device, int max_batch, const wbc_params* param
     TRY(cudaMalloc(&c->w_dev, nb * 6 * sizeof(double)));
     TRY(cudaMalloc(&c->scratch, (size_t)nteams * gl::TOTAL * sizeof(double)));
     TRY(cudaMalloc(&c->queue, 64));
-    TRY(cudaMalloc(&c->d_in, nb * (kInDoublesNoTerrain + 40) * sizeof(double)));
+    TRY(cudaMalloc(&c->d_in, nb * (kInDoublesNoTerrain + 41) * sizeof(double)));
     TRY(cudaMalloc(&c->d_out, nb * kOutDoubles * sizeof(double)));
     TRY(cudaMalloc(&c->d_mode, nb * sizeof(int)));
     TRY(cudaMalloc(&c->d_iout, nb * kOutInts * sizeof(int)));
-    TRY(cudaMallocHost(&c->h_pin, nb * (kInDoublesNoTerrain + 40) * sizeof(double)));
+    TRY(cudaMallocHost(&c->h_pin, nb * (kInDoublesNoTerrain + 41) * sizeof(double)));
     TRY(cudaMallocHost(&c->h_pin_i, nb * kOutInts * sizeof(int)));
     TRY(cudaMemset(c->yd, 0, nb * 6 * sizeof(double)));
     TRY(cudaMemset(c->yw, 0, nb * 6 * sizeof(double)));
@@ -332,13 +392,13 @@ static int check_inputs(const wbc_inputs* in, int n)
 // Stage host SoA inputs into the ctx's device buffers through the pinned bounce buffer (one H2D copy).
 static int stage_inputs(wbc_ctx* c, int n, const wbc_inputs* in, cudaStream_t s, DevInputs* dev)
 {
-    const double* src[14] = {in->base_pos, in->base_rot, in->base_rpy, in->base_vel, in->q, in->dq, in->com_des_pos, in->com_des_vel,
-                             in->com_des_acc, in->sw_des_pos, in->sw_des_vel, in->sw_des_acc, in->foot_force, in->terrain};
-    const double** dst[14] = {&dev->base_pos, &dev->base_rot, &dev->base_rpy, &dev->base_vel, &dev->q, &dev->dq, &dev->com_des_pos,
+    const double* src[15] = {in->base_pos, in->base_rot, in->base_rpy, in->base_vel, in->q, in->dq, in->com_des_pos, in->com_des_vel,
+                             in->com_des_acc, in->sw_des_pos, in->sw_des_vel, in->sw_des_acc, in->foot_force, in->terrain, in->obs_gain};
+    const double** dst[15] = {&dev->base_pos, &dev->base_rot, &dev->base_rpy, &dev->base_vel, &dev->q, &dev->dq, &dev->com_des_pos,
                               &dev->com_des_vel, &dev->com_des_acc, &dev->sw_des_pos, &dev->sw_des_vel, &dev->sw_des_acc,
-                              &dev->foot_force, &dev->terrain};
+                              &dev->foot_force, &dev->terrain, &dev->obs_gain};
     size_t off = 0;
-    for (int f = 0; f < 14; f++) {
+    for (int f = 0; f < 15; f++) {
         if (!src[f]) { *dst[f] = nullptr; continue; }
         for (int k = 0; k < kInFieldK[f]; k++) memcpy(c->h_pin + off + (size_t)k * n, src[f] + (size_t)k * in->ld, (size_t)n * sizeof(double));
         *dst[f] = c->d_in + off;
@@ -356,7 +416,7 @@ static void to_dev_inputs(const wbc_inputs* in, DevInputs* d)
     d->base_pos = in->base_pos; d->base_rot = in->base_rot; d->base_rpy = in->base_rpy; d->base_vel = in->base_vel;
     d->q = in->q; d->dq = in->dq; d->com_des_pos = in->com_des_pos; d->com_des_vel = in->com_des_vel; d->com_des_acc = in->com_des_acc;
     d->sw_des_pos = in->sw_des_pos; d->sw_des_vel = in->sw_des_vel; d->sw_des_acc = in->sw_des_acc; d->foot_force = in->foot_force;
-    d->terrain = in->terrain; d->mode = in->mode; d->ld = in->ld;
+    d->terrain = in->terrain; d->mode = in->mode; d->obs_gain = in->obs_gain; d->ld = in->ld;
 }
 
 int wbc_cycle(wbc_ctx* c, int n, const wbc_inputs* in, const wbc_outputs* out, void* cuda_stream, unsigned flags)
@@ -404,6 +464,7 @@ int wbc_cycle(wbc_ctx* c, int n, const wbc_inputs* in, const wbc_outputs* out, v
     CU(cudaEventRecord(c->ev2, s));
     CU(cudaGetLastError());
     c->launches = 2;
+    c->last_n = n;
     if (!dev_ptrs) {
         // one D2H of the packed result block, then scatter into the caller's SoA arrays
         // packed layout: tau 12 | w 6 | x 30 | obj 1 | flops 1 -- copy only the prefix the caller asked for
@@ -418,6 +479,48 @@ int wbc_cycle(wbc_ctx* c, int n, const wbc_inputs* in, const wbc_outputs* out, v
         if (out->qp_flops) memcpy(out->qp_flops, c->h_pin + (size_t)49 * n, (size_t)n * 8);
         if (out->status) memcpy(out->status, c->h_pin_i, (size_t)n * 4);
         if (out->qp_info) for (int k = 0; k < 8; k++) memcpy(out->qp_info + (size_t)k * out->ld, c->h_pin_i + (size_t)(1 + k) * n, (size_t)n * 4);
+    } else if (!(flags & WBC_NO_SYNC)) {
+        CU(cudaStreamSynchronize(s));
+    }
+    return WBC_OK;
+}
+
+int wbc_plant_step(wbc_ctx* c, int n, double* base_pos, double* base_vel, double* foot_force, const double* x, const double* push, long ld,
+                   void* cuda_stream, unsigned flags)
+{
+    if (!c || !base_vel || !push) return fail(WBC_EINVAL, "wbc_plant_step: null argument");
+    if (foot_force && !x) return fail(WBC_EINVAL, "wbc_plant_step: closed loop (foot_force) needs the QP solution x");
+    if (n < 0 || n > c->max_batch || ld < n) return fail(WBC_EINVAL, "wbc_plant_step: n outside [0, max_batch] or ld < n");
+    if (n != c->last_n) return fail(WBC_EINVAL, "wbc_plant_step: n differs from the last wbc_cycle on this ctx");
+    if (n == 0) { c->launches = 0; return WBC_OK; }
+    CU(cudaSetDevice(c->device));
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : c->stream;
+    const bool dev_ptrs = (flags & WBC_DEVICE_PTRS) != 0;
+    double *dpos = base_pos, *dvel = base_vel, *dff = foot_force;
+    const double *dpush = push, *dx = x;
+    long dld = ld;
+    if (!dev_ptrs) {
+        // convenience path for small host-side rollouts: packed staging in the input buffer
+        // layout (doubles per instance): pos 3 | vel 6 | foot_force 12 | push 6 | x[18:30] at rows 18..29 of a 30-row block
+        double* h = c->h_pin;
+        const size_t N = (size_t)n;
+        for (int k = 0; k < 3; k++) memcpy(h + k * N, base_pos ? base_pos + (size_t)k * ld : base_vel, N * 8);
+        for (int k = 0; k < 6; k++) memcpy(h + (3 + k) * N, base_vel + (size_t)k * ld, N * 8);
+        for (int k = 0; k < 6; k++) memcpy(h + (21 + k) * N, push + (size_t)k * ld, N * 8);
+        if (foot_force) for (int k = 0; k < 12; k++) memcpy(h + (45 + k) * N, x + (size_t)(18 + k) * ld, N * 8);
+        CU(cudaMemcpyAsync(c->d_in, h, 57 * N * 8, cudaMemcpyHostToDevice, s));
+        dpos = base_pos ? c->d_in : nullptr; dvel = c->d_in + 3 * N; dff = foot_force ? c->d_in + 9 * N : nullptr;
+        dpush = c->d_in + 21 * N; dx = c->d_in + 27 * N; dld = n;
+    }
+    wbc_plant_kernel<<<(n + 127) / 128, 128, 0, s>>>(c->params, n, c->recs, dpos, dvel, dff, dx, dpush, dld);
+    CU(cudaGetLastError());
+    c->launches = 1;
+    if (!dev_ptrs) {
+        CU(cudaMemcpyAsync(c->h_pin, c->d_in, (size_t)21 * n * 8, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        if (base_pos) for (int k = 0; k < 3; k++) memcpy(base_pos + (size_t)k * ld, c->h_pin + (size_t)k * n, (size_t)n * 8);
+        for (int k = 0; k < 6; k++) memcpy(base_vel + (size_t)k * ld, c->h_pin + (size_t)(3 + k) * n, (size_t)n * 8);
+        if (foot_force) for (int k = 0; k < 12; k++) memcpy(foot_force + (size_t)k * ld, c->h_pin + (size_t)(9 + k) * n, (size_t)n * 8);
     } else if (!(flags & WBC_NO_SYNC)) {
         CU(cudaStreamSynchronize(s));
     }

@@ -379,17 +379,20 @@ WBC_DEVFN inline void front_cycle(const Params& P, const DevInputs& in, const Fr
     }
     // ---- estimate() (main.cpp:692-725)
     const double comv6[6] = {comv.x, comv.y, comv.z, w0.x, w0.y, w0.z};     // CoM_vel, main.cpp:602
-    double west[6];
+    double west[6], rho6[6], dd6[6];
+    for (int a = 0; a < 6; a++) {
+        double rho = 0.0, fc = 0.0;
+        for (int b = 0; b < 6; b++) rho += Mc[a * 6 + b] * comv6[b];        // 699, 705
+        for (int r = 0; r < 12; r++) fc += Jc[r * 6 + a] * Fg[r];           // 696-698
+        rho6[a] = rho;
+        dd6[a] = -mtot * (a == 2 ? P.g_acc : 0.0) + fc;                     // 700-706
+    }
     if (P.observer_enabled) {
-        const double T = P.obs_dt, k0 = P.obs_gain;
+        const double T = P.obs_dt, k0 = in.obs_gain ? in.obs_gain[i] : P.obs_gain;
         const double mgain = (1.0 / (1.0 + k0 * T)) * k0;                   // (I + k0 T)^-1 k0, main.cpp:716
         for (int a = 0; a < 6; a++) {
-            double rho = 0.0, fc = 0.0;
-            for (int b = 0; b < 6; b++) rho += Mc[a * 6 + b] * comv6[b];    // 699, 705
-            for (int r = 0; r < 12; r++) fc += Jc[r * 6 + a] * Fg[r];       // 696-698
-            const double dd = -mtot * (a == 2 ? P.g_acc : 0.0) + fc;        // 700-706
-            const double yd = st.yd[(long)a * st.ld + i] + dd * T;          // 717
-            const double wv = mgain * (rho - st.yw[(long)a * st.ld + i] - yd);   // 718
+            const double yd = st.yd[(long)a * st.ld + i] + dd6[a] * T;      // 717
+            const double wv = mgain * (rho6[a] - st.yw[(long)a * st.ld + i] - yd);   // 718
             st.yd[(long)a * st.ld + i] = yd;                                // 721-724
             st.yw[(long)a * st.ld + i] += wv * T;                           // 719
             west[a] = wv;
@@ -456,6 +459,10 @@ WBC_DEVFN inline void front_cycle(const Params& P, const DevInputs& in, const Fr
         }
     }
     rec[QR_MODE] = (double)mode;
+    for (int a = 0; a < 6; a++) { rec[QR_RHO + a] = rho6[a]; rec[QR_DD + a] = dd6[a]; }
+    rec[QR_XBC] = xbc.x; rec[QR_XBC + 1] = xbc.y; rec[QR_XBC + 2] = xbc.z;
+    for (int sf = 0; sf < 4; sf++)
+        for (int k = 0; k < 9; k++) rec[QR_FOOTR + 9 * sf + k] = footR[kFootLeg[sf]].m[k];
 
     if (dbg) {
         const long dl = dbg->ld;

@@ -58,6 +58,7 @@ struct DevInputs {
     const double* foot_force;   // [12][ld]
     const double* terrain;      // [40][ld] or nullptr (flat ground, main.cpp:1062-1078)
     const int* mode;            // [ld]
+    const double* obs_gain;     // [ld] or nullptr: per-instance observer gain k0 (config 5's sweep); nullptr = Params::obs_gain
     long ld;
 };
 
@@ -106,6 +107,11 @@ constexpr int QR_DDQMIN = 444;  // [12]
 constexpr int QR_SWRHS = 456;   // [6]      vdotswdes - Jdqdsw (main.cpp:1378)
 constexpr int QR_CFR = 462;     // [4][15]  friction rows per stacked foot (main.cpp:1072-1078)
 constexpr int QR_MODE = 522;    // [1]      contact mode as a double
-constexpr int QPREC_DOUBLES = 528;   // padded to a multiple of 16 doubles (128 B)
+// momentum balance of the cycle, for the synthetic plant of BASELINE config 5 (wbc_plant_kernel); not read by the solver
+constexpr int QR_RHO = 523;     // [6]      rho = Mc CoM_vel                       (main.cpp:699, 705)
+constexpr int QR_DD = 529;      // [6]      d = -m g_acc e3 + Jc' Fgrf             (main.cpp:700-706)
+constexpr int QR_XBC = 535;     // [3]      com - base origin                      (main.cpp:518)
+constexpr int QR_FOOTR = 538;   // [4][9]   world_R_foot per stacked foot, row-major (main.cpp:459-487)
+constexpr int QPREC_DOUBLES = 576;   // padded to a multiple of 16 doubles (128 B)
 
 }  // namespace wbc

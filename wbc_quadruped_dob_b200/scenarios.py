@@ -183,6 +183,54 @@ def make(n, mode_mix=(1.0, 0.0, 0.0), pushes=False, terrain=False, seed=1, start
     return {k: np.ascontiguousarray(np.concatenate([p[k] for p in parts], axis=-1)) for k in parts[0]}
 
 
+SWEEP_DIRECTIONS, SWEEP_MAGNITUDES = 16, (5.0, 10.0, 20.0, 30.0, 40.0, 50.0, 65.0, 80.0)
+SWEEP_GAINS = (1.0, 2.0, 5.0, 10.0, 20.0, 50.0, 100.0, 200.0)
+SWEEP_STATES = 256
+
+
+def push_sweep(n=None, start=0, directions=SWEEP_DIRECTIONS, magnitudes=SWEEP_MAGNITUDES, gains=SWEEP_GAINS, states=SWEEP_STATES, seed=4):
+    """BASELINE config 5: disturbance-rejection sweep.  The grid is
+    directions x magnitudes x observer gains x states = 16 x 8 x 8 x 256 = 262144 standing instances; instance
+    i = ((d * M + m) * G + g) * S + s.  The push is a horizontal force of the given magnitude (5..80 N, the range of
+    force_plugin's case studies, fp.cpp:157, 206) in direction 2 pi d / D applied at the hip of leg (d mod 4), i.e. a
+    world wrench [F; r x F] at the CoM.  Joints are at rest (dq = 0: the plant of this config is a CoM momentum
+    integrator with locked joints), the observer starts from yd = yw = 0 and the measured foot forces carry the
+    robot's weight.  Returns the scenario plus "obs_gain" [n], "push" [6,n] and "grid" (d, m, g, s index arrays).
+    Instances [start, start+n) of the grid (default: all)."""
+    D, M, G, S = int(directions), len(magnitudes), len(gains), int(states)
+    total = D * M * G * S
+    n = total - start if n is None else int(n)
+    idx = start + np.arange(n)
+    s_i = idx % S
+    g_i = (idx // S) % G
+    m_i = (idx // (S * G)) % M
+    d_i = (idx // (S * G * M)) % D
+    # the states: block-seeded like make(), indexed by s only, so that every grid cell sees the same 256 robots
+    base = make(S, mode_mix=(1.0, 0.0, 0.0), pushes=False, terrain=False, seed=seed, start=0)
+    sc = {k: np.ascontiguousarray(v[..., s_i]) for k, v in base.items()}
+    sc["dq"] = np.zeros((12, n))
+    sc["base_vel"] = np.zeros((6, n))
+    sc["com_des_vel"] = np.zeros((6, n))
+    sc["com_des_acc"] = np.zeros((6, n))
+    sc["obs_yd"] = np.zeros((6, n))
+    sc["obs_yw"] = np.zeros((6, n))
+    # weight carried equally, expressed in the sensor (foot link) frame of a level robot: close enough to start from
+    ff = np.zeros((12, n))
+    ff[2::3] = TOTAL_MASS * 9.81 / 4.0
+    sc["foot_force"] = ff
+    com, _ = forward_kinematics(sc["base_pos"], sc["base_rot"], sc["q"])
+    ang = 2.0 * np.pi * d_i / D
+    mag = np.asarray(magnitudes, dtype=np.float64)[m_i]
+    F = np.vstack([mag * np.cos(ang), mag * np.sin(ang), np.zeros(n)])
+    R0 = sc["base_rot"].T.reshape(n, 3, 3)
+    hip = sc["base_pos"].T + np.einsum("nij,nj->ni", R0, _HIP_XYZ[d_i % 4])
+    r = hip - com
+    sc["push"] = np.vstack([F, np.cross(r, F.T).T])
+    sc["obs_gain"] = np.asarray(gains, dtype=np.float64)[g_i]
+    sc["grid"] = np.vstack([d_i, m_i, g_i, s_i])
+    return sc
+
+
 def make_config(name, n=None, start=0):
     cfg = dict(CONFIGS[name])
     n_cfg = cfg.pop("n")
