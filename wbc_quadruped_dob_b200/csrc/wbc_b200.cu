@@ -74,7 +74,10 @@ __global__ void __launch_bounds__(SOLVE_T) wbc_solve_kernel(Params P, int n, con
     for (;;) {
         const int i = next_instance(queue);
         if (i >= n) break;
-        const double* rec = recs + (long)i * QPREC_DOUBLES;
+        // the record is staged in the (still idle) CI | Z arrays: one cp.async round trip instead of scattered global reads
+        double* rec = SM_(w, sl::OFF_CI);
+        static_assert(QR_MODE + 1 <= NICCAP * LDH + 1152, "QP record fits the staging area");
+        ex.copy_in(rec, recs + (long)i * QPREC_DOUBLES, QR_MODE + 1);
         const QpShape sh = qp_shape((int)rec[QR_MODE]);
         // Q -> H array (ld 31), c -> exb, L -> the warp's global C array (scaled in place by the solver)
         assemble_qp<LDH>(ex, P, rec, sh, W_H(w), W_EXB(w), W_C(w));
@@ -85,6 +88,7 @@ __global__ void __launch_bounds__(SOLVE_T) wbc_solve_kernel(Params P, int n, con
             for (int k = ex.lane(); k < 30; k += SOLVE_T) xs[k] = 0.0;
             ex.sync();
         }
+        ex.copy_in(rec, recs + (long)i * QPREC_DOUBLES, QR_MODE + 1);     // the solver used the arrays; stage again
         torque_and_objective(ex, P, rec, sh, xs, out.tau + i, out.ld, out.qp_obj ? out.qp_obj + i : nullptr);
         if (out.x)
             for (int k = ex.lane(); k < 30; k += SOLVE_T) out.x[(long)k * out.ld + i] = xs[k];
