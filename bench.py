@@ -125,6 +125,7 @@ def main():
     ap.add_argument("--workload", default="standing_4096", choices=sorted(S.CONFIGS) + [SWEEP])
     ap.add_argument("--per-gpu", type=int, default=None, help="instances per GPU (default: the workload's own size, 1M config: /8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fifo", action="store_true", help="index-order work queue (WBC_FIFO_DISPATCH) instead of longest-first")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -138,7 +139,8 @@ def main():
     config = {"workload": "%s: %d DogBot instances per GPU x %d GPU(s), 18-DoF, mode mix %s, pushes=%s, terrain=%s, seed %d" % (
         args.workload, per_gpu, world, cfg["mode_mix"], cfg["pushes"], cfg["terrain"], cfg["seed"]),
         "instances_per_gpu": per_gpu, "global_batch": per_gpu * world, "parallelism": "shard%d" % world,
-        "l2": "flushed between timed steps (256 MiB write)", "solver": "DENSE-AUL/QQP restatement, reference settings (1e-2, 1e4, 5)"}
+        "l2": "flushed between timed steps (256 MiB write)",
+        "dispatch": "fifo" if args.fifo else "longest-first, predicted from each instance's previous cycle (results are order-independent)", "solver": "DENSE-AUL/QQP restatement, reference settings (1e-2, 1e4, 5)"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -172,6 +174,7 @@ def main():
     sc = S.push_sweep(n=n, start=lo) if sweep else S.make(n, start=lo, **cfg)
     grid = sc.pop("grid", None)
     batch = api.WbcBatch(max_batch=n, device=local_rank)
+    batch.fifo_dispatch = args.fifo
     batch.set_observer_state(sc["obs_yd"], sc["obs_yw"])
     dev_in = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in sc.items() if isinstance(v, np.ndarray)}
     dev_out = {"tau": torch.zeros(12, n, dtype=torch.float64, device=dev), "w": torch.zeros(6, n, dtype=torch.float64, device=dev)}

@@ -48,6 +48,9 @@ extern "C" {
 #define WBC_HOST_PTRS 0u         /* in/out pointers are host memory: H2D + D2H copies are part of the call */
 #define WBC_DEVICE_PTRS 1u       /* in/out pointers are device memory on the ctx's GPU: launch only */
 #define WBC_NO_SYNC 2u           /* (device pointers only) return after enqueueing on the stream */
+#define WBC_FIFO_DISPATCH 4u     /* wbc_cycle: hand instances to the solver warps in index order.  Default: longest solve first,
+                                    predicted from each instance's previous cycle on this ctx with the same n (the ctx keeps a
+                                    per-instance duration); the order never changes a result, only when the batch's tail ends. */
 
 typedef struct wbc_ctx wbc_ctx;
 

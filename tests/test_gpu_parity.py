@@ -49,6 +49,28 @@ def test_cycle_matches_oracle_on_baseline_configs(gpu_batch, oracle, have_ref, c
     print(cfg, "worst torque rel err", worst)
 
 
+def test_dispatch_order_never_changes_a_result(gpu_batch):
+    """The work queue hands out instances longest-first from the second cycle on (WBC_FIFO_DISPATCH turns that off):
+    every output must be bit-identical whichever order the warps took the instances in, and the order the front kernel
+    builds must be a permutation (a lost or duplicated ticket would leave a stale or doubly written torque)."""
+    sc = S.make(3000, mode_mix=(0.4, 0.3, 0.3), pushes=True, seed=91)
+    want = ("x", "qp_obj", "status", "qp_info")
+    gpu_batch.fifo_dispatch = True
+    gpu_batch.set_observer_state(sc["obs_yd"], sc["obs_yw"])
+    first = gpu_batch.cycle(sc, want=want)
+    gpu_batch.fifo_dispatch = False
+    for _ in range(3):      # cycles 2.. use the durations recorded by the cycle before
+        gpu_batch.set_observer_state(sc["obs_yd"], sc["obs_yw"])
+        again = gpu_batch.cycle(sc, want=want)
+        for k in ("tau", "w", "x", "qp_obj", "status", "qp_info"):
+            assert np.array_equal(first[k], again[k]), k
+    # a different batch size right after: the stale order is not used
+    sub = {k: (np.ascontiguousarray(v[..., :1000]) if isinstance(v, np.ndarray) else v) for k, v in sc.items()}
+    gpu_batch.set_observer_state(sub["obs_yd"], sub["obs_yw"])
+    part = gpu_batch.cycle(sub, want=want)
+    assert np.array_equal(part["tau"], first["tau"][:, :1000])
+
+
 def test_update_stages_match_oracle(gpu_batch, oracle):
     sc = S.make(64, mode_mix=(0.34, 0.33, 0.33), pushes=True, seed=77)
     dbg = gpu_batch.debug_update(sc)

@@ -12,3 +12,4 @@ for f in ("gpurun_out/q_bench_4096.json","gpurun_out/q_bench_65536.json"):
     except Exception as e: print(f, "ERR", e)
 PY
 tail -3 gpurun_out/q_bench.err
+timeout 300 python bench.py --fifo --no-cpu-baseline 2>> gpurun_out/q_bench.err | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('fifo 4096 value %.0f solve_ms %.3f' % (d['value'], d['roofline']['kernel_ms']))"

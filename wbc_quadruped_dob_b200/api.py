@@ -20,7 +20,7 @@ import numpy as np
 from . import build as _build
 
 MODE_STANCE, MODE_SWING_BR_FL, MODE_SWING_BL_FR = 0, 1, 2
-HOST_PTRS, DEVICE_PTRS, NO_SYNC = 0, 1, 2
+HOST_PTRS, DEVICE_PTRS, NO_SYNC, FIFO_DISPATCH = 0, 1, 2, 4
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
@@ -132,6 +132,7 @@ class WbcBatch:
         h = C.c_void_p()
         _check(self.lib.wbc_create(C.byref(h), self.device, self.max_batch, C.byref(self.params)), "wbc_create")
         self.h = h
+        self.fifo_dispatch = False      # True: WBC_FIFO_DISPATCH (index-order work queue instead of longest-first)
 
     def close(self):
         if getattr(self, "h", None):
@@ -209,7 +210,7 @@ class WbcBatch:
         for k in ("tau", "w", "x", "qp_obj", "status", "qp_info", "qp_flops"):
             setattr(o, k, _ptr(out.get(k)))
         o.ld = max(n, 1)
-        _check(self.lib.wbc_cycle(self.h, n, C.byref(ins), C.byref(o), None, HOST_PTRS), "wbc_cycle")
+        _check(self.lib.wbc_cycle(self.h, n, C.byref(ins), C.byref(o), None, HOST_PTRS | (FIFO_DISPATCH if self.fifo_dispatch else 0)), "wbc_cycle")
         return out
 
     def cycle_device(self, dev_in, dev_out, n, ld, stream=None, sync=True):
@@ -224,7 +225,7 @@ class WbcBatch:
         for k in ("tau", "w", "x", "qp_obj", "status", "qp_info", "qp_flops"):
             setattr(o, k, _ptr(dev_out.get(k)))
         o.ld = ld
-        flags = DEVICE_PTRS | (0 if sync else NO_SYNC)
+        flags = DEVICE_PTRS | (0 if sync else NO_SYNC) | (FIFO_DISPATCH if self.fifo_dispatch else 0)
         _check(self.lib.wbc_cycle(self.h, n, C.byref(ins), C.byref(o), stream, flags), "wbc_cycle")
 
     def debug_update(self, sc, n=None):

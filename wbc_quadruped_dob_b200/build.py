@@ -8,8 +8,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libwbc_b200.so")
 SOURCES = ["wbc_b200.cu"]
-HEADERS = ["qp_denseaul.cuh", "wbc_assemble.cuh", "wbc_front.cuh", "wbc_types.h", "dogbot_model.h",
-           os.path.join("..", "..", "include", "wbc_b200.h")]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [os.path.join("..", "..", "include", "wbc_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v", "-Wno-deprecated-gpu-targets"]
 

@@ -29,10 +29,48 @@ constexpr int SOLVE_CTAS_PER_SM = (227 * 1024) / (sl::BYTES + 1024);
 
 // ------------------------------------------------------------------------------------------------
 // kernels
+// ---- longest-first dispatch of the solver's work queue.
+// A solve takes 4..50 Cholesky factorisations, i.e. its duration varies ~10x between instances, and a batch of a few
+// thousand instances is only a few waves of the resident warps: with first-come dispatch the step ends when the
+// longest solve that happened to start late finishes (measured: 4096 instances take 1.5x their share of the
+// steady-state rate).  Consecutive control cycles of one robot are 2.5 ms apart and hit nearly the same active set,
+// so the duration of an instance's previous solve predicts this one: the solve kernel records each instance's cycle
+// count and a histogram of it, and the NEXT cycle's front kernel turns them into a dispatch order, longest first
+// (a counting sort: bucket bases from the histogram, one atomic per instance).  Results do not depend on the order.
+constexpr int ORD_NB = 256;                   // cost buckets of 65536 cycles (cost unit = 1024 cycles)
+struct DispatchOrder {
+    const unsigned* cost;     // [n] duration of the previous solve of instance i, 1024-cycle units (NULL: keep ticket order)
+    const int* hist;          // [ORD_NB] histogram of bucket(cost) over the n instances
+    int* cursor;              // [ORD_NB] zeroed
+    int* order;               // [n] out: instance index per ticket
+};
+__device__ __forceinline__ int cost_bucket(unsigned cost) { const unsigned b = cost >> 6; return b < ORD_NB ? (int)b : ORD_NB - 1; }
+
 __global__ void __launch_bounds__(64) wbc_front_kernel(Params P, DevInputs in, FrontState st, int n, double* __restrict__ recs,
-                                                       double* __restrict__ w_out, long w_ld, DevDebug dbg, int has_dbg)
+                                                       double* __restrict__ w_out, long w_ld, DevDebug dbg, int has_dbg, DispatchOrder ord)
 {
+    __shared__ int base[ORD_NB];
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ord.cost) {
+        // base[b] = number of instances in costlier buckets: lane l scans buckets 255-8l .. 248-8l
+        if (threadIdx.x < 32) {
+            const int l = threadIdx.x;
+            int h[8], sum = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) { h[k] = ord.hist[ORD_NB - 1 - (8 * l + k)]; sum += h[k]; }
+            int incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (l >= o) incl += t; }
+            int run = incl - sum;
+#pragma unroll
+            for (int k = 0; k < 8; k++) { base[ORD_NB - 1 - (8 * l + k)] = run; run += h[k]; }
+        }
+        __syncthreads();
+        if (i < n) {
+            const int b = cost_bucket(ord.cost[i]);
+            ord.order[base[b] + atomicAdd(ord.cursor + b, 1)] = (int)i;
+        }
+    }
     if (i >= n) return;
     front_cycle(P, in, st, i, recs + i * QPREC_DOUBLES, w_out, w_ld, has_dbg ? &dbg : nullptr);
 }
@@ -60,7 +98,9 @@ __device__ __forceinline__ int next_instance(int* queue)
 }
 
 __global__ void __launch_bounds__(SOLVE_T) wbc_solve_kernel(Params P, int n, const double* __restrict__ recs, SolveOut out,
-                                                            double* __restrict__ scratch_base, int* __restrict__ queue)
+                                                            double* __restrict__ scratch_base, int* __restrict__ queue,
+                                                            const int* __restrict__ order, unsigned* __restrict__ cost,
+                                                            int* __restrict__ hist_next)
 {
     Work w;
     w.g = scratch_base + (long)blockIdx.x * gl::TOTAL;
@@ -72,8 +112,10 @@ __global__ void __launch_bounds__(SOLVE_T) wbc_solve_kernel(Params P, int n, con
     for (int k = ex.lane(); k < sl::TOTAL; k += SOLVE_T) WBC_SM(w)[k] = 0.0;
     ex.sync();
     for (;;) {
-        const int i = next_instance(queue);
-        if (i >= n) break;
+        const int ticket = next_instance(queue);
+        if (ticket >= n) break;
+        const int i = order ? order[ticket] : ticket;
+        const long long t0 = clock64();
         // the record is staged in the (still idle) CI | Z arrays: one cp.async round trip instead of scattered global reads
         double* rec = SM_(w, sl::OFF_CI);
         static_assert(QR_MODE + 1 <= NICCAP * LDH + 1152, "QP record fits the staging area");
@@ -92,7 +134,13 @@ __global__ void __launch_bounds__(SOLVE_T) wbc_solve_kernel(Params P, int n, con
         torque_and_objective(ex, P, rec, sh, xs, out.tau + i, out.ld, out.qp_obj ? out.qp_obj + i : nullptr);
         if (out.x)
             for (int k = ex.lane(); k < 30; k += SOLVE_T) out.x[(long)k * out.ld + i] = xs[k];
-        if (ex.lane() == 0) write_info(st, i, out.ld, out.status, out.qp_info, out.qp_flops);
+        if (ex.lane() == 0) {
+            write_info(st, i, out.ld, out.status, out.qp_info, out.qp_flops);
+            const unsigned long long dt = (unsigned long long)(clock64() - t0) >> 10;
+            const unsigned cu = dt > 0xffffffffull ? 0xffffffffu : (unsigned)dt;
+            cost[i] = cu;
+            atomicAdd(hist_next + cost_bucket(cu), 1);
+        }
         ex.sync();
     }
 }
@@ -243,7 +291,11 @@ struct wbc_ctx {
     double* yw;
     double* w_dev;       // [6][max_batch] (when the caller passes no w)
     double* scratch;     // [nblocks][gl::TOTAL]
-    int* queue;          // work-queue counter
+    int* queue;          // work-queue counter [0], dispatch cursors [1, 1+ORD_NB), cost histograms [2][ORD_NB] after them
+    unsigned* cost;      // [max_batch] duration of each instance's last solve (1024-cycle units)
+    int* order;          // [max_batch] dispatch order built by the front kernel
+    int order_n;         // batch size `cost` and the current histogram describe (0 = none)
+    int hist_sel;        // which histogram the last solve filled
     int nblocks, threads;   // solver launch shape
     // staging for WBC_HOST_PTRS
     double* d_in;        // [93+40][max_batch]
@@ -279,7 +331,7 @@ int wbc_destroy(wbc_ctx* c)
 {
     if (!c) return WBC_OK;
     cudaSetDevice(c->device);
-    cudaFree(c->recs); cudaFree(c->yd); cudaFree(c->yw); cudaFree(c->w_dev); cudaFree(c->scratch); cudaFree(c->queue);
+    cudaFree(c->recs); cudaFree(c->yd); cudaFree(c->yw); cudaFree(c->w_dev); cudaFree(c->scratch); cudaFree(c->queue); cudaFree(c->cost); cudaFree(c->order);
     cudaFree(c->d_in); cudaFree(c->d_out); cudaFree(c->d_mode); cudaFree(c->d_iout); cudaFree(c->d_dense);
     if (c->h_pin) cudaFreeHost(c->h_pin);
     if (c->h_pin_i) cudaFreeHost(c->h_pin_i);
@@ -322,7 +374,10 @@ int wbc_create(wbc_ctx** out, int device, int max_batch, const wbc_params* param
     TRY(cudaMalloc(&c->yw, nb * 6 * sizeof(double)));
     TRY(cudaMalloc(&c->w_dev, nb * 6 * sizeof(double)));
     TRY(cudaMalloc(&c->scratch, (size_t)nteams * gl::TOTAL * sizeof(double)));
-    TRY(cudaMalloc(&c->queue, 64));
+    TRY(cudaMalloc(&c->queue, (1 + 3 * ORD_NB) * sizeof(int)));
+    TRY(cudaMemset(c->queue, 0, (1 + 3 * ORD_NB) * sizeof(int)));
+    TRY(cudaMalloc(&c->cost, nb * sizeof(unsigned)));
+    TRY(cudaMalloc(&c->order, nb * sizeof(int)));
     TRY(cudaMalloc(&c->d_in, nb * (kInDoublesNoTerrain + 41) * sizeof(double)));
     TRY(cudaMalloc(&c->d_out, nb * kOutDoubles * sizeof(double)));
     TRY(cudaMalloc(&c->d_mode, nb * sizeof(int)));
@@ -458,17 +513,27 @@ int wbc_cycle(wbc_ctx* c, int n, const wbc_inputs* in, const wbc_outputs* out, v
     st.yd = c->yd; st.yw = c->yw; st.ld = c->max_batch;
     DevDebug nodbg;
     memset(&nodbg, 0, sizeof(nodbg));
-    CU(cudaMemsetAsync(c->queue, 0, sizeof(int), s));
+    // dispatch order: longest solve first, predicted by each instance's previous solve (same batch size only)
+    int* hist_prev = c->queue + 1 + ORD_NB + c->hist_sel * ORD_NB;
+    int* hist_next = c->queue + 1 + ORD_NB + (c->hist_sel ^ 1) * ORD_NB;
+    const bool ordered = !(flags & WBC_FIFO_DISPATCH) && c->order_n == n && n > 1;
+    DispatchOrder ord;
+    ord.cost = ordered ? c->cost : nullptr; ord.hist = hist_prev; ord.cursor = c->queue + 1; ord.order = c->order;
+    CU(cudaMemsetAsync(c->queue, 0, (1 + ORD_NB) * sizeof(int), s));
+    CU(cudaMemsetAsync(hist_next, 0, ORD_NB * sizeof(int), s));
     CU(cudaEventRecord(c->ev0, s));
     const int fthreads = front_threads(c, n);
-    wbc_front_kernel<<<(n + fthreads - 1) / fthreads, fthreads, 0, s>>>(c->params, din, st, n, c->recs, w_ptr, w_ld, nodbg, 0);
+    wbc_front_kernel<<<(n + fthreads - 1) / fthreads, fthreads, 0, s>>>(c->params, din, st, n, c->recs, w_ptr, w_ld, nodbg, 0, ord);
     CU(cudaEventRecord(c->ev1, s));
     const int nblocks = n < c->nblocks ? n : c->nblocks;
-    wbc_solve_kernel<<<nblocks, c->threads, sl::BYTES, s>>>(c->params, n, c->recs, so, c->scratch, c->queue);
+    wbc_solve_kernel<<<nblocks, c->threads, sl::BYTES, s>>>(c->params, n, c->recs, so, c->scratch, c->queue, ordered ? c->order : nullptr,
+                                                           c->cost, hist_next);
     CU(cudaEventRecord(c->ev2, s));
     CU(cudaGetLastError());
     c->launches = 2;
     c->last_n = n;
+    c->hist_sel ^= 1;
+    c->order_n = n;
     if (!dev_ptrs) {
         // one D2H of the packed result block, then scatter into the caller's SoA arrays
         // packed layout: tau 12 | w 6 | x 30 | obj 1 | flops 1 -- copy only the prefix the caller asked for
@@ -580,7 +645,7 @@ int wbc_debug_update(wbc_ctx* c, int n, const wbc_inputs* in, const wbc_debug* d
     FrontState st;
     st.yd = ytmp; st.yw = ytmp + 6L * n; st.ld = n;
     const int fthreads = front_threads(c, n);
-    wbc_front_kernel<<<(n + fthreads - 1) / fthreads, fthreads, 0, s>>>(c->params, din, st, n, c->recs, c->w_dev, c->max_batch, dd, 1);
+    wbc_front_kernel<<<(n + fthreads - 1) / fthreads, fthreads, 0, s>>>(c->params, din, st, n, c->recs, c->w_dev, c->max_batch, dd, 1, DispatchOrder{nullptr, nullptr, nullptr, nullptr});
     e = cudaStreamSynchronize(s);
     if (e == cudaSuccess) e = cudaGetLastError();
     off = 0;
