@@ -5,7 +5,7 @@ timeout 300 python bench.py > gpurun_out/q_bench_4096.json 2> gpurun_out/q_bench
 timeout 300 python bench.py --workload trot_65536 --steps 10 --no-cpu-baseline > gpurun_out/q_bench_65536.json 2>> gpurun_out/q_bench.err
 timeout 300 python bench.py --workload mixed_terrain_1m --steps 10 --no-cpu-baseline > gpurun_out/q_bench_1m.json 2>> gpurun_out/q_bench.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launch.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:wbc_ -s 6 -c 2 -o gpurun_out/full -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"wbc_(front|solve)_kernel" -s 6 -c 2 -o gpurun_out/full -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
 cat gpurun_out/q_pytest.log
 python - <<'PY'
 import json

@@ -19,10 +19,11 @@ def main():
         if m and kern in m.group(3):
             funcs.append((int(m.group(1), 16), int(m.group(2), 16), m.group(4)))
     funcs.sort()
-    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
+    out = subprocess.run(["ncu", "-i", rep, "--kernel-name", "regex:" + kern, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
     lines = out.splitlines()
     start = next(i for i, l in enumerate(lines) if l.startswith('"Address"'))
-    rd = csv.DictReader(lines[start:])
+    end = next((i for i in range(start + 1, len(lines)) if lines[i].startswith('"Kernel Name"')), len(lines))   # first launch only
+    rd = csv.DictReader(lines[start:end])
     rows = list(rd)
     base = int(rows[0]["Address"], 16)
     stall_cols = [c for c in rows[0].keys() if c.startswith("stall_") and "Not Issued" not in c]
