@@ -213,10 +213,33 @@ struct WarpEx {
     }
 };
 #endif
-// all-reduce by butterflies: every lane ends with bit-identical results (IEEE add / max are commutative)
+// all-reduce by butterflies: every lane ends with bit-identical results (IEEE add / max are commutative).
+// On the device the butterfly is one shared, rolled, non-inlined routine: the solver is instruction-fetch bound
+// (DESIGN.md 4.2), and an inlined 5-step double-precision butterfly is 25 instructions at each of ~60 call sites.
+#if defined(__CUDACC__)
+__device__ __noinline__ double warp_sum_ni(double v)
+{
+#pragma unroll 1
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __noinline__ double warp_max_ni(double v)
+{
+#pragma unroll 1
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+#endif
 template <int N, class Ex>
 WBC_HD void red_sum(const Ex& ex, double* v)
 {
+#if defined(__CUDA_ARCH__)
+    if (Ex::NL == 32) {
+#pragma unroll
+        for (int k = 0; k < N; k++) v[k] = warp_sum_ni(v[k]);
+        return;
+    }
+#endif
     for (int o = Ex::NL / 2; o > 0; o >>= 1) {
 #pragma unroll
         for (int k = 0; k < N; k++) v[k] += ex.shfl_xor(v[k], o);
@@ -225,6 +248,13 @@ WBC_HD void red_sum(const Ex& ex, double* v)
 template <int N, class Ex>
 WBC_HD void red_max(const Ex& ex, double* v)
 {
+#if defined(__CUDA_ARCH__)
+    if (Ex::NL == 32) {
+#pragma unroll
+        for (int k = 0; k < N; k++) v[k] = warp_max_ni(v[k]);
+        return;
+    }
+#endif
     for (int o = Ex::NL / 2; o > 0; o >>= 1) {
 #pragma unroll
         for (int k = 0; k < N; k++) v[k] = fmax(v[k], ex.shfl_xor(v[k], o));

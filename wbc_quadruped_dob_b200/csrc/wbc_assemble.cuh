@@ -49,30 +49,40 @@ WBC_HDN inline void assemble_qp(const Ex& ex, const Params& P, const double* rec
     const double* Jd = rec + QR_JDQD;
     const double* Wc = rec + QR_WCOM;
     const int nf = 3 * sh.nst;                 // force variables
+#pragma unroll 1
     for (int k = lane; k < 30 * LDQ; k += Ex::NL) Q[k] = 0.0;
+#pragma unroll 1
     for (int k = lane; k < 30; k += Ex::NL) c[k] = 0.0;
+#pragma unroll 1
     for (int k = lane; k < sh.nrows * 31; k += Ex::NL) L[k] = 0.0;
     ex.sync();
     // Q = T_s' Q1 T_s + R   (main.cpp:994-1001, 1176-1189)
+#pragma unroll 1
     for (int k = lane; k < nf * nf; k += Ex::NL) {
         const int a = k / nf, b = k % nf;
         const int ra = sh.strow[a / 3] + a % 3, rb = sh.strow[b / 3] + b % 3;
         double s = 0.0;
+#pragma unroll 1
         for (int t = 0; t < 6; t++) s += Jc[ra * 6 + t] * P.q1_weight * Jc[rb * 6 + t];
         Q[(18 + a) * LDQ + 18 + b] = s + (a == b ? 1.0 : 0.0);
     }
+#pragma unroll 1
     for (int k = lane; k < 18; k += Ex::NL) Q[k * LDQ + k] = 1.0;
     if (sh.nst == 2)
+#pragma unroll 1
         for (int k = 24 + lane; k < 30; k += Ex::NL) Q[k * LDQ + k] = P.slack_weight;      // main.cpp:1187-1189
     // c = -T_s' Q1 Wcom_des   (main.cpp:1033, 1224)
+#pragma unroll 1
     for (int a = lane; a < nf; a += Ex::NL) {
         const int ra = sh.strow[a / 3] + a % 3;
         double s = 0.0;
+#pragma unroll 1
         for (int t = 0; t < 6; t++) s += Jc[ra * 6 + t] * P.q1_weight * Wc[t];
         c[18 + a] = -s;
     }
     // equality rows (main.cpp:1039-1048, 1231-1241)
     const bool rhs_on = (sh.nst == 4) || P.fix_swing_rhs;
+#pragma unroll 1
     for (int k = lane; k < 6 * 31; k += Ex::NL) {
         const int a = k / 31, b = k % 31;
         double v = 0.0;
@@ -81,6 +91,7 @@ WBC_HDN inline void assemble_qp(const Ex& ex, const Params& P, const double* rec
         else if (b == 30 && rhs_on) v = -hc[a];
         L[a * 31 + b] = v;
     }
+#pragma unroll 1
     for (int k = lane; k < nf * 31; k += Ex::NL) {
         const int a = k / 31, b = k % 31;
         const int ra = sh.strow[a / 3] + a % 3;
@@ -93,12 +104,14 @@ WBC_HDN inline void assemble_qp(const Ex& ex, const Params& P, const double* rec
     // inequality rows
     const int r0 = sh.neq;                       // first inequality row
     const int nfr = 5 * sh.nst;                  // friction rows (main.cpp:1062-1085, 1266-1298)
+#pragma unroll 1
     for (int k = lane; k < nfr * 3; k += Ex::NL) {
         const int r = k / 3, cc = k % 3, f = r / 5, rr = r % 5;
         const int sf = sh.strow[f] / 3;
         L[(r0 + r) * 31 + 18 + 3 * f + cc] = rec[QR_CFR + 15 * sf + 3 * rr + cc];
     }
     const int rt = r0 + nfr;                     // torque limits (main.cpp:1054-1057, 1088-1095)
+#pragma unroll 1
     for (int k = lane; k < 12 * 31; k += Ex::NL) {
         const int a = k / 31, b = k % 31;
         double v = 0.0, vn = 0.0;
@@ -110,6 +123,7 @@ WBC_HDN inline void assemble_qp(const Ex& ex, const Params& P, const double* rec
     }
     int rq = rt + 24;
     if (sh.nst == 2) {                           // swing-foot tracking with slack (main.cpp:1251-1262, 1378-1379)
+#pragma unroll 1
         for (int k = lane; k < 6 * 31; k += Ex::NL) {
             const int a = k / 31, b = k % 31;
             const int ra = sh.swrow[a / 3] + a % 3;
@@ -123,6 +137,7 @@ WBC_HDN inline void assemble_qp(const Ex& ex, const Params& P, const double* rec
         }
         rq += 12;
     }
+#pragma unroll 1
     for (int a = lane; a < 12; a += Ex::NL) {    // joint-acceleration limits (main.cpp:1058-1059, 1098-1107)
         L[(rq + a) * 31 + 6 + a] = 1.0;
         L[(rq + a) * 31 + 30] = rec[QR_DDQMAX + a];
@@ -144,22 +159,28 @@ WBC_HDN inline void torque_and_objective(const Ex& ex, const Params& P, const do
     const double* Jj = rec + QR_JJ;
     const double* Wc = rec + QR_WCOM;
     const int nf = 3 * sh.nst;
+#pragma unroll 1
     for (int a = lane; a < 12; a += Ex::NL) {
         double s = 0.0;
+#pragma unroll 1
         for (int b = 0; b < 12; b++) s += Mjj[a * 12 + b] * x[6 + b];
         s += hj[a];
         double jf = 0.0;
+#pragma unroll 1
         for (int t = 0; t < nf; t++) jf += Jj[(sh.strow[t / 3] + t % 3) * 12 + a] * x[18 + t];
         tau_out[(long)a * tau_ld] = s - jf;
     }
     if (obj_out) {
         // x'Qx = sum_i R_ii x_i^2 + q1 |Jst_c' f|^2 ;  c'x = -q1 (Jst_c' f) . Wcom_des
         double sq = 0.0;
+#pragma unroll 1
         for (int k = lane; k < 30; k += Ex::NL) sq += ((sh.nst == 2 && k >= 24) ? P.slack_weight : 1.0) * x[k] * x[k];
         sq = wbcqp::red_sum1(ex, sq);
         double jj = 0.0, jw = 0.0;
+#pragma unroll 1
         for (int t = lane; t < 6; t += Ex::NL) {
             double s = 0.0;
+#pragma unroll 1
             for (int a = 0; a < nf; a++) s += Jc[(sh.strow[a / 3] + a % 3) * 6 + t] * x[18 + a];
             jj += s * s;
             jw += s * Wc[t];

@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include <new>
 
@@ -297,6 +298,7 @@ struct wbc_ctx {
     int order_n;         // batch size `cost` and the current histogram describe (0 = none)
     int hist_sel;        // which histogram the last solve filled
     int nblocks, threads;   // solver launch shape
+    int solve_smem;         // dynamic shared memory per solver CTA (sl::BYTES, or padded by WBC_SOLVE_CTAS_PER_SM)
     // staging for WBC_HOST_PTRS
     double* d_in;        // [93+40][max_batch]
     double* d_out;       // [50][max_batch]
@@ -364,6 +366,16 @@ int wbc_create(wbc_ctx** out, int device, int max_batch, const wbc_params* param
     const size_t nb = (size_t)max_batch;
     c->threads = SOLVE_T;
     c->nblocks = c->sm_count * SOLVE_CTAS_PER_SM;
+    c->solve_smem = sl::BYTES;
+    // occupancy experiment knob: fewer resident solver warps per SM (the shared-memory request is padded so that
+    // exactly that many CTAs fit); used by tools/ to measure how throughput scales with resident warps
+    if (const char* ev = getenv("WBC_SOLVE_CTAS_PER_SM")) {
+        const int k = atoi(ev);
+        if (k >= 1 && k < SOLVE_CTAS_PER_SM) {
+            c->nblocks = c->sm_count * k;
+            c->solve_smem = (((227 * 1024) / k - 1024) / 16) * 16;
+        }
+    }
     const long nteams = c->nblocks;
     cudaError_t e = cudaSuccess;
 #define TRY(call) if (e == cudaSuccess) e = (call)
@@ -387,8 +399,8 @@ int wbc_create(wbc_ctx** out, int device, int max_batch, const wbc_params* param
     TRY(cudaMemset(c->yd, 0, nb * 6 * sizeof(double)));
     TRY(cudaMemset(c->yw, 0, nb * 6 * sizeof(double)));
     TRY(cudaMemset(c->scratch, 0, (size_t)nteams * gl::TOTAL * sizeof(double)));
-    TRY(cudaFuncSetAttribute(wbc_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sl::BYTES));
-    TRY(cudaFuncSetAttribute(wbc_dense_qp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sl::BYTES));
+    TRY(cudaFuncSetAttribute(wbc_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->solve_smem));
+    TRY(cudaFuncSetAttribute(wbc_dense_qp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->solve_smem));
     TRY(cudaFuncSetAttribute(wbc_solve_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     TRY(cudaFuncSetAttribute(wbc_dense_qp_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 #undef TRY
@@ -526,7 +538,7 @@ int wbc_cycle(wbc_ctx* c, int n, const wbc_inputs* in, const wbc_outputs* out, v
     wbc_front_kernel<<<(n + fthreads - 1) / fthreads, fthreads, 0, s>>>(c->params, din, st, n, c->recs, w_ptr, w_ld, nodbg, 0, ord);
     CU(cudaEventRecord(c->ev1, s));
     const int nblocks = n < c->nblocks ? n : c->nblocks;
-    wbc_solve_kernel<<<nblocks, c->threads, sl::BYTES, s>>>(c->params, n, c->recs, so, c->scratch, c->queue, ordered ? c->order : nullptr,
+    wbc_solve_kernel<<<nblocks, c->threads, c->solve_smem, s>>>(c->params, n, c->recs, so, c->scratch, c->queue, ordered ? c->order : nullptr,
                                                            c->cost, hist_next);
     CU(cudaEventRecord(c->ev2, s));
     CU(cudaGetLastError());
@@ -700,7 +712,7 @@ int wbc_qp_solve(wbc_ctx* c, int n, const double* Q, const double* cvec, const d
     const int nblocks = n < c->nblocks ? n : c->nblocks;
     CU(cudaEventRecord(c->ev0, s));
     CU(cudaEventRecord(c->ev1, s));
-    wbc_dense_qp_kernel<<<nblocks, c->threads, sl::BYTES, s>>>(c->params, n, dQ, dc, dL, nrows, neq, dx, dstatus, dinfo, dflops, c->scratch, c->queue);
+    wbc_dense_qp_kernel<<<nblocks, c->threads, c->solve_smem, s>>>(c->params, n, dQ, dc, dL, nrows, neq, dx, dstatus, dinfo, dflops, c->scratch, c->queue);
     CU(cudaEventRecord(c->ev2, s));
     CU(cudaGetLastError());
     c->launches = 1;
