@@ -138,143 +138,166 @@ __device__ __noinline__ void eval4(double xcA, double xcB, double dA, double dB,
     __syncwarp();
 }
 
-// Cholesky of the masked, regularised E into the packed factor (see chol_cols in qp_warp.cuh for the layout),
-// two columns per step.  Row c of the factor is owned by lane c & 31 (slot c >> 5).  diagA / diagB: the diagonal
-// E_ii + regulariser (1 for a fixed variable) in two-slot form; freeB: slack variable 30 + lane is free.
+// ---- Constrained-Newton linear algebra, slack block first ------------------------------------------------
+// The model matrix of the free variables is  E_FF = [Hreg, B'; B, D]  with B = the rows rho c_k of the free slack
+// variables and D = diag(d_k) (d_k = rho + regulariser).  ALGLIB factors it with the slack variables last
+// (opt.cpp:31058-31201); the same matrix is factored here with the slack block FIRST: its Cholesky factor is the
+// diagonal sqrt(D), the coupling block is T = D^-1/2 B, and only the 30 x 30 Schur complement
+//     M = Hreg - T'T = U'U
+// is factored densely.  Same matrix, same solution of E_FF d = -g up to rounding; a third of the flops of the
+// (30 + nic)^3/3 factorisation, every row owned by exactly one lane, and no dependence on nic in the code shape.
+//   * T [nic][32] lives behind the packed 30 x 30 factor in the Z array (rows of fixed variables are not used);
+//   * fixing slack k after the build (qqpsolver_cnewtonupdate, opt.cpp:31314-31426) turns row/column k of E_FF into
+//     the identity, i.e. M <- M + T_k T_k': a rank-one update of U;
+//   * the Newton direction:  dx = M^-1 (-g_x + B' D^-1 g_s),  ds = -D^-1 (g_s + B dx).
+constexpr int OFF_T = 464;      // offset of T in the Z array (zoff(30) = 450, 16-byte aligned rows of 32)
+static_assert(OFF_T + NICCAP * 32 <= 1152, "T fits behind the 30 x 30 factor");
+
+// rsB: 1/sqrt(d_k) of slack lane k (free variables only); diagA: regularised diagonal of main variable `lane`.
 // Returns false on a non-positive pivot.
-__device__ __noinline__ bool chol_build(int n, double diagA, double diagB, int freeB)
+__device__ __noinline__ bool chol_build30(double diagA, double rsB, unsigned fmask)
 {
     const int l = threadIdx.x & 31;
     double* Z = wbc_smem + sl::OFF_Z;
+    double* T = Z + OFF_T;
     double* zd = wbc_smem + sl::OFF_V + V_ZD * VLS;
     double* zrinv = wbc_smem + sl::OFF_V + V_ZRINV * VLS;
-    const double* H = wbc_smem + sl::OFF_H;
-    const double* CI = wbc_smem + sl::OFF_CI;
-    // rows: c0 = l, c1 = l + 32.  a(k, c) for a main column k < 30:
-    //   c < 30: H[k][c];  c >= 30: free(c) * CI[c-30][k]
-    const int c0 = l, c1 = l + 32;
-    const double* src0 = (c0 < NMAIN) ? H + c0 : CI + (c0 - NMAIN) * LDH;
-    const int str0 = (c0 < NMAIN) ? LDH : 1;
-    const double* src1 = CI + (c1 - NMAIN) * LDH;
-    // the free flags and diagonals of rows c0 / c1 come from the two-slot registers of other lanes
-    const int f30 = __shfl_sync(FULL, freeB, 0), f31 = __shfl_sync(FULL, freeB, 1);
-    const int fB1 = __shfl_sync(FULL, freeB, (l + 2) & 31);           // slack index of row c1 = l + 2
-    const double m0 = (c0 < NMAIN) ? 1.0 : ((c0 == NMAIN ? f30 : f31) ? 1.0 : 0.0);
-    const double m1 = (c1 < n && fB1) ? 1.0 : 0.0;
-    const double dg30 = bshfl(diagB, 0), dg31 = bshfl(diagB, 1);
-    const double dgB1 = bshfl(diagB, (l + 2) & 31);
-    const double dg0 = (c0 < NMAIN) ? diagA : (c0 == NMAIN ? dg30 : dg31);
-    const double dg1 = dgB1;
-    double* r0 = Z + zoff(c0);
-    double* r1 = Z + zoff(c1 < n ? c1 : 0);
-    const bool has1 = n > 32;
-    for (int k = 0; k < n; k += 2) {
-        const bool two = (k + 1 < n);
+    const double* H = wbc_smem + sl::OFF_H + l;             // column l (H symmetric); lanes 30, 31 read finite in-bounds values
+    const double* CI = wbc_smem + sl::OFF_CI + l;
+#pragma unroll 1
+    for (unsigned m = fmask; m; m &= m - 1u) {
+        const int k = __ffs((int)m) - 1;
+        const double rs = bshfl(rsB, k);
+        T[k * 32 + l] = (l < NMAIN) ? CI[k * LDH] * rs : 0.0;
+    }
+    __syncwarp();
+    const int c = l;
+    double* r0 = Z + zoff(c < NMAIN ? c : NMAIN - 1);
+    const double* Tc = T + l;
+#pragma unroll 1
+    for (int k = 0; k < NMAIN; k += 2) {
         const double* rk = Z + zoff(k);
-        const double* rk1 = Z + zoff(two ? k + 1 : k);
-        // dots over m < k (k even: whole pairs)
-        double p00 = 0.0, p01 = 0.0, p10 = 0.0, p11 = 0.0;     // [slot][column]
-        double q00 = 0.0, q01 = 0.0, q10 = 0.0, q11 = 0.0;
+        const double* rk1 = Z + zoff(k + 1);
+        double p0 = 0.0, q0 = 0.0, p1 = 0.0, q1 = 0.0;
 #pragma unroll 1
         for (int m = 0; m < k; m += 2) {
-            const double2 zk = ld2(rk + m), zk1 = ld2(rk1 + m);
-            const double2 z0 = ld2(r0 + m);
-            p00 += z0.x * zk.x; q00 += z0.y * zk.y;
-            p01 += z0.x * zk1.x; q01 += z0.y * zk1.y;
-            if (has1) {
-                const double2 z1 = ld2(r1 + m);
-                p10 += z1.x * zk.x; q10 += z1.y * zk.y;
-                p11 += z1.x * zk1.x; q11 += z1.y * zk1.y;
-            }
+            const double2 zk = ld2(rk + m), zk1 = ld2(rk1 + m), z0 = ld2(r0 + m);
+            p0 += z0.x * zk.x; q0 += z0.y * zk.y;
+            p1 += z0.x * zk1.x; q1 += z0.y * zk1.y;
         }
-        // matrix entries of the two columns
-        double a00, a01, a10, a11;
-        if (k < NMAIN) {        // k even, so k + 1 < 30 too
-            a00 = src0[k * str0] * m0; a01 = src0[(k + 1) * str0] * m0;
-            a10 = has1 ? src1[k] * m1 : 0.0; a11 = has1 ? src1[k + 1] * m1 : 0.0;
-        } else { a00 = a01 = a10 = a11 = 0.0; }
-        if (c0 == k) a00 = dg0;
-        if (c0 == k + 1) a01 = dg0;
-        if (c1 == k) a10 = dg1;
-        if (c1 == k + 1) a11 = dg1;
-        double v00 = a00 - (p00 + q00), v01 = a01 - (p01 + q01);
-        double v10 = a10 - (p10 + q10), v11 = a11 - (p11 + q11);
-        // column k
-        const double piv0 = bshfl((k < 32) ? v00 : v10, k & 31);
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll 1
+        for (unsigned m = fmask; m; m &= m - 1u) {
+            const int i = __ffs((int)m) - 1;
+            const double tc = Tc[i * 32];
+            const double2 tk = ld2(T + i * 32 + k);
+            s0 += tc * tk.x; s1 += tc * tk.y;
+        }
+        double v0 = ((c == k) ? diagA : H[k * LDH]) - s0 - (p0 + q0);
+        double v1 = ((c == k + 1) ? diagA : H[(k + 1) * LDH]) - s1 - (p1 + q1);
+        const double piv0 = bshfl(v0, k);
         if (!(piv0 > 0.0)) return false;
         const double ri0 = rsqrt(piv0);
-        const double z0k = v00 * ri0, z1k = v10 * ri0;          // meaningful for rows c > k
-        if (c0 > k && c0 < n) r0[k] = z0k;
-        if (has1 && c1 > k && c1 < n) r1[k] = z1k;
-        if (l == 0) { zd[k] = piv0 * ri0; zrinv[k] = ri0; }
-        if (two) {
-            // column k + 1: subtract the contribution of column k
-            const double zk1k = bshfl(((k + 1) < 32) ? z0k : z1k, (k + 1) & 31);
-            v01 -= z0k * zk1k;
-            v11 -= z1k * zk1k;
-            const double piv1 = bshfl(((k + 1) < 32) ? v01 : v11, (k + 1) & 31);
-            if (!(piv1 > 0.0)) return false;
-            const double ri1 = rsqrt(piv1);
-            if (c0 > k + 1 && c0 < n) r0[k + 1] = v01 * ri1;
-            if (has1 && c1 > k + 1 && c1 < n) r1[k + 1] = v11 * ri1;
-            if (l == 0) { zd[k + 1] = piv1 * ri1; zrinv[k + 1] = ri1; }
+        const double z0k = v0 * ri0;
+        if (c > k && c < NMAIN) r0[k] = z0k;
+        const double zk1k = bshfl(z0k, k + 1);
+        v1 -= z0k * zk1k;
+        const double piv1 = bshfl(v1, k + 1);
+        if (!(piv1 > 0.0)) return false;
+        const double ri1 = rsqrt(piv1);
+        if (c > k + 1 && c < NMAIN) r0[k + 1] = v1 * ri1;
+        if (l == 0) {
+            *reinterpret_cast<double2*>(zd + k) = make_double2(piv0 * ri0, piv1 * ri1);
+            *reinterpret_cast<double2*>(zrinv + k) = make_double2(ri0, ri1);
         }
         __syncwarp();
     }
     return true;
 }
 
-// Solve U'U x = rhs with the packed factor; rhs and result in shared memory at `x` (index = variable).
-// Row c of the factor is owned by lane c & 31 (slot c >> 5).  The running right-hand side stays in registers; the
-// owner of component k never touches it again after step k, so scaling by 1/U_kk is done once at the end of each sweep.
-__device__ __noinline__ void tri_solve(double* x, int n)
+// Solve U'U x = rhs (30 x 30 packed factor); rhs and result in shared memory at x[0..30).
+__device__ __noinline__ void tri_solve30(double* x)
 {
     const int l = threadIdx.x & 31;
     const double* Z = wbc_smem + sl::OFF_Z;
-    const double* zrinv = wbc_smem + sl::OFF_V + V_ZRINV * VLS;
-    const int c1 = l + 32;
-    const double* r0 = Z + zoff(l);
-    const double* r1 = Z + zoff(c1 < n ? c1 : 0);
-    const double zr0 = zrinv[l], zr1 = zrinv[c1 < n ? c1 : 0];
-    double x0 = x[l], x1 = (c1 < n) ? x[c1] : 0.0;          // lanes >= n (n < 32) carry finite garbage that is never broadcast
-    const int n0 = n < 32 ? n : 32;
-    // forward: U' y = rhs, column oriented
+    const double* r0 = Z + zoff(l < NMAIN ? l : NMAIN - 1);
+    const double zr0 = wbc_smem[sl::OFF_V + V_ZRINV * VLS + l];
+    double x0 = x[l];                                       // lanes 30, 31 carry finite values that are never broadcast
 #pragma unroll 1
-    for (int k = 0; k < n0; k++) {
+    for (int k = 0; k < NMAIN; k++) {                       // forward: U' y = rhs, column oriented
         const double yk = bshfl(x0 * zr0, k);
         if (l > k) x0 -= r0[k] * yk;
-        x1 -= r1[k] * yk;
     }
+    x0 *= zr0;
 #pragma unroll 1
-    for (int k = 32; k < n; k++) {
-        const double yk = bshfl(x1 * zr1, k - 32);
-        if (c1 > k) x1 -= r1[k] * yk;
-    }
-    x0 *= zr0; x1 *= zr1;
-    // backward: U x = y
-#pragma unroll 1
-    for (int k = n - 1; k >= 32; k--) {
-        const double xk = bshfl(x1 * zr1, k - 32);
-        const double* rk = Z + zoff(k);
-        x0 -= rk[l] * xk;
-        if (c1 < k) x1 -= rk[c1] * xk;
-    }
-#pragma unroll 1
-    for (int k = n0 - 1; k >= 0; k--) {
+    for (int k = NMAIN - 1; k >= 0; k--) {                  // backward: U x = y
         const double xk = bshfl(x0 * zr0, k);
         const double* rk = Z + zoff(k);
         if (l < k) x0 -= rk[l] * xk;
     }
-    x0 *= zr0; x1 *= zr1;
+    x0 *= zr0;
     __syncwarp();
-    if (l < n) x[l] = x0;
-    if (c1 < n) x[c1] = x1;
+    if (l < NMAIN) x[l] = x0;
     __syncwarp();
 }
 
-__device__ __noinline__ void givens_fix(int n, int k)
+// U'U <- U'U + T_k T_k'  (slack variable k leaves the free set)
+__device__ __noinline__ void rank1_fix30(int k)
 {
-    givens_fix_regs<2>(WarpEx(), wbc_smem + sl::OFF_Z, wbc_smem + sl::OFF_V + V_ZD * VLS, wbc_smem + sl::OFF_V + V_ZRINV * VLS, n, k);
+    const int l = threadIdx.x & 31;
+    double* Z = wbc_smem + sl::OFF_Z;
+    double* zd = wbc_smem + sl::OFF_V + V_ZD * VLS;
+    double* zrinv = wbc_smem + sl::OFF_V + V_ZRINV * VLS;
+    double x = (l < NMAIN) ? Z[OFF_T + k * 32 + l] : 0.0;
+    const unsigned nz = __ballot_sync(FULL, x != 0.0);
+    if (nz == 0u) return;
+    double* r0 = Z + zoff(l < NMAIN ? l : NMAIN - 1);
+#pragma unroll 1
+    for (int j = __ffs((int)nz) - 1; j < NMAIN; j++) {
+        const double xj = bshfl(x, j);
+        if (xj == 0.0) continue;
+        const double ljj = zd[j], zri = zrinv[j];
+        const double rr = ljj * ljj + xj * xj;
+        const double rinv = rsqrt(rr);
+        const double r = rr * rinv;
+        const double s = xj * zri, ci = ljj * rinv, cc = r * zri;
+        if (l > j && l < NMAIN) {
+            const double lcj = (r0[j] + s * x) * ci;
+            x = cc * x - s * lcj;
+            r0[j] = lcj;
+        }
+        __syncwarp();
+        if (l == 0) { zd[j] = r; zrinv[j] = rinv; }
+    }
+    __syncwarp();
+}
+
+// Newton direction from the gradient (two-slot registers; gB already zeroed on fixed slack variables, winvB = 1/d_k on the
+// free ones and 0 elsewhere).  The direction is written to the mirror `sdc` (main and slack part, pad entry untouched).
+__device__ __noinline__ void newton_direction(double gA, double gB, double winvB, unsigned freemask, int nic)
+{
+    const int l = threadIdx.x & 31;
+    double* sdc = wbc_smem + sl::OFF_V + V_DC * VLS;
+    const double* CIc = wbc_smem + sl::OFF_CI + l;
+    const double u = gB * winvB;
+    double r = -gA;
+#pragma unroll 1
+    for (unsigned m = freemask; m; m &= m - 1u) {
+        const int k = __ffs((int)m) - 1;
+        r += CIc[k * LDH] * bshfl(u, k);
+    }
+    if (l < NMAIN) sdc[l] = r;
+    __syncwarp();
+    tri_solve30(sdc);
+    const double* row = wbc_smem + sl::OFF_CI + (l < nic ? l : 0) * LDH;
+    double t0 = 0.0, t1 = 0.0;
+#pragma unroll 1
+    for (int j = 0; j < NMAIN; j += 2) {
+        const double2 dv = ld2(sdc + j);
+        t0 += row[j] * dv.x; t1 += row[j + 1] * dv.y;
+    }
+    if (l < nic) sdc[NMAIN + l] = -(gB + (t0 + t1)) * winvB;
+    __syncwarp();
 }
 
 __device__ __forceinline__ void red3(double& a, double& b, double& c)
@@ -466,6 +489,7 @@ __device__ __noinline__ int qqp_optimize_fast(const Work w, int nic, double rho,
     const bool vA = l < NMAIN, vB = l < nic;
     int nsymv = 0;                      // products with E (2 n^2 flops each), for the instrumented flop count
     int nchol = 0, nfree = 0, cnmodelage = 0;
+    int nschur = 0, nfix = 0;           // slack rows folded into Schur complements / solves, rank-one fixes (flop count)
     double* sxc = wbc_smem + sl::OFF_V + V_XC * VLS;
     double* sdc = wbc_smem + sl::OFF_V + V_DC * VLS;
     const double* spare = wbc_smem + sl::OFF_V + V_SPARE * VLS;
@@ -544,18 +568,22 @@ __device__ __noinline__ int qqp_optimize_fast(const Work w, int nic, double rho,
         // constrained Newton phase (30353-30527)
         int newtcnt = 0;
         int freeB = 0;
+        double winvB = 0.0;
 #pragma unroll 1
         for (;;) {
             bool b;
             if (newtcnt == 0) {
-                // qqpsolver_cnewtonbuild (31058-31201): free set, regularised diagonal, factorisation
+                // qqpsolver_cnewtonbuild (31058-31201): free set, regularised diagonal, factorisation (slack block first)
                 freeB = vB ? !(xcB == 0.0) : 0;
                 const unsigned fmask = __ballot_sync(FULL, freeB != 0);
                 nfree = NMAIN + __popc(fmask);
                 cnmodelage = 0;
                 nchol++;
+                nschur += __popc(fmask);
                 const double2 dg = newton_diag(nic, rho, fmask);
-                b = chol_build(n, dg.x, dg.y, freeB);
+                const double rsB = freeB ? rsqrt(dg.y) : 0.0;
+                winvB = rsB * rsB;
+                b = chol_build30(dg.x, rsB, fmask);
                 if (b) cgmax = cgminits;
             } else {
                 // qqpsolver_cnewtonupdate (31314-31426)
@@ -567,11 +595,11 @@ __device__ __noinline__ int qqp_optimize_fast(const Work w, int nic, double rho,
                 else if (cnmodelage + ntofix > cnmaxupdates) b = false;
                 else {
 #pragma unroll 1
-                    for (int k = 0; k < nic; k++)
-                        if ((fixmask >> k) & 1u) givens_fix(n, NMAIN + k);
-                    if (tofix) freeB = 0;
+                    for (unsigned m = fixmask; m; m &= m - 1u) rank1_fix30(__ffs((int)m) - 1);
+                    if (tofix) { freeB = 0; winvB = 0.0; }
                     nfree -= ntofix;
                     cnmodelage += ntofix;
+                    nfix += ntofix;
                     b = true;
                 }
             }
@@ -583,10 +611,8 @@ __device__ __noinline__ int qqp_optimize_fast(const Work w, int nic, double rho,
             const double ngA = gA, ngB = (vB && freeB) ? gB : 0.0;
             const double gg = wsum(ngA * ngA + ngB * ngB);
             if (gg <= 0.0) break;
-            if (vA) sdc[l] = -ngA;
-            if (vB) sdc[NMAIN + l] = -ngB;
-            __syncwarp();
-            tri_solve(sdc, n);
+            newton_direction(ngA, ngB, winvB, __ballot_sync(FULL, freeB != 0), nic);
+            nschur += 2;
             const double dA = vA ? sdc[l] : 0.0, dB = vB ? sdc[NMAIN + l] : 0.0;
             const int code = quadratic_model(dA, dB, gA, gB, xcA, xcB, nic2, rho, absasum, absasum2, mb);
             const int d1est = (code >> 2) - 1, d2est = (code & 3) - 1;
@@ -616,7 +642,8 @@ __device__ __noinline__ int qqp_optimize_fast(const Work w, int nic, double rho,
     if (vB) exxc[NMAIN + l] = (xcB < 0.0 || xcB == 0.0) ? 0.0 : xcB;
     __syncwarp();
     *ncholesky += nchol;
-    *flops_io += 2.0 * n * n * (double)nsymv + (double)nchol * ((double)n * n * n / 3.0);
+    // work actually done: products with E, 30^3/3 per factorisation, 30^2 per slack row folded in, 3 * 30^2 per rank-one fix
+    *flops_io += 2.0 * n * n * (double)nsymv + (double)nchol * 9000.0 + 900.0 * (double)nschur + 2700.0 * (double)nfix;
     return term;
 }
 

@@ -1,6 +1,6 @@
 // Assembly of the ground-reaction-force QP (Q, c, L) from the compact QP record, and the maps back
 // from the QP solution to joint torques and objective value.  Team-cooperative (executor `Ex`, see
-// qp_denseaul.cuh).  Layouts follow the reference exactly:
+// qp_warp.cuh).  Layouts follow the reference exactly:
 //   stance  main.cpp:984-1120   x = [ddq_com(6) | ddq_j(12) | f(12)],          L 86 x 31, 18 equalities
 //   swing   main.cpp:1163-1389  x = [ddq_com(6) | ddq_j(12) | f_st(6) | g(6)], L 82 x 31, 12 equalities
 //   torque  main.cpp:1126, 1396 tau = Mjj ddq_j + h_j - Jst_j' f
