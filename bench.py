@@ -245,14 +245,25 @@ def main():
     e2e_steps = args.steps
     want = ("x",) if sweep else ()
 
-    def e2e_step():
-        out = batch.cycle(sc, want=want)
-        if sweep:   # host-side rollout: the plant's H2D/D2H copies are part of the step too
-            batch.plant_step(sc["base_pos"], sc["base_vel"], sc["push"], foot_force=sc["foot_force"], x=out["x"])
-        return out
+    # the caller's arrays live in page-locked host memory (wbc_host_alloc), as a controller process feeding the
+    # batch every cycle would keep them: wbc_cycle then DMAs them directly (pageable arrays take its bounce buffer)
+    sc_host = batch.pinned_inputs(sc)
+    for k in ("push",):
+        if k in sc_host and isinstance(sc_host[k], np.ndarray):
+            sc_host[k] = batch.pinned_copy(np.ascontiguousarray(sc_host[k]))
+    out_pin = {"tau": batch.pinned((12, n)), "w": batch.pinned((6, n))}
     if sweep:
-        batch.set_observer_state(sc["obs_yd"], sc["obs_yw"])
-    for _ in range(2):
+        out_pin["x"] = batch.pinned((30, n))
+
+    def e2e_step():
+        out = batch.cycle(sc_host, want=want, out=out_pin)
+        if sweep:   # host-side rollout: the plant's H2D/D2H copies are part of the step too
+            batch.plant_step(sc_host["base_pos"], sc_host["base_vel"], sc_host["push"], foot_force=sc_host["foot_force"], x=out["x"])
+        return out
+    # same observer trajectory as the device-resident loop: the estimate feeds back into the QP (main.cpp:1032), so the
+    # work per cycle drifts as the observer integrates; both loops start from the scenario's initial observer state
+    batch.set_observer_state(sc["obs_yd"], sc["obs_yw"])
+    for _ in range(args.warmup):
         e2e_step()
     if world > 1:
         dist.barrier()

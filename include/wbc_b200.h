@@ -29,6 +29,7 @@
 #ifndef WBC_B200_H
 #define WBC_B200_H
 
+#include <stddef.h>
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -51,6 +52,8 @@ extern "C" {
 #define WBC_FIFO_DISPATCH 4u     /* wbc_cycle: hand instances to the solver warps in index order.  Default: longest solve first,
                                     predicted from each instance's previous cycle on this ctx with the same n (the ctx keeps a
                                     per-instance duration); the order never changes a result, only when the batch's tail ends. */
+#define WBC_HOST_SLAB 8u         /* (host pointers) the input arrays are carved, in wbc_inputs field order, from ONE page-locked
+                                  * allocation with ld == n: adjacent fields are moved with a single copy */
 
 typedef struct wbc_ctx wbc_ctx;
 
@@ -172,8 +175,18 @@ int wbc_plant_step(wbc_ctx* ctx, int n, double* base_pos, double* base_vel, doub
 
 /* Device-side timing of the last wbc_cycle on this ctx (CUDA events on the launching stream), ms. */
 int wbc_last_timing(wbc_ctx* ctx, float* front_ms, float* solve_ms);
+/* Per-instance solve duration of the last wbc_cycle on this ctx, in SM clock cycles (clock64 around the instance's
+ * set-up + DENSE-AUL solve + torque map; the same figure that orders the next cycle's longest-first dispatch).
+ * cycles [n], host pointer; synchronises the ctx's last launch stream work via a blocking copy. */
+int wbc_last_solve_cycles(wbc_ctx* ctx, int n, unsigned long long* cycles);
 /* Number of kernels launched by the last wbc_cycle / wbc_qp_solve. */
 int wbc_last_launches(wbc_ctx* ctx);
+
+/* Page-locked host memory for the SoA arrays handed to wbc_cycle with WBC_HOST_PTRS.  Arrays that are page-locked
+ * (from here, cudaMallocHost or cudaHostRegister) are copied to and from the device directly; pageable arrays go
+ * through the ctx's pinned bounce buffer (one extra host-side pass over the data). */
+int wbc_host_alloc(void** p, size_t bytes);
+int wbc_host_free(void* p);
 
 /* FP64 DFMA peak microbenchmark (roofline denominator): returns achieved FLOP/s on the ctx's device. */
 int wbc_measure_dfma_peak(wbc_ctx* ctx, double* flops_per_s);

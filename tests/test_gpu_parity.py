@@ -199,3 +199,36 @@ def test_device_pointer_path_with_torch(gpu_batch):
     gpu_batch.cycle_device(dev_in, dev_out, n, n, stream=torch.cuda.current_stream().cuda_stream)
     assert np.array_equal(dev_out["tau"].cpu().numpy(), host["tau"])
     assert np.array_equal(dev_out["w"].cpu().numpy(), host["w"])
+
+
+def test_page_locked_arrays_take_the_direct_copy_path_with_identical_results(gpu_batch):
+    """wbc_host_alloc'ed SoA arrays are DMA'd directly (no bounce buffer); results are bit-identical to the pageable
+    path, with a padded leading dimension (ld > n) and preallocated page-locked outputs."""
+    sc, gold = util.load_golden("cycle_trot_pushes")
+    n = sc["mode"].shape[0]
+    ref = _run(gpu_batch, sc)
+    ld = n + 7
+    pin = {}
+    for k, v in sc.items():
+        if not isinstance(v, np.ndarray) or k in ("obs_yd", "obs_yw"):
+            pin[k] = v
+            continue
+        shape = (v.shape[0], ld) if v.ndim == 2 else (ld,)
+        a = gpu_batch.pinned(shape, v.dtype)
+        a[...] = 0
+        a[..., :n] = v
+        pin[k] = a
+    out = {"tau": gpu_batch.pinned((12, n)), "w": gpu_batch.pinned((6, n)), "x": gpu_batch.pinned((30, n)), "qp_obj": gpu_batch.pinned((n,))}
+    gpu_batch.set_observer_state(sc["obs_yd"], sc["obs_yw"])
+    got = gpu_batch.cycle(pin, n=n, out=out)
+    for k in ("tau", "w", "x", "qp_obj"):
+        assert np.array_equal(got[k], ref[k]), k
+    util.check_cycle_parity({**got, "status": ref["status"]}, gold, what="pinned")
+
+
+def test_last_solve_cycles_reports_every_instance(gpu_batch):
+    sc, _ = util.load_golden("cycle_standing")
+    n = sc["mode"].shape[0]
+    _run(gpu_batch, sc)
+    cyc = gpu_batch.last_solve_cycles(n)
+    assert cyc.shape == (n,) and (cyc > 0).all() and (cyc < 2e9).all()

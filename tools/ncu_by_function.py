@@ -46,7 +46,8 @@ def main():
     for name, d in sorted(agg.items(), key=lambda kv: -kv[1]["samples"]):
         top = sorted(d["stalls"].items(), key=lambda kv: -kv[1])[:4]
         short = re.sub(r"INS_6TeamExILi\d+EEE.*", "", name)
-        print("%-60s inst %5.1f%%  samples %5.1f%%  %s" % (short[:60], 100.0 * d["inst"] / max(tot_i, 1), 100.0 * d["samples"] / max(tot_s, 1),
+        noi = sum(v for k, v in d["stalls"].items() if "no_inst" in k)
+        print("%-60s inst %5.1f%%  samples %5.1f%%  no_inst(all) %4.2f%%  %s" % (short[:60], 100.0 * d["inst"] / max(tot_i, 1), 100.0 * d["samples"] / max(tot_s, 1), 100.0 * noi / max(tot_s, 1),
                                                          " ".join("%s=%.0f%%" % (k[6:], 100.0 * v / max(d["samples"], 1)) for k, v in top)))
 
 

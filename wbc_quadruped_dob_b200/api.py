@@ -20,7 +20,7 @@ import numpy as np
 from . import build as _build
 
 MODE_STANCE, MODE_SWING_BR_FL, MODE_SWING_BL_FR = 0, 1, 2
-HOST_PTRS, DEVICE_PTRS, NO_SYNC, FIFO_DISPATCH = 0, 1, 2, 4
+HOST_PTRS, DEVICE_PTRS, NO_SYNC, FIFO_DISPATCH, HOST_SLAB = 0, 1, 2, 4, 8
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
@@ -63,7 +63,8 @@ _lib = None
 
 EXPORTS = ["wbc_default_params", "wbc_last_error", "wbc_version", "wbc_create", "wbc_destroy", "wbc_set_params",
            "wbc_set_observer_state", "wbc_get_observer_state", "wbc_cycle", "wbc_debug_update", "wbc_qp_solve",
-           "wbc_plant_step", "wbc_last_timing", "wbc_last_launches", "wbc_measure_dfma_peak"]
+           "wbc_plant_step", "wbc_last_timing", "wbc_last_solve_cycles", "wbc_last_launches", "wbc_host_alloc", "wbc_host_free",
+           "wbc_measure_dfma_peak"]
 
 
 def lib_path():
@@ -93,7 +94,10 @@ def load():
     lib.wbc_plant_step.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_void_p,
                                    C.c_uint]
     lib.wbc_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    lib.wbc_last_solve_cycles.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_ulonglong)]
     lib.wbc_last_launches.argtypes = [C.c_void_p]
+    lib.wbc_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
+    lib.wbc_host_free.argtypes = [C.c_void_p]
     lib.wbc_measure_dfma_peak.argtypes = [C.c_void_p, _dp]
     _lib = lib
     return lib
@@ -132,12 +136,16 @@ class WbcBatch:
         h = C.c_void_p()
         _check(self.lib.wbc_create(C.byref(h), self.device, self.max_batch, C.byref(self.params)), "wbc_create")
         self.h = h
+        self._pinned = []
         self.fifo_dispatch = False      # True: WBC_FIFO_DISPATCH (index-order work queue instead of longest-first)
 
     def close(self):
         if getattr(self, "h", None):
             self.lib.wbc_destroy(self.h)
             self.h = None
+        for p in getattr(self, "_pinned", []):
+            self.lib.wbc_host_free(p)
+        self._pinned = []
 
     __del__ = close
 
@@ -195,22 +203,58 @@ class WbcBatch:
             raise WbcError("n exceeds the arrays' leading dimension")
         return ins
 
-    def cycle(self, sc, n=None, want=("x", "qp_obj", "status", "qp_info", "qp_flops")):
-        """One control cycle on HOST (numpy) SoA inputs; returns a dict of numpy arrays [k, n]."""
+    def pinned(self, shape, dtype=np.float64):
+        """A numpy array in page-locked host memory (wbc_host_alloc): wbc_cycle copies such arrays to / from the device
+        directly instead of through its bounce buffer.  Freed with the batch."""
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        _check(self.lib.wbc_host_alloc(C.byref(p), max(nbytes, 8)), "wbc_host_alloc")
+        self._pinned.append(p)
+        buf = (C.c_char * max(nbytes, 8)).from_address(p.value)
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def pinned_copy(self, a):
+        out = self.pinned(a.shape, a.dtype)
+        out[...] = a
+        return out
+
+    def pinned_inputs(self, sc):
+        """Copy a scenario's input arrays into ONE page-locked slab laid out in wbc_inputs field order, so that
+        wbc_cycle moves them with a single host-to-device copy.  Returns a dict of views (other keys passed through)."""
+        n = int(sc["mode"].shape[0])
+        fields = [(name, k) for name, k in IN_FIELDS if sc.get(name) is not None]
+        rows = sum(k for _, k in fields) + (1 if sc.get("obs_gain") is not None else 0)
+        slab = self.pinned((rows, n))
+        out, r = dict(sc), 0
+        for name, k in fields:
+            out[name] = slab[r:r + k]
+            out[name][...] = sc[name]
+            r += k
+        if sc.get("obs_gain") is not None:
+            out["obs_gain"] = slab[r]
+            out["obs_gain"][...] = sc["obs_gain"]
+        out["mode"] = self.pinned_copy(np.ascontiguousarray(sc["mode"], dtype=np.int32))
+        out["_slab"] = True          # cycle() passes WBC_HOST_SLAB
+        return out
+
+    def cycle(self, sc, n=None, want=("x", "qp_obj", "status", "qp_info", "qp_flops"), out=None):
+        """One control cycle on HOST (numpy) SoA inputs; returns a dict of numpy arrays [k, n].  `out`: preallocated
+        result arrays to fill (e.g. page-locked ones from pinned()); its keys decide what is returned."""
         keep = []
         n = int(sc["mode"].shape[0]) if n is None else int(n)
         ins = self._inputs_struct(sc, n, keep)
-        out = {"tau": np.zeros((12, n)), "w": np.zeros((6, n))}
-        if "x" in want: out["x"] = np.zeros((30, n))
-        if "qp_obj" in want: out["qp_obj"] = np.zeros(n)
-        if "status" in want: out["status"] = np.zeros(n, dtype=np.int32)
-        if "qp_info" in want: out["qp_info"] = np.zeros((8, n), dtype=np.int32)
-        if "qp_flops" in want: out["qp_flops"] = np.zeros(n)
+        if out is None:
+            out = {"tau": np.zeros((12, n)), "w": np.zeros((6, n))}
+            if "x" in want: out["x"] = np.zeros((30, n))
+            if "qp_obj" in want: out["qp_obj"] = np.zeros(n)
+            if "status" in want: out["status"] = np.zeros(n, dtype=np.int32)
+            if "qp_info" in want: out["qp_info"] = np.zeros((8, n), dtype=np.int32)
+            if "qp_flops" in want: out["qp_flops"] = np.zeros(n)
         o = _Outputs()
         for k in ("tau", "w", "x", "qp_obj", "status", "qp_info", "qp_flops"):
             setattr(o, k, _ptr(out.get(k)))
         o.ld = max(n, 1)
-        _check(self.lib.wbc_cycle(self.h, n, C.byref(ins), C.byref(o), None, HOST_PTRS | (FIFO_DISPATCH if self.fifo_dispatch else 0)), "wbc_cycle")
+        _check(self.lib.wbc_cycle(self.h, n, C.byref(ins), C.byref(o), None, HOST_PTRS | (FIFO_DISPATCH if self.fifo_dispatch else 0) | (HOST_SLAB if sc.get("_slab") else 0)), "wbc_cycle")
         return out
 
     def cycle_device(self, dev_in, dev_out, n, ld, stream=None, sync=True):
@@ -278,6 +322,12 @@ class WbcBatch:
         a, b = C.c_float(0), C.c_float(0)
         _check(self.lib.wbc_last_timing(self.h, C.byref(a), C.byref(b)), "wbc_last_timing")
         return a.value, b.value
+
+    def last_solve_cycles(self, n):
+        """Per-instance solve duration of the last cycle in SM clock cycles (numpy uint64 [n])."""
+        out = np.zeros(n, dtype=np.uint64)
+        _check(self.lib.wbc_last_solve_cycles(self.h, n, out.ctypes.data_as(C.POINTER(C.c_ulonglong))), "wbc_last_solve_cycles")
+        return out
 
     def last_launches(self):
         return int(self.lib.wbc_last_launches(self.h))

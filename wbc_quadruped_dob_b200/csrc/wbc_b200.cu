@@ -460,8 +460,19 @@ static int check_inputs(const wbc_inputs* in, int n)
     return WBC_OK;
 }
 
-// Stage host SoA inputs into the ctx's device buffers through the pinned bounce buffer (one H2D copy).
-static int stage_inputs(wbc_ctx* c, int n, const wbc_inputs* in, cudaStream_t s, DevInputs* dev)
+// Page-locked host memory (cudaMallocHost / cudaHostRegister) can be the source or target of an asynchronous copy
+// directly; pageable memory goes through the ctx's pinned bounce buffer.
+static bool is_pinned_host(const void* p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+// Stage host SoA inputs into the ctx's device buffers, one H2D copy per field so that the DMA of a field overlaps the
+// host-side packing of the next: straight from the caller's arrays when they are page-locked, else through the
+// pinned bounce buffer.
+static int stage_inputs(wbc_ctx* c, int n, const wbc_inputs* in, cudaStream_t s, DevInputs* dev, bool slab)
 {
     const double* src[15] = {in->base_pos, in->base_rot, in->base_rpy, in->base_vel, in->q, in->dq, in->com_des_pos, in->com_des_vel,
                              in->com_des_acc, in->sw_des_pos, in->sw_des_vel, in->sw_des_acc, in->foot_force, in->terrain, in->obs_gain};
@@ -469,13 +480,31 @@ static int stage_inputs(wbc_ctx* c, int n, const wbc_inputs* in, cudaStream_t s,
                               &dev->com_des_vel, &dev->com_des_acc, &dev->sw_des_pos, &dev->sw_des_vel, &dev->sw_des_acc,
                               &dev->foot_force, &dev->terrain, &dev->obs_gain};
     size_t off = 0;
+    const size_t row = (size_t)n * sizeof(double);
+    // a run of page-locked fields that are adjacent in host memory in field order (one slab, ld == n) is one copy
+    const double* run_src = nullptr;
+    size_t run_off = 0, run_rows = 0;
     for (int f = 0; f < 15; f++) {
         if (!src[f]) { *dst[f] = nullptr; continue; }
-        for (int k = 0; k < kInFieldK[f]; k++) memcpy(c->h_pin + off + (size_t)k * n, src[f] + (size_t)k * in->ld, (size_t)n * sizeof(double));
+        const int K = kInFieldK[f];
+        const bool pinned = is_pinned_host(src[f]);
+        if (run_src && !(slab && pinned && in->ld == n && src[f] == run_src + run_rows * n)) {
+            CU(cudaMemcpyAsync(c->d_in + run_off, run_src, run_rows * row, cudaMemcpyHostToDevice, s));
+            run_src = nullptr;
+        }
+        if (slab && pinned && in->ld == n) {
+            if (!run_src) { run_src = src[f]; run_off = off; run_rows = 0; }
+            run_rows += K;
+        } else if (pinned) {
+            CU(cudaMemcpy2DAsync(c->d_in + off, row, src[f], (size_t)in->ld * sizeof(double), row, K, cudaMemcpyHostToDevice, s));
+        } else {
+            for (int k = 0; k < K; k++) memcpy(c->h_pin + off + (size_t)k * n, src[f] + (size_t)k * in->ld, row);
+            CU(cudaMemcpyAsync(c->d_in + off, c->h_pin + off, row * K, cudaMemcpyHostToDevice, s));
+        }
         *dst[f] = c->d_in + off;
-        off += (size_t)kInFieldK[f] * n;
+        off += (size_t)K * n;
     }
-    CU(cudaMemcpyAsync(c->d_in, c->h_pin, off * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (run_src) CU(cudaMemcpyAsync(c->d_in + run_off, run_src, run_rows * row, cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(c->d_mode, in->mode, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, s));
     dev->mode = c->d_mode;
     dev->ld = n;
@@ -513,7 +542,7 @@ int wbc_cycle(wbc_ctx* c, int n, const wbc_inputs* in, const wbc_outputs* out, v
         w_ptr = out->w ? out->w : c->w_dev;
         w_ld = out->w ? out->ld : c->max_batch;
     } else {
-        rc = stage_inputs(c, n, in, s, &din);
+        rc = stage_inputs(c, n, in, s, &din, (flags & WBC_HOST_SLAB) != 0);
         if (rc) return rc;
         so.tau = c->d_out; so.x = out->x ? c->d_out + 18L * n : nullptr; so.qp_obj = out->qp_obj ? c->d_out + 48L * n : nullptr;
         so.qp_flops = out->qp_flops ? c->d_out + 49L * n : nullptr;
@@ -547,17 +576,26 @@ int wbc_cycle(wbc_ctx* c, int n, const wbc_inputs* in, const wbc_outputs* out, v
     c->hist_sel ^= 1;
     c->order_n = n;
     if (!dev_ptrs) {
-        // one D2H of the packed result block, then scatter into the caller's SoA arrays
-        // packed layout: tau 12 | w 6 | x 30 | obj 1 | flops 1 -- copy only the prefix the caller asked for
-        const size_t nd = (size_t)((out->qp_flops) ? 50 : (out->qp_obj ? 49 : (out->x ? 48 : 18))) * n;
-        CU(cudaMemcpyAsync(c->h_pin, c->d_out, nd * sizeof(double), cudaMemcpyDeviceToHost, s));
+        // results: straight into the caller's arrays where they are page-locked, else one D2H of the packed block
+        // (tau 12 | w 6 | x 30 | obj 1 | flops 1) into the bounce buffer and a scatter after the synchronisation
+        struct OutF { double* p; int k0, K; long ld; } of[5] = {{out->tau, 0, 12, out->ld}, {out->w, 12, 6, out->ld}, {out->x, 18, 30, out->ld},
+                                                                {out->qp_obj, 48, 1, n}, {out->qp_flops, 49, 1, n}};
+        bool direct[5];
+        const size_t row = (size_t)n * sizeof(double);
+        int hi = 0;                                   // bounce prefix, in rows
+        for (int f = 0; f < 5; f++) {
+            direct[f] = of[f].p && is_pinned_host(of[f].p);
+            if (of[f].p && !direct[f]) hi = of[f].k0 + of[f].K;
+        }
+        for (int f = 0; f < 5; f++)
+            if (direct[f])
+                CU(cudaMemcpy2DAsync(of[f].p, (size_t)of[f].ld * sizeof(double), c->d_out + (size_t)of[f].k0 * n, row, row, of[f].K, cudaMemcpyDeviceToHost, s));
+        if (hi) CU(cudaMemcpyAsync(c->h_pin, c->d_out, (size_t)hi * row, cudaMemcpyDeviceToHost, s));
         if (out->status || out->qp_info) CU(cudaMemcpyAsync(c->h_pin_i, c->d_iout, (size_t)kOutInts * n * sizeof(int), cudaMemcpyDeviceToHost, s));
         CU(cudaStreamSynchronize(s));
-        for (int k = 0; k < 12; k++) memcpy(out->tau + (size_t)k * out->ld, c->h_pin + (size_t)k * n, (size_t)n * 8);
-        if (out->w) for (int k = 0; k < 6; k++) memcpy(out->w + (size_t)k * out->ld, c->h_pin + (size_t)(12 + k) * n, (size_t)n * 8);
-        if (out->x) for (int k = 0; k < 30; k++) memcpy(out->x + (size_t)k * out->ld, c->h_pin + (size_t)(18 + k) * n, (size_t)n * 8);
-        if (out->qp_obj) memcpy(out->qp_obj, c->h_pin + (size_t)48 * n, (size_t)n * 8);
-        if (out->qp_flops) memcpy(out->qp_flops, c->h_pin + (size_t)49 * n, (size_t)n * 8);
+        for (int f = 0; f < 5; f++)
+            if (of[f].p && !direct[f])
+                for (int k = 0; k < of[f].K; k++) memcpy(of[f].p + (size_t)k * of[f].ld, c->h_pin + (size_t)(of[f].k0 + k) * n, row);
         if (out->status) memcpy(out->status, c->h_pin_i, (size_t)n * 4);
         if (out->qp_info) for (int k = 0; k < 8; k++) memcpy(out->qp_info + (size_t)k * out->ld, c->h_pin_i + (size_t)(1 + k) * n, (size_t)n * 4);
     } else if (!(flags & WBC_NO_SYNC)) {
@@ -621,7 +659,37 @@ int wbc_last_timing(wbc_ctx* c, float* front_ms, float* solve_ms)
     return WBC_OK;
 }
 
+int wbc_last_solve_cycles(wbc_ctx* c, int n, unsigned long long* cycles)
+{
+    if (!c || !cycles || n < 0 || n > c->max_batch) return fail(WBC_EINVAL, "wbc_last_solve_cycles: bad arguments");
+    if (n == 0) return WBC_OK;
+    CU(cudaSetDevice(c->device));
+    CU(cudaDeviceSynchronize());
+    unsigned* h = (unsigned*)malloc((size_t)n * sizeof(unsigned));
+    if (!h) return fail(WBC_ENOMEM, "out of host memory");
+    const cudaError_t e = cudaMemcpy(h, c->cost, (size_t)n * sizeof(unsigned), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess)
+        for (int i = 0; i < n; i++) cycles[i] = (unsigned long long)h[i] << 10;     // stored >> 10
+    free(h);
+    if (e != cudaSuccess) return fail(WBC_ECUDA, "wbc_last_solve_cycles: %s", cudaGetErrorString(e));
+    return WBC_OK;
+}
 int wbc_last_launches(wbc_ctx* c) { return c ? c->launches : 0; }
+
+int wbc_host_alloc(void** p, size_t bytes)
+{
+    if (!p || bytes == 0) return fail(WBC_EINVAL, "wbc_host_alloc: bad arguments");
+    const cudaError_t e = cudaMallocHost(p, bytes);
+    if (e != cudaSuccess) { *p = nullptr; return fail(e == cudaErrorMemoryAllocation ? WBC_ENOMEM : WBC_ECUDA, "wbc_host_alloc: %s", cudaGetErrorString(e)); }
+    return WBC_OK;
+}
+int wbc_host_free(void* p)
+{
+    if (!p) return WBC_OK;
+    const cudaError_t e = cudaFreeHost(p);
+    if (e != cudaSuccess) return fail(WBC_ECUDA, "wbc_host_free: %s", cudaGetErrorString(e));
+    return WBC_OK;
+}
 
 int wbc_debug_update(wbc_ctx* c, int n, const wbc_inputs* in, const wbc_debug* dbg, unsigned flags)
 {
@@ -634,7 +702,7 @@ int wbc_debug_update(wbc_ctx* c, int n, const wbc_inputs* in, const wbc_debug* d
     CU(cudaSetDevice(c->device));
     cudaStream_t s = c->stream;
     DevInputs din;
-    rc = stage_inputs(c, n, in, s, &din);
+    rc = stage_inputs(c, n, in, s, &din, (flags & WBC_HOST_SLAB) != 0);
     if (rc) return rc;
     static const int K[17] = {324, 18, 18, 216, 12, 3, 3, 36, 144, 18, 18, 216, 12, 12, 12, 12, 6};
     double* host[17] = {dbg->M, dbg->h, dbg->g, dbg->Jac_lin, dbg->Jdqd_lin, dbg->com, dbg->com_vel, dbg->Mcom_b, dbg->Mcom_j, dbg->hcom,
