@@ -52,6 +52,8 @@ extern "C" {
 #define WBC_FIFO_DISPATCH 4u     /* wbc_cycle: hand instances to the solver warps in index order.  Default: longest solve first,
                                     predicted from each instance's previous cycle on this ctx with the same n (the ctx keeps a
                                     per-instance duration); the order never changes a result, only when the batch's tail ends. */
+#define WBC_SAMPLED_TRAJ 16u     /* wbc_cycle: com_des_* and sw_des_* come from the last wbc_sample_trajectory(out = NULL) on this ctx;
+                                  * those six wbc_inputs pointers are ignored (may be NULL) and are not copied from the host */
 #define WBC_HOST_SLAB 8u         /* (host pointers) the input arrays are carved, in wbc_inputs field order, from ONE page-locked
                                   * allocation with ld == n: adjacent fields are moved with a single copy */
 
@@ -181,6 +183,31 @@ int wbc_last_timing(wbc_ctx* ctx, float* front_ms, float* solve_ms);
 int wbc_last_solve_cycles(wbc_ctx* ctx, int n, unsigned long long* cycles);
 /* Number of kernels launched by the last wbc_cycle / wbc_qp_solve. */
 int wbc_last_launches(wbc_ctx* ctx);
+
+/* ---- On-device trajectory sampling -------------------------------------------------------------
+ * The reference samples four towr::Spline objects at wall-clock time t on the host every cycle: base_linear_ and
+ * base_angular_ (main.cpp:1004-1010) and ee_motion_ of the two swing feet (main.cpp:1333-1368); towr::Spline::GetPoint
+ * is spline.cc:48-93, the cubic-Hermite coefficients polynomial.cc:98-104.  wbc_set_trajectory uploads the node tables
+ * of a plan once; wbc_sample_trajectory evaluates them on the GPU for every instance, so a cycle needs only t. */
+#define WBC_TRAJ_SPLINES 4   /* 0 base_linear, 1 base_angular, 2 first swing foot, 3 second swing foot (Jsw row order) */
+#define WBC_TRAJ_MAX_SEG 8
+typedef struct wbc_trajectory {
+    int nseg;                  /* cubic-Hermite polynomials per spline, 1..WBC_TRAJ_MAX_SEG                              */
+    const double* durations;   /* [4*nseg][ld]        row s*nseg + j: duration of polynomial j of spline s               */
+    const double* nodes;       /* [4*(nseg+1)*6][ld]  row (s*(nseg+1) + k)*6 + c: node k, c = 0..2 position, 3..5 velocity */
+    long ld;
+} wbc_trajectory;
+typedef struct wbc_traj_samples {   /* the six desired-trajectory arrays of wbc_inputs, each [6][ld] */
+    double *com_des_pos, *com_des_vel, *com_des_acc, *sw_des_pos, *sw_des_vel, *sw_des_acc;
+    long ld;
+} wbc_traj_samples;
+/* Upload (host pointers) or copy (WBC_DEVICE_PTRS) the plan of n instances into the ctx. */
+int wbc_set_trajectory(wbc_ctx* ctx, int n, const wbc_trajectory* tr, void* cuda_stream, unsigned flags);
+/* Sample the ctx's plan at time t[i] per instance (t == NULL: t_all for every instance).  One kernel launch.
+ * out == NULL: the samples stay in the ctx, for a following wbc_cycle(..., WBC_SAMPLED_TRAJ);
+ * out != NULL: written to the caller's arrays -- device arrays with WBC_DEVICE_PTRS (e.g. the ones handed to
+ * wbc_cycle as device inputs), else host arrays (a D2H copy; for inspection and tests).  t follows the same flag. */
+int wbc_sample_trajectory(wbc_ctx* ctx, int n, const double* t, double t_all, const wbc_traj_samples* out, void* cuda_stream, unsigned flags);
 
 /* Page-locked host memory for the SoA arrays handed to wbc_cycle with WBC_HOST_PTRS.  Arrays that are page-locked
  * (from here, cudaMallocHost or cudaHostRegister) are copied to and from the device directly; pageable arrays go
