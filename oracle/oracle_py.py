@@ -254,3 +254,35 @@ def plant_step(sc, push, x=None, params=None, gravity=(0.0, 0.0, -9.8)):
         lib.wbc_oracle_plant_step(C.byref(params), C.byref(arr[i]), _dp(pt[i]), _dp(xs[i]) if xs is not None else None, _dp(pos[i]),
                                   _dp(vel[i]), _dp(ff[i]))
     return np.ascontiguousarray(pos.T), np.ascontiguousarray(vel.T), (np.ascontiguousarray(ff.T) if xs is not None else None)
+
+
+def spline_point(durations, nodes, t):
+    """towr::Spline::GetPoint (oracle restatement): durations [nseg], nodes [nseg+1, 6] -> (id, p, v, a)."""
+    lib = oracle_lib()
+    pd = C.POINTER(C.c_double)
+    lib.wbc_oracle_spline_point.argtypes = [C.c_int, pd, pd, C.c_double, pd, pd, pd]
+    lib.wbc_oracle_spline_point.restype = C.c_int
+    d = np.ascontiguousarray(durations, dtype=np.float64)
+    nd = np.ascontiguousarray(nodes, dtype=np.float64)
+    p, v, a = np.zeros(3), np.zeros(3), np.zeros(3)
+    sid = lib.wbc_oracle_spline_point(d.shape[0], d.ctypes.data_as(pd), nd.ctypes.data_as(pd), float(t), p.ctypes.data_as(pd),
+                                      v.ctypes.data_as(pd), a.ctypes.data_as(pd))
+    return sid, p, v, a
+
+
+def sample_trajectory(traj, t):
+    """All instances of a plan (scenarios.make_trajectory layout) at times t [n] -> dict of the six [6, n] arrays."""
+    nseg, dur, nodes = traj["nseg"], traj["durations"], traj["nodes"]
+    n = dur.shape[1]
+    out = {k: np.zeros((6, n)) for k in ("com_des_pos", "com_des_vel", "com_des_acc", "sw_des_pos", "sw_des_vel", "sw_des_acc")}
+    for i in range(n):
+        for s in range(4):
+            d = dur[s * nseg:(s + 1) * nseg, i]
+            nd = nodes[s * (nseg + 1) * 6:(s + 1) * (nseg + 1) * 6, i].reshape(nseg + 1, 6)
+            sid, p, v, a = spline_point(d, nd, t[i])
+            assert sid >= 0, "time outside the plan"
+            pre, r0 = ("com_des_" if s < 2 else "sw_des_"), (s & 1) * 3
+            out[pre + "pos"][r0:r0 + 3, i] = p
+            out[pre + "vel"][r0:r0 + 3, i] = v
+            out[pre + "acc"][r0:r0 + 3, i] = a
+    return out

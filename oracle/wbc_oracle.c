@@ -710,3 +710,43 @@ double wbc_oracle_batch(const wbc_oracle_params* p, const wbc_oracle_in* in, int
     free(args);
     return (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
 }
+
+
+/* ------------------------------------------------------------------------------------------------
+ * towr spline sampling (the planner side of main.cpp:1004-1010, 1333-1368), literal:
+ *   Spline::GetSegmentID   spline.cc:48-66   first i with cumulative duration >= t - 1e-10
+ *   Spline::GetLocalTime   spline.cc:68-79   subtract the durations of the earlier polynomials one by one
+ *   CubicHermitePolynomial::UpdateCoeff  polynomial.cc:98-104
+ *   Polynomial::GetPoint / GetDerivativeWrtCoeff  polynomial.cc:50-76  (std::pow, accumulation from zero in the order A..D) */
+int wbc_oracle_spline_point(int nseg, const double* durations, const double* nodes, double t_global, double* p, double* v, double* a)
+{
+    const double eps = 1e-10;
+    if (t_global < 0.0) return -1;                 /* assert(t_global >= 0.0) */
+    double t = 0.0;
+    int id = -1;
+    for (int i = 0; i < nseg; i++) {
+        t += durations[i];
+        if (t >= t_global - eps) { id = i; break; }
+    }
+    if (id < 0) return -1;                         /* assert(false): this should never be reached */
+    double t_local = t_global;
+    for (int i = 0; i < id; i++) t_local -= durations[i];
+    const double T = durations[id];
+    const double* n0 = nodes + 6 * id;
+    const double* n1 = nodes + 6 * (id + 1);
+    for (int d = 0; d < 3; d++) {
+        double coeff[4];
+        coeff[0] = n0[d];
+        coeff[1] = n0[3 + d];
+        coeff[2] = -(3 * (n0[d] - n1[d]) + T * (2 * n0[3 + d] + n1[3 + d])) / pow(T, 2);
+        coeff[3] = (2 * (n0[d] - n1[d]) + T * (n0[3 + d] + n1[3 + d])) / pow(T, 3);
+        double op = 0.0, ov = 0.0, oa = 0.0;
+        for (int c = 0; c < 4; c++) {
+            op += pow(t_local, c) * coeff[c];
+            ov += (c >= 1 ? c * pow(t_local, c - 1) : 0.0) * coeff[c];
+            oa += (c >= 2 ? c * (c - 1) * pow(t_local, c - 2) : 0.0) * coeff[c];
+        }
+        p[d] = op; v[d] = ov; a[d] = oa;
+    }
+    return id;
+}

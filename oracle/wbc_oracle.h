@@ -106,6 +106,10 @@ int  wbc_oracle_cycle(const wbc_oracle_params* p, const wbc_oracle_in* in, wbc_q
  * and, in closed loop, the next sensor-frame foot forces (12). */
 void wbc_oracle_plant_step(const wbc_oracle_params* p, const wbc_oracle_in* in, const double* push, const double* x,
                            double* base_pos_out, double* base_vel_out, double* foot_force_out);
+/* towr::Spline::GetPoint(t) for one spline of nseg cubic-Hermite polynomials in 3 dimensions (spline.cc:48-93,
+ * polynomial.cc:50-104): durations[nseg]; nodes[(nseg+1)][6] = position(3), velocity(3) per node.
+ * Outputs p, v, a (3 each).  Returns the polynomial id, or -1 where the reference would assert (t < 0, t past the end). */
+int wbc_oracle_spline_point(int nseg, const double* durations, const double* nodes, double t, double* p, double* v, double* a);
 /* n instances on nthreads host threads (disjoint contiguous ranges); returns wall seconds. */
 double wbc_oracle_batch(const wbc_oracle_params* p, const wbc_oracle_in* in, int n, int nthreads,
                         wbc_qp_fn solve, wbc_oracle_out* out);

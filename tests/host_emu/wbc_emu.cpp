@@ -6,6 +6,7 @@
 #include "emu_work.h"
 #include "../../wbc_quadruped_dob_b200/csrc/wbc_assemble.cuh"
 #include "../../wbc_quadruped_dob_b200/csrc/wbc_front.cuh"
+#include "../../wbc_quadruped_dob_b200/csrc/wbc_traj.cuh"
 
 #include <cstdlib>
 #include <cstring>
@@ -73,6 +74,17 @@ int emu_assemble(const Params* P, const double* rec, double* Q, double* c, doubl
     assemble_qp<30>(ex, *P, rec, sh, Q, c, L);
     *nrows = sh.nrows; *neq = sh.neq;
     return 0;
+}
+
+// The device's spline sampling (wbc_traj.cuh) for n instances: out36 is [36][ld] in wbc_traj_kernel's block order.
+void emu_sample_trajectory(int n, int nseg, const double* dur, const double* nodes, long ld, const double* t, double* out36)
+{
+    for (int i = 0; i < n; i++) {
+        wbc::TrajOut o;
+        for (int b = 0; b < 6; b++) o.p[b] = out36 + (long)b * 6 * ld + i;
+        o.ld = ld;
+        wbc::sample_trajectory_instance(nseg, dur + i, nodes + i, ld, t[i], o);
+    }
 }
 
 int emu_sizeof_params() { return (int)sizeof(Params); }

@@ -101,6 +101,19 @@ class Emu:
         self.lib.emu_cycle(C.byref(P), C.byref(io), n)
         return out
 
+    def sample_trajectory(self, traj, t):
+        dur = np.ascontiguousarray(traj["durations"], dtype=np.float64)
+        nodes = np.ascontiguousarray(traj["nodes"], dtype=np.float64)
+        t = np.ascontiguousarray(t, dtype=np.float64)
+        n = dur.shape[1]
+        out = np.zeros((36, n))
+        self.lib.emu_sample_trajectory.argtypes = [C.c_int, C.c_int, _dp, _dp, C.c_long, _dp, _dp]
+        self.lib.emu_sample_trajectory.restype = None
+        self.lib.emu_sample_trajectory(n, int(traj["nseg"]), dur.ctypes.data_as(_dp), nodes.ctypes.data_as(_dp), n, t.ctypes.data_as(_dp),
+                                       out.ctypes.data_as(_dp))
+        names = ["com_des_pos", "com_des_vel", "com_des_acc", "sw_des_pos", "sw_des_vel", "sw_des_acc"]
+        return {k: out[6 * b:6 * b + 6] for b, k in enumerate(names)}
+
     def qp_solve(self, Q, c, L, neq, epsx=1e-2, rho=1e4, outerits=5, kkt_mode=1):
         Q = np.ascontiguousarray(Q, dtype=np.float64)
         c = np.ascontiguousarray(c, dtype=np.float64)

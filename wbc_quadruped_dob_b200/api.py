@@ -20,7 +20,7 @@ import numpy as np
 from . import build as _build
 
 MODE_STANCE, MODE_SWING_BR_FL, MODE_SWING_BL_FR = 0, 1, 2
-HOST_PTRS, DEVICE_PTRS, NO_SYNC, FIFO_DISPATCH, HOST_SLAB = 0, 1, 2, 4, 8
+HOST_PTRS, DEVICE_PTRS, NO_SYNC, FIFO_DISPATCH, HOST_SLAB, SAMPLED_TRAJ = 0, 1, 2, 4, 8, 16
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
@@ -55,6 +55,17 @@ class _Debug(C.Structure):
     _fields_ = [(n, C.c_void_p) for n, _ in DEBUG_FIELDS] + [("ld", C.c_long)]
 
 
+class _Trajectory(C.Structure):
+    _fields_ = [("nseg", C.c_int), ("durations", C.c_void_p), ("nodes", C.c_void_p), ("ld", C.c_long)]
+
+
+TRAJ_FIELDS = ["com_des_pos", "com_des_vel", "com_des_acc", "sw_des_pos", "sw_des_vel", "sw_des_acc"]
+
+
+class _TrajSamples(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in TRAJ_FIELDS] + [("ld", C.c_long)]
+
+
 class WbcError(RuntimeError):
     pass
 
@@ -64,6 +75,7 @@ _lib = None
 EXPORTS = ["wbc_default_params", "wbc_last_error", "wbc_version", "wbc_create", "wbc_destroy", "wbc_set_params",
            "wbc_set_observer_state", "wbc_get_observer_state", "wbc_cycle", "wbc_debug_update", "wbc_qp_solve",
            "wbc_plant_step", "wbc_last_timing", "wbc_last_solve_cycles", "wbc_last_launches", "wbc_host_alloc", "wbc_host_free",
+           "wbc_set_trajectory", "wbc_sample_trajectory",
            "wbc_measure_dfma_peak"]
 
 
@@ -98,6 +110,8 @@ def load():
     lib.wbc_last_launches.argtypes = [C.c_void_p]
     lib.wbc_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
     lib.wbc_host_free.argtypes = [C.c_void_p]
+    lib.wbc_set_trajectory.argtypes = [C.c_void_p, C.c_int, C.POINTER(_Trajectory), C.c_void_p, C.c_uint]
+    lib.wbc_sample_trajectory.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.POINTER(_TrajSamples), C.c_void_p, C.c_uint]
     lib.wbc_measure_dfma_peak.argtypes = [C.c_void_p, _dp]
     _lib = lib
     return lib
@@ -167,13 +181,13 @@ class WbcBatch:
         return yd, yw
 
     @staticmethod
-    def _inputs_struct(sc, n, keep):
+    def _inputs_struct(sc, n, keep, skip=()):
         ins = _Inputs()
         ld = None
         for name, k in IN_FIELDS:
-            a = sc.get(name)
+            a = None if name in skip else sc.get(name)
             if a is None:
-                if name != "terrain":
+                if name != "terrain" and name not in skip:
                     raise WbcError("missing input array '%s'" % name)
                 setattr(ins, name, None)
                 continue
@@ -218,6 +232,29 @@ class WbcBatch:
         out[...] = a
         return out
 
+    def set_trajectory(self, traj):
+        """Upload a plan (scenarios.make_trajectory layout: nseg, durations [4*nseg, n], nodes [4*(nseg+1)*6, n])."""
+        d = np.ascontiguousarray(traj["durations"], dtype=np.float64)
+        nd = np.ascontiguousarray(traj["nodes"], dtype=np.float64)
+        n = d.shape[1]
+        tr = _Trajectory(int(traj["nseg"]), d.ctypes.data, nd.ctypes.data, n)
+        _check(self.lib.wbc_set_trajectory(self.h, n, C.byref(tr), None, HOST_PTRS), "wbc_set_trajectory")
+
+    def sample_trajectory(self, n, t=None, t_all=0.0, fetch=False):
+        """Sample the uploaded plan on the GPU at per-instance times t [n] (or t_all for everyone).  The samples stay on
+        the device for cycle(..., sampled_traj=True); fetch=True also returns them as a dict of [6, n] host arrays."""
+        tp = None
+        if t is not None:
+            t = np.ascontiguousarray(t, dtype=np.float64)
+            tp = t.ctypes.data
+        _check(self.lib.wbc_sample_trajectory(self.h, n, tp, float(t_all), None, None, HOST_PTRS), "wbc_sample_trajectory")
+        if not fetch:
+            return None
+        out = {k: np.zeros((6, n)) for k in TRAJ_FIELDS}
+        o = _TrajSamples(*[out[k].ctypes.data for k in TRAJ_FIELDS], n)
+        _check(self.lib.wbc_sample_trajectory(self.h, n, tp, float(t_all), C.byref(o), None, HOST_PTRS), "wbc_sample_trajectory")
+        return out
+
     def pinned_inputs(self, sc):
         """Copy a scenario's input arrays into ONE page-locked slab laid out in wbc_inputs field order, so that
         wbc_cycle moves them with a single host-to-device copy.  Returns a dict of views (other keys passed through)."""
@@ -237,12 +274,12 @@ class WbcBatch:
         out["_slab"] = True          # cycle() passes WBC_HOST_SLAB
         return out
 
-    def cycle(self, sc, n=None, want=("x", "qp_obj", "status", "qp_info", "qp_flops"), out=None):
+    def cycle(self, sc, n=None, want=("x", "qp_obj", "status", "qp_info", "qp_flops"), out=None, sampled_traj=False):
         """One control cycle on HOST (numpy) SoA inputs; returns a dict of numpy arrays [k, n].  `out`: preallocated
         result arrays to fill (e.g. page-locked ones from pinned()); its keys decide what is returned."""
         keep = []
         n = int(sc["mode"].shape[0]) if n is None else int(n)
-        ins = self._inputs_struct(sc, n, keep)
+        ins = self._inputs_struct(sc, n, keep, skip=TRAJ_FIELDS if sampled_traj else ())
         if out is None:
             out = {"tau": np.zeros((12, n)), "w": np.zeros((6, n))}
             if "x" in want: out["x"] = np.zeros((30, n))
@@ -254,7 +291,7 @@ class WbcBatch:
         for k in ("tau", "w", "x", "qp_obj", "status", "qp_info", "qp_flops"):
             setattr(o, k, _ptr(out.get(k)))
         o.ld = max(n, 1)
-        _check(self.lib.wbc_cycle(self.h, n, C.byref(ins), C.byref(o), None, HOST_PTRS | (FIFO_DISPATCH if self.fifo_dispatch else 0) | (HOST_SLAB if sc.get("_slab") else 0)), "wbc_cycle")
+        _check(self.lib.wbc_cycle(self.h, n, C.byref(ins), C.byref(o), None, HOST_PTRS | (FIFO_DISPATCH if self.fifo_dispatch else 0) | (HOST_SLAB if sc.get("_slab") else 0) | (SAMPLED_TRAJ if sampled_traj else 0)), "wbc_cycle")
         return out
 
     def cycle_device(self, dev_in, dev_out, n, ld, stream=None, sync=True):

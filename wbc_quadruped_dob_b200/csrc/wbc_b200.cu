@@ -18,6 +18,7 @@
 #include "qp_warp.cuh"
 #include "wbc_assemble.cuh"
 #include "wbc_front.cuh"
+#include "wbc_traj.cuh"
 #include "wbc_types.h"
 
 using namespace wbc;
@@ -144,6 +145,19 @@ __global__ void __launch_bounds__(SOLVE_T) wbc_solve_kernel(Params P, int n, con
         }
         ex.sync();
     }
+}
+
+// Thread per instance: evaluate the plan's four splines at the instance's time (wbc_traj.cuh).
+__global__ void __launch_bounds__(128) wbc_traj_kernel(int n, int nseg, const double* __restrict__ dur, const double* __restrict__ nodes, long ld,
+                                                       const double* __restrict__ t, double t_all, wbc::TrajOut out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    wbc::TrajOut o;
+#pragma unroll
+    for (int b = 0; b < 6; b++) o.p[b] = out.p[b] + i;
+    o.ld = out.ld;
+    wbc::sample_trajectory_instance(nseg, dur + i, nodes + i, ld, t ? t[i] : t_all, o);
 }
 
 // OPT-operator path: dense, instance-major (Q [n][900], c [n][30], L [n][nrows*31], x [n][30]).
@@ -308,6 +322,13 @@ struct wbc_ctx {
     int* h_pin_i;
     size_t dense_cap;    // bytes of dense staging
     double* d_dense;     // dense QP staging (Q, c, L, x)
+    // on-device trajectory sampling (wbc_traj.cuh): plan tables and the last samples, ld = max_batch
+    int traj_nseg, traj_n;        // segments per spline of the uploaded plan (0 = none), instances it covers
+    double* traj_dur;             // [4 * TRAJ_MAX_SEG][max_batch]
+    double* traj_nodes;           // [4 * (TRAJ_MAX_SEG + 1) * 6][max_batch]
+    double* traj_s;               // [36][max_batch] samples of the last wbc_sample_trajectory(out = NULL)
+    double* traj_t;               // [max_batch] staging of per-instance times
+    int traj_sampled_n;           // instances the samples cover (0 = none)
     float front_ms, solve_ms;
     int launches;
     int last_n;          // instances of the last wbc_cycle (wbc_plant_step reads their records)
@@ -334,6 +355,7 @@ int wbc_destroy(wbc_ctx* c)
     if (!c) return WBC_OK;
     cudaSetDevice(c->device);
     cudaFree(c->recs); cudaFree(c->yd); cudaFree(c->yw); cudaFree(c->w_dev); cudaFree(c->scratch); cudaFree(c->queue); cudaFree(c->cost); cudaFree(c->order);
+    cudaFree(c->traj_dur); cudaFree(c->traj_nodes); cudaFree(c->traj_s); cudaFree(c->traj_t);
     cudaFree(c->d_in); cudaFree(c->d_out); cudaFree(c->d_mode); cudaFree(c->d_iout); cudaFree(c->d_dense);
     if (c->h_pin) cudaFreeHost(c->h_pin);
     if (c->h_pin_i) cudaFreeHost(c->h_pin_i);
@@ -449,14 +471,16 @@ static int front_threads(const wbc_ctx* c, int n)
     return 32;
 }
 
-static int check_inputs(const wbc_inputs* in, int n)
+static int check_inputs(const wbc_inputs* in, int n, bool sampled_traj = false)
 {
     if (!in) return fail(WBC_EINVAL, "null wbc_inputs");
     if (in->ld < n) return fail(WBC_EINVAL, "wbc_inputs.ld < n");
     const void* req[] = {in->base_pos, in->base_rot, in->base_rpy, in->base_vel, in->q, in->dq, in->com_des_pos, in->com_des_vel,
                          in->com_des_acc, in->sw_des_pos, in->sw_des_vel, in->sw_des_acc, in->foot_force, in->mode};
-    for (const void* p : req)
-        if (!p) return fail(WBC_EINVAL, "wbc_inputs: a required array is NULL (only `terrain` may be)");
+    for (int f = 0; f < 14; f++) {
+        if (sampled_traj && f >= 6 && f <= 11) continue;      // com_des_*, sw_des_*: taken from the ctx's samples
+        if (!req[f]) return fail(WBC_EINVAL, "wbc_inputs: a required array is NULL (only `terrain` may be)");
+    }
     return WBC_OK;
 }
 
@@ -472,7 +496,7 @@ static bool is_pinned_host(const void* p)
 // Stage host SoA inputs into the ctx's device buffers, one H2D copy per field so that the DMA of a field overlaps the
 // host-side packing of the next: straight from the caller's arrays when they are page-locked, else through the
 // pinned bounce buffer.
-static int stage_inputs(wbc_ctx* c, int n, const wbc_inputs* in, cudaStream_t s, DevInputs* dev, bool slab)
+static int stage_inputs(wbc_ctx* c, int n, const wbc_inputs* in, cudaStream_t s, DevInputs* dev, bool slab, bool sampled_traj = false)
 {
     const double* src[15] = {in->base_pos, in->base_rot, in->base_rpy, in->base_vel, in->q, in->dq, in->com_des_pos, in->com_des_vel,
                              in->com_des_acc, in->sw_des_pos, in->sw_des_vel, in->sw_des_acc, in->foot_force, in->terrain, in->obs_gain};
@@ -485,8 +509,17 @@ static int stage_inputs(wbc_ctx* c, int n, const wbc_inputs* in, cudaStream_t s,
     const double* run_src = nullptr;
     size_t run_off = 0, run_rows = 0;
     for (int f = 0; f < 15; f++) {
-        if (!src[f]) { *dst[f] = nullptr; continue; }
         const int K = kInFieldK[f];
+        if (sampled_traj && f >= 6 && f <= 11) {
+            // desired-trajectory rows: filled on the device from the ctx's samples (one strided D2D copy, below)
+            if (run_src) { CU(cudaMemcpyAsync(c->d_in + run_off, run_src, run_rows * row, cudaMemcpyHostToDevice, s)); run_src = nullptr; }
+            if (f == 6)
+                CU(cudaMemcpy2DAsync(c->d_in + off, row, c->traj_s, (size_t)c->max_batch * sizeof(double), row, wbc::TRAJ_OUT_ROWS, cudaMemcpyDeviceToDevice, s));
+            *dst[f] = c->d_in + off;
+            off += (size_t)K * n;
+            continue;
+        }
+        if (!src[f]) { *dst[f] = nullptr; continue; }
         const bool pinned = is_pinned_host(src[f]);
         if (run_src && !(slab && pinned && in->ld == n && src[f] == run_src + run_rows * n)) {
             CU(cudaMemcpyAsync(c->d_in + run_off, run_src, run_rows * row, cudaMemcpyHostToDevice, s));
@@ -524,10 +557,14 @@ int wbc_cycle(wbc_ctx* c, int n, const wbc_inputs* in, const wbc_outputs* out, v
     if (!c || !out) return fail(WBC_EINVAL, "wbc_cycle: null argument");
     if (n < 0 || n > c->max_batch) return fail(WBC_EINVAL, "wbc_cycle: n outside [0, max_batch]");
     if (n == 0) { c->launches = 0; return WBC_OK; }
-    int rc = check_inputs(in, n);
+    const bool sampled = (flags & WBC_SAMPLED_TRAJ) != 0;
+    int rc = check_inputs(in, n, sampled);
     if (rc) return rc;
     if (!out->tau || out->ld < n) return fail(WBC_EINVAL, "wbc_cycle: outputs.tau is required and outputs.ld >= n");
     const bool dev_ptrs = (flags & WBC_DEVICE_PTRS) != 0;
+    if (sampled && c->traj_sampled_n < n) return fail(WBC_EINVAL, "wbc_cycle: WBC_SAMPLED_TRAJ without a wbc_sample_trajectory(out = NULL) covering n instances");
+    if (sampled && dev_ptrs && in->ld != c->max_batch)
+        return fail(WBC_EINVAL, "wbc_cycle: WBC_SAMPLED_TRAJ with device pointers needs inputs.ld == max_batch (or sample into your own arrays)");
     CU(cudaSetDevice(c->device));
     cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : c->stream;
 
@@ -537,12 +574,17 @@ int wbc_cycle(wbc_ctx* c, int n, const wbc_inputs* in, const wbc_outputs* out, v
     long w_ld;
     if (dev_ptrs) {
         to_dev_inputs(in, &din);
+        if (sampled) {
+            const size_t blk = (size_t)6 * c->max_batch;
+            din.com_des_pos = c->traj_s; din.com_des_vel = c->traj_s + blk; din.com_des_acc = c->traj_s + 2 * blk;
+            din.sw_des_pos = c->traj_s + 3 * blk; din.sw_des_vel = c->traj_s + 4 * blk; din.sw_des_acc = c->traj_s + 5 * blk;
+        }
         so.tau = out->tau; so.x = out->x; so.qp_obj = out->qp_obj; so.status = out->status; so.qp_info = out->qp_info;
         so.qp_flops = out->qp_flops; so.ld = out->ld;
         w_ptr = out->w ? out->w : c->w_dev;
         w_ld = out->w ? out->ld : c->max_batch;
     } else {
-        rc = stage_inputs(c, n, in, s, &din, (flags & WBC_HOST_SLAB) != 0);
+        rc = stage_inputs(c, n, in, s, &din, (flags & WBC_HOST_SLAB) != 0, sampled);
         if (rc) return rc;
         so.tau = c->d_out; so.x = out->x ? c->d_out + 18L * n : nullptr; so.qp_obj = out->qp_obj ? c->d_out + 48L * n : nullptr;
         so.qp_flops = out->qp_flops ? c->d_out + 49L * n : nullptr;
@@ -599,6 +641,77 @@ int wbc_cycle(wbc_ctx* c, int n, const wbc_inputs* in, const wbc_outputs* out, v
         if (out->status) memcpy(out->status, c->h_pin_i, (size_t)n * 4);
         if (out->qp_info) for (int k = 0; k < 8; k++) memcpy(out->qp_info + (size_t)k * out->ld, c->h_pin_i + (size_t)(1 + k) * n, (size_t)n * 4);
     } else if (!(flags & WBC_NO_SYNC)) {
+        CU(cudaStreamSynchronize(s));
+    }
+    return WBC_OK;
+}
+
+// ---- on-device trajectory sampling (spline.cc:48-93, polynomial.cc:50-104, main.cpp:1004-1010, 1333-1368)
+int wbc_set_trajectory(wbc_ctx* c, int n, const wbc_trajectory* tr, void* cuda_stream, unsigned flags)
+{
+    if (!c || !tr || !tr->durations || !tr->nodes) return fail(WBC_EINVAL, "wbc_set_trajectory: null argument");
+    if (n <= 0 || n > c->max_batch || tr->ld < n) return fail(WBC_EINVAL, "wbc_set_trajectory: n outside (0, max_batch] or ld < n");
+    if (tr->nseg < 1 || tr->nseg > wbc::TRAJ_MAX_SEG) return fail(WBC_EINVAL, "wbc_set_trajectory: nseg outside [1, WBC_TRAJ_MAX_SEG]");
+    CU(cudaSetDevice(c->device));
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : c->stream;
+    const size_t mb = (size_t)c->max_batch;
+    if (!c->traj_dur) {
+        CU(cudaMalloc(&c->traj_dur, mb * wbc::traj_duration_rows(wbc::TRAJ_MAX_SEG) * sizeof(double)));
+        CU(cudaMalloc(&c->traj_nodes, mb * wbc::traj_node_rows(wbc::TRAJ_MAX_SEG) * sizeof(double)));
+        CU(cudaMalloc(&c->traj_s, mb * wbc::TRAJ_OUT_ROWS * sizeof(double)));
+        CU(cudaMalloc(&c->traj_t, mb * sizeof(double)));
+    }
+    const cudaMemcpyKind kind = (flags & WBC_DEVICE_PTRS) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    const size_t row = (size_t)n * sizeof(double);
+    CU(cudaMemcpy2DAsync(c->traj_dur, mb * sizeof(double), tr->durations, (size_t)tr->ld * sizeof(double), row, wbc::traj_duration_rows(tr->nseg), kind, s));
+    CU(cudaMemcpy2DAsync(c->traj_nodes, mb * sizeof(double), tr->nodes, (size_t)tr->ld * sizeof(double), row, wbc::traj_node_rows(tr->nseg), kind, s));
+    CU(cudaStreamSynchronize(s));            // the caller may free or overwrite its tables on return
+    c->traj_nseg = tr->nseg;
+    c->traj_n = n;
+    c->traj_sampled_n = 0;
+    return WBC_OK;
+}
+
+int wbc_sample_trajectory(wbc_ctx* c, int n, const double* t, double t_all, const wbc_traj_samples* out, void* cuda_stream, unsigned flags)
+{
+    if (!c) return fail(WBC_EINVAL, "wbc_sample_trajectory: null ctx");
+    if (c->traj_nseg == 0) return fail(WBC_EINVAL, "wbc_sample_trajectory: no plan uploaded (wbc_set_trajectory)");
+    if (n <= 0 || n > c->traj_n) return fail(WBC_EINVAL, "wbc_sample_trajectory: n exceeds the uploaded plan");
+    const bool dev_ptrs = (flags & WBC_DEVICE_PTRS) != 0;
+    if (out) {
+        if (out->ld < n) return fail(WBC_EINVAL, "wbc_traj_samples.ld < n");
+        const double* req[6] = {out->com_des_pos, out->com_des_vel, out->com_des_acc, out->sw_des_pos, out->sw_des_vel, out->sw_des_acc};
+        for (const double* p : req)
+            if (!p) return fail(WBC_EINVAL, "wbc_traj_samples: an array is NULL");
+    }
+    CU(cudaSetDevice(c->device));
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : c->stream;
+    const double* dt = t;
+    if (t && !dev_ptrs) {
+        CU(cudaMemcpyAsync(c->traj_t, t, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s));
+        dt = c->traj_t;
+    }
+    wbc::TrajOut o;
+    const bool to_caller = out && dev_ptrs;
+    if (to_caller) {
+        o.p[0] = out->com_des_pos; o.p[1] = out->com_des_vel; o.p[2] = out->com_des_acc;
+        o.p[3] = out->sw_des_pos; o.p[4] = out->sw_des_vel; o.p[5] = out->sw_des_acc;
+        o.ld = out->ld;
+    } else {
+        for (int b = 0; b < 6; b++) o.p[b] = c->traj_s + (size_t)b * 6 * c->max_batch;
+        o.ld = c->max_batch;
+    }
+    wbc_traj_kernel<<<(n + 127) / 128, 128, 0, s>>>(n, c->traj_nseg, c->traj_dur, c->traj_nodes, c->max_batch, dt, t_all, o);
+    CU(cudaGetLastError());
+    c->launches = 1;
+    if (!to_caller) c->traj_sampled_n = n;
+    if (out && !dev_ptrs) {
+        double* host[6] = {out->com_des_pos, out->com_des_vel, out->com_des_acc, out->sw_des_pos, out->sw_des_vel, out->sw_des_acc};
+        for (int b = 0; b < 6; b++)
+            CU(cudaMemcpy2DAsync(host[b], (size_t)out->ld * sizeof(double), c->traj_s + (size_t)b * 6 * c->max_batch, (size_t)c->max_batch * sizeof(double),
+                                 (size_t)n * sizeof(double), 6, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+    } else if (!(flags & WBC_NO_SYNC) && !dev_ptrs) {
         CU(cudaStreamSynchronize(s));
     }
     return WBC_OK;

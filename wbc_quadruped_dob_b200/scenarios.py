@@ -284,3 +284,33 @@ def trot_replay(cycles_per_phase=46, seed=0x0D06B07):
     sc["sw_des_vel"] = np.zeros((6, n)); sc["sw_des_acc"] = np.zeros((6, n))
     sc["obs_yd"] = np.zeros((6, n)); sc["obs_yw"] = np.zeros((6, n))
     return sc
+
+
+def make_trajectory(sc, nseg=3, seed=11):
+    """A synthetic plan for the n instances of scenario `sc` in the table layout of wbc_set_trajectory:
+    four splines (base_linear, base_angular, two swing feet) of `nseg` cubic-Hermite polynomials each, starting at the
+    scenario's desired CoM pose / swing-foot targets, plus sample times t [n] inside the plan.  Every 5th instance is
+    sampled exactly on a junction of spline 0 (towr returns the previous polynomial there, spline.cc:48-66), every 7th
+    at t = 0."""
+    n = int(sc["mode"].shape[0])
+    rng = np.random.Generator(np.random.Philox(key=[seed, 0x7261]))
+    dur = rng.uniform(0.1, 0.5, size=(4 * nseg, n))
+    nodes = np.zeros((4 * (nseg + 1) * 6, n))
+    starts = [(sc["com_des_pos"][0:3], sc["com_des_vel"][0:3], 0.02, 0.05), (sc["com_des_pos"][3:6], sc["com_des_vel"][3:6], 0.03, 0.1),
+              (sc["sw_des_pos"][0:3], sc["sw_des_vel"][0:3], 0.03, 0.3), (sc["sw_des_pos"][3:6], sc["sw_des_vel"][3:6], 0.03, 0.3)]
+    for s, (p0, v0, sp, sv) in enumerate(starts):
+        p, v = np.array(p0, dtype=np.float64), np.array(v0, dtype=np.float64)
+        for k in range(nseg + 1):
+            r = (s * (nseg + 1) + k) * 6
+            nodes[r:r + 3], nodes[r + 3:r + 6] = p, v
+            p = p + rng.normal(0.0, sp, size=(3, n))
+            v = rng.normal(0.0, sv, size=(3, n))
+    total = np.min([dur[s * nseg:(s + 1) * nseg].sum(axis=0) for s in range(4)], axis=0)
+    t = rng.uniform(0.0, 1.0, size=n) * total
+    idx = np.arange(n)
+    j = idx % nseg
+    junction = np.cumsum(dur[0:nseg], axis=0)[j, idx]
+    on_j = (idx % 5 == 0) & (junction <= total)
+    t[on_j] = junction[on_j]
+    t[idx % 7 == 0] = 0.0
+    return {"nseg": nseg, "durations": np.ascontiguousarray(dur), "nodes": np.ascontiguousarray(nodes), "t": t}
