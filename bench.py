@@ -297,8 +297,16 @@ def main():
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         hbm_ach = n * (IN_BYTES + OUT_BYTES) / (float(np.mean(step_ms)) * 1e-3) / 1e9
+        traffic, traffic_src = None, None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(args.workload)
+            if tr and per_gpu == n_cfg:
+                traffic, traffic_src = tr["bytes_per_launch"], tr["source"]
+        except Exception:
+            pass
         roofline = {"bound": "fp64", "kernel": "wbc_solve_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                    "frac": achieved / peak, "traffic": None,
+                    "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write)", "traffic_source": traffic_src,
+                    "algorithmic_bytes_per_launch": n * (8 * 528 + OUT_BYTES),
                     "peak_source": "own DFMA microbenchmark in this process (MEASURED_PEAKS.json has no FP64 figure)",
                     "flops_per_solve": flops_launch / n, "kernel_ms": solve_avg_ms, "front_kernel_ms": float(np.mean(front_ms)),
                     "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,

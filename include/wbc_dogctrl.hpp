@@ -135,8 +135,20 @@ public:
     void enable_terrain() { terrain.assign((size_t)40 * n_, 0.0); }
     void set_observer_state(const double* yd, const double* yw) { check(wbc_set_observer_state(ctx_.get(), n_, yd, yw, n_), "wbc_set_observer_state"); }
     void get_observer_state(double* yd, double* yw) { check(wbc_get_observer_state(ctx_.get(), n_, yd, yw, n_), "wbc_get_observer_state"); }
+    // Planner hand-over (once per plan): the node tables of the four towr splines of every instance, see wbc_trajectory.
+    // durations [4*nseg][n], nodes [4*(nseg+1)*6][n].  Replaces keeping `SplineHolder solution` on the host (main.cpp:900-960).
+    void set_trajectory(int nseg, const double* durations, const double* nodes)
+    {
+        wbc_trajectory tr;
+        tr.nseg = nseg; tr.durations = durations; tr.nodes = nodes; tr.ld = n_;
+        check(wbc_set_trajectory(ctx_.get(), n_, &tr, nullptr, WBC_HOST_PTRS), "wbc_set_trajectory");
+    }
+    // solution.base_linear_->GetPoint(t) ... ee_motion_.at(k)->GetPoint(t) of every instance, evaluated on the GPU
+    // (main.cpp:1004-1010, 1333-1368); the samples stay on the device for cycle(true).
+    void sample_trajectory(double t) { check(wbc_sample_trajectory(ctx_.get(), n_, nullptr, t, nullptr, nullptr, WBC_HOST_PTRS), "wbc_sample_trajectory"); }
     // One control cycle for all n instances: host buffers in, host buffers out (H2D + 2 kernels + D2H).
-    void cycle()
+    // sampled_trajectory: take com_des_* / sw_des_* from the last sample_trajectory() instead of the host vectors.
+    void cycle(bool sampled_trajectory = false)
     {
         wbc_inputs in;
         in.base_pos = base_pos.data(); in.base_rot = base_rot.data(); in.base_rpy = base_rpy.data(); in.base_vel = base_vel.data();
@@ -147,7 +159,7 @@ public:
         wbc_outputs out;
         out.tau = tau.data(); out.w = w.data(); out.x = x.data(); out.qp_obj = qp_obj.data(); out.status = status.data();
         out.qp_info = nullptr; out.qp_flops = nullptr; out.ld = n_;
-        check(wbc_cycle(ctx_.get(), n_, &in, &out, nullptr, WBC_HOST_PTRS), "wbc_cycle");
+        check(wbc_cycle(ctx_.get(), n_, &in, &out, nullptr, WBC_HOST_PTRS | (sampled_trajectory ? WBC_SAMPLED_TRAJ : 0u)), "wbc_cycle");
     }
 
 private:
