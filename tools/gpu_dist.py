@@ -21,3 +21,9 @@ f0, s0 = b.last_timing()
 print("  kernel ms front %.3f solve %.3f ; sum of latencies / 1184 warps = %.3f ms" % (f0, s0, ms.sum() / 1184))
 top = np.argsort(-cyc)[:8]
 for i in top: print("  heavy inst %d ms %.3f flops %.3g nchol %d outer %d qqp %d nicwork %d flags %d" % (i, ms[i], fl[i], qi[0][i], qi[1][i], qi[2][i], qi[3][i], qi[5][i]))
+fb = (qi[5] & 8) != 0
+if fb.any():
+    print("  literal-KKT fallback instances: %d (%.2f%%), latency ms mean %.3f max %.3f (others mean %.3f)" % (fb.sum(), 100.0 * fb.mean(), ms[fb].mean(), ms[fb].max(), ms[~fb].mean()))
+sp = (qi[5] & 32) != 0
+if sp.any():
+    print("  spill-mode instances: %d, latency ms mean %.3f max %.3f" % (sp.sum(), ms[sp].mean(), ms[sp].max()))

@@ -53,7 +53,7 @@ __device__ __noinline__ double2 symv(const double* __restrict__ x, int nic2, dou
     const double* Crow = wbc_smem + sl::OFF_CI + l * LDH;   // slack row l
     const double* Ccol = wbc_smem + sl::OFF_CI + l;         // column l of the slack rows
     double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
-#pragma unroll
+#pragma unroll 5
     for (int j = 0; j < NMAIN; j += 2) {
         const double2 xv = ld2(x + j);
         a0 += H[j * LDH] * xv.x;
