@@ -125,6 +125,9 @@ def main():
     ap.add_argument("--workload", default="standing_4096", choices=sorted(S.CONFIGS) + [SWEEP])
     ap.add_argument("--per-gpu", type=int, default=None, help="instances per GPU (default: the workload's own size, 1M config: /8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--traj-on-device", action="store_true",
+                    help="e2e loop only: the plan's spline tables live in HBM and are sampled on the GPU each step (SURVEY 8f-1); "
+                         "the 36 desired-trajectory doubles per instance are not sent from the host")
     ap.add_argument("--fifo", action="store_true", help="index-order work queue (WBC_FIFO_DISPATCH) instead of longest-first")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -255,7 +258,18 @@ def main():
     if sweep:
         out_pin["x"] = batch.pinned((30, n))
 
+    traj = None
+    if args.traj_on_device and not sweep:
+        # a plan whose splines start at the scenario's desired pose; sampled at t = 0 it reproduces the workload's inputs
+        traj = S.make_trajectory(sc, nseg=3, seed=11)
+        batch.set_trajectory(traj)
+        sc_host = batch.pinned_inputs({k: v for k, v in sc.items() if k not in api.TRAJ_FIELDS})
+        config["trajectory"] = "sampled on the device every step from per-instance spline tables (3 polynomials per spline) at t = 0"
+
     def e2e_step():
+        if traj is not None:
+            batch.sample_trajectory(n, t_all=0.0)
+            return batch.cycle(sc_host, want=want, out=out_pin, sampled_traj=True)
         out = batch.cycle(sc_host, want=want, out=out_pin)
         if sweep:   # host-side rollout: the plant's H2D/D2H copies are part of the step too
             batch.plant_step(sc_host["base_pos"], sc_host["base_vel"], sc_host["push"], foot_force=sc_host["foot_force"], x=out["x"])
@@ -314,9 +328,9 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": tot_ms / args.steps, "p50_ms": float(np.median(step_ms)), "higher_is_better": True, "scaling": scaling,
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks,
-                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": n * (IN_BYTES + (8 + 57 * 8 if sweep else 0)),
+                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": n * (IN_BYTES - (36 * 8 if args.traj_on_device and not sweep else 0) + (8 + 57 * 8 if sweep else 0)),
                         "d2h_bytes_per_step": n * (OUT_BYTES + (30 * 8 + 21 * 8 if sweep else 0))},
-                "gpu_launches": launches, "roofline": roofline,
+                "gpu_launches": launches, "e2e_gpu_launches": (3 if (sweep or (args.traj_on_device and not sweep)) else 2) * e2e_steps, "roofline": roofline,
                 "stats": {"solver_failures": stats["solver_failures"], "mean_ncholesky": stats["sum_ncholesky"] / total_inst,
                           "mean_outer_its": stats["sum_outer_its"] / total_inst, "max_kkt_dim": stats["max_kkt_dim"],
                           "wall_s_timed_region": t_wall}}
