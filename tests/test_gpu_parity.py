@@ -232,3 +232,33 @@ def test_last_solve_cycles_reports_every_instance(gpu_batch):
     _run(gpu_batch, sc)
     cyc = gpu_batch.last_solve_cycles(n)
     assert cyc.shape == (n,) and (cyc > 0).all() and (cyc < 2e9).all()
+
+
+def test_full_size_properties_config4_shard_131072():
+    """BASELINE config 4's per-GPU shard (1 M instances over 8 GPUs = 131 072 each, mixed gaits, rough terrain) through
+    size-independent properties: permutation equivariance (reversing the instance order reverses the outputs bit for
+    bit although the work queue, the longest-first order and the warp that solves each instance all change), and the
+    friction pyramids of the stance instances in their own per-foot terrain frames."""
+    n = 131072
+    sc = S.make_config("mixed_terrain_1m", n=n)
+    b = api.WbcBatch(max_batch=n, device=0)
+    try:
+        got = _run(b, sc)
+        assert (got["status"] == 0).all()
+        assert np.isfinite(got["tau"]).all() and np.isfinite(got["w"]).all()
+        rev = {k: (np.ascontiguousarray(v[..., ::-1]) if isinstance(v, np.ndarray) else v) for k, v in sc.items()}
+        got_r = _run(b, rev)
+        for k in ("tau", "w", "x"):
+            assert np.array_equal(got_r[k][:, ::-1], got[k]), k
+        st = sc["mode"] == 0
+        x, T = got["x"][:, st], sc["terrain"][:, st]
+        assert np.abs(got["tau"][:, st]).max() <= 60.0 * (1 + 1e-3)
+        for f in range(4):
+            fv = x[18 + 3 * f:21 + 3 * f]
+            nn, t1, t2, mu = T[10 * f:10 * f + 3], T[10 * f + 3:10 * f + 6], T[10 * f + 6:10 * f + 9], T[10 * f + 9]
+            fn = (nn * fv).sum(axis=0)
+            assert fn.min() > -1e-3
+            assert (np.abs((t1 * fv).sum(axis=0)) <= mu * fn + 1e-2).all()
+            assert (np.abs((t2 * fv).sum(axis=0)) <= mu * fn + 1e-2).all()
+    finally:
+        b.close()
