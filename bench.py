@@ -39,6 +39,7 @@ IN_BYTES = 8 * 93 + 4     # algorithmic input bytes per instance (flat ground)
 OUT_BYTES = 8 * 18        # tau + w
 
 
+REPLAY = "trot_replay_single"  # BASELINE config 1: ONE robot replaying a 184-cycle synthetic trot, one control cycle per step (latency case)
 SWEEP = "push_sweep"          # BASELINE config 5: closed-loop disturbance-rejection sweep, fixed 262144-instance grid
 SWEEP_TOTAL = S.SWEEP_DIRECTIONS * len(S.SWEEP_MAGNITUDES) * len(S.SWEEP_GAINS) * S.SWEEP_STATES
 
@@ -116,13 +117,85 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def single_robot_replay(args):
+    """BASELINE configs[0]: one DogBot, one control cycle per step (the 400 Hz loop of main.cpp:836-1955), observer state
+    chained on the device.  Reports cycles/s (= solves/s), p50/p95 latency of a cycle, device-resident and end to end,
+    beside the CPU oracle + reference ALGLIB running the same replay on one host thread."""
+    import torch
+    from wbc_quadruped_dob_b200 import api
+    sc = S.trot_replay()
+    ncyc = sc["mode"].shape[0]
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    batch = api.WbcBatch(max_batch=1, device=0)
+    dev_in = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in sc.items() if isinstance(v, np.ndarray) and k not in ("obs_yd", "obs_yw")}
+    dev_out = {"tau": torch.zeros(12, 1, dtype=torch.float64, device=dev), "w": torch.zeros(6, 1, dtype=torch.float64, device=dev)}
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    sp = stream.cuda_stream
+
+    def dev_cycle(i):
+        one = {k: (v[i:] if v.dim() == 1 else v[:, i:]) for k, v in dev_in.items()}     # pointer offset, ld = ncyc
+        batch.cycle_device(one, dev_out, 1, ncyc, stream=sp, sync=False)
+
+    host = [{k: (np.ascontiguousarray(v[..., i:i + 1]) if isinstance(v, np.ndarray) else v) for k, v in sc.items()} for i in range(ncyc)]
+    steps, warm = max(args.steps, ncyc), max(args.warmup, 3)
+    batch.set_observer_state(np.zeros((6, 1)), np.zeros((6, 1)))
+    for i in range(warm):
+        dev_cycle(i % ncyc)
+    torch.cuda.synchronize()
+    batch.set_observer_state(np.zeros((6, 1)), np.zeros((6, 1)))
+    sampler = ClockSampler(0)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for it in range(steps):
+        ev[it][0].record(stream)
+        dev_cycle(it % ncyc)
+        ev[it][1].record(stream)
+        ev[it][1].synchronize()
+    step_ms = np.array([a.elapsed_time(b) for a, b in ev])
+    batch.set_observer_state(np.zeros((6, 1)), np.zeros((6, 1)))
+    e2e_ms = []
+    for it in range(warm + steps):
+        t0 = time.perf_counter()
+        out = batch.cycle(host[it % ncyc], want=())
+        if it >= warm:
+            e2e_ms.append(1e3 * (time.perf_counter() - t0))
+    clocks = sampler.stop()
+    e2e_ms = np.array(e2e_ms)
+    line = {"metric": METRIC, "value": 1e3 / float(step_ms.mean()), "unit": UNIT, "n_gpus": 1, "steps": steps, "warmup": warm,
+            "ms_per_step": float(step_ms.mean()), "p50_ms": float(np.median(step_ms)), "p95_ms": float(np.percentile(step_ms, 95)),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s: ONE DogBot, 184-cycle synthetic trot replay (46 stance + 46 swing{BR,FL} + 46 stance + 46 swing{BL,FR}), one control cycle per step, observer chained" % REPLAY,
+                       "instances_per_gpu": 1, "global_batch": 1, "parallelism": "single robot", "l2": "not flushed (a 400 Hz loop keeps its working set warm)"},
+            "clocks": clocks,
+            "e2e": {"value": 1e3 / float(e2e_ms.mean()), "unit": UNIT, "p50_ms": float(np.median(e2e_ms)), "p95_ms": float(np.percentile(e2e_ms, 95)),
+                    "h2d_bytes_per_step": IN_BYTES, "d2h_bytes_per_step": OUT_BYTES},
+            "gpu_launches": 2 * steps}
+    if not args.no_cpu_baseline:
+        from oracle import oracle_py as op
+        op.build(ref=True)
+        t0 = time.perf_counter()
+        yd, yw = np.zeros((6, 1)), np.zeros((6, 1))
+        for i in range(ncyc):
+            one = dict(host[i]); one["obs_yd"], one["obs_yw"] = yd, yw
+            ref, _ = op.run_cycle_batch(one, nthreads=1)
+            yd, yw = ref["yd"].T.copy(), ref["yw"].T.copy()
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": ncyc / dt, "unit": UNIT, "cores": 1, "kind": "reference" if op.have_ref() else "port",
+                                "sample": "the same 184-cycle replay, one host thread (the reference's control loop is single-threaded), %.3f ms per cycle" % (1e3 * dt / ncyc)}
+    print(json.dumps(line))
+    batch.close()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="standing_4096", choices=sorted(S.CONFIGS) + [SWEEP])
+    ap.add_argument("--workload", default="standing_4096", choices=sorted(S.CONFIGS) + [SWEEP, REPLAY])
     ap.add_argument("--per-gpu", type=int, default=None, help="instances per GPU (default: the workload's own size, 1M config: /8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--traj-on-device", action="store_true",
@@ -134,6 +207,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.workload == REPLAY:
+        if args.impl == "reference":
+            args.no_cpu_baseline = False
+        return single_robot_replay(args) if rank == 0 else 0
     cfg = workload_cfg(args.workload)
     n_cfg = cfg.pop("n")
     sweep = args.workload == SWEEP
@@ -261,7 +338,7 @@ def main():
     traj = None
     if args.traj_on_device and not sweep:
         # a plan whose splines start at the scenario's desired pose; sampled at t = 0 it reproduces the workload's inputs
-        traj = S.make_trajectory(sc, nseg=3, seed=11)
+        traj = S.make_trajectory(sc, nseg=3, seed=11, match_acc=True)
         batch.set_trajectory(traj)
         sc_host = batch.pinned_inputs({k: v for k, v in sc.items() if k not in api.TRAJ_FIELDS})
         config["trajectory"] = "sampled on the device every step from per-instance spline tables (3 polynomials per spline) at t = 0"

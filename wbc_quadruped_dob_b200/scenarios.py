@@ -286,16 +286,19 @@ def trot_replay(cycles_per_phase=46, seed=0x0D06B07):
     return sc
 
 
-def make_trajectory(sc, nseg=3, seed=11):
+def make_trajectory(sc, nseg=3, seed=11, match_acc=False):
     """A synthetic plan for the n instances of scenario `sc` in the table layout of wbc_set_trajectory:
     four splines (base_linear, base_angular, two swing feet) of `nseg` cubic-Hermite polynomials each, starting at the
     scenario's desired CoM pose / swing-foot targets, plus sample times t [n] inside the plan.  Every 5th instance is
     sampled exactly on a junction of spline 0 (towr returns the previous polynomial there, spline.cc:48-66), every 7th
-    at t = 0."""
+    at t = 0.  match_acc: choose the second node of every spline so that the acceleration at t = 0 equals the scenario's
+    desired acceleration too (p1 = p0 + (a0 T^2 / 2 + 2 T v0) / 3, v1 = 0): sampled at t = 0 the plan then reproduces
+    the scenario's 36 desired-trajectory inputs (positions and velocities bit for bit, accelerations to rounding)."""
     n = int(sc["mode"].shape[0])
     rng = np.random.Generator(np.random.Philox(key=[seed, 0x7261]))
     dur = rng.uniform(0.1, 0.5, size=(4 * nseg, n))
     nodes = np.zeros((4 * (nseg + 1) * 6, n))
+    accs = [sc["com_des_acc"][0:3], sc["com_des_acc"][3:6], sc["sw_des_acc"][0:3], sc["sw_des_acc"][3:6]]
     starts = [(sc["com_des_pos"][0:3], sc["com_des_vel"][0:3], 0.02, 0.05), (sc["com_des_pos"][3:6], sc["com_des_vel"][3:6], 0.03, 0.1),
               (sc["sw_des_pos"][0:3], sc["sw_des_vel"][0:3], 0.03, 0.3), (sc["sw_des_pos"][3:6], sc["sw_des_vel"][3:6], 0.03, 0.3)]
     for s, (p0, v0, sp, sv) in enumerate(starts):
@@ -303,6 +306,11 @@ def make_trajectory(sc, nseg=3, seed=11):
         for k in range(nseg + 1):
             r = (s * (nseg + 1) + k) * 6
             nodes[r:r + 3], nodes[r + 3:r + 6] = p, v
+            if match_acc and k == 0:
+                T = dur[s * nseg]
+                p = p + (accs[s] * T * T / 2.0 + 2.0 * T * v) / 3.0
+                v = np.zeros((3, n))
+                continue
             p = p + rng.normal(0.0, sp, size=(3, n))
             v = rng.normal(0.0, sv, size=(3, n))
     total = np.min([dur[s * nseg:(s + 1) * nseg].sum(axis=0) for s in range(4)], axis=0)
