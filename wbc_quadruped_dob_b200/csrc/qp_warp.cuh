@@ -102,7 +102,21 @@ constexpr long OFF_Z = OFF_CI + MAXNIC * LDH + 8;                // spill packed
 constexpr long OFF_V = OFF_Z + 5216;                             // spill [16][104]
 constexpr long OFF_QRV = OFF_V + NVEC * VLG;
 constexpr long OFF_SV0 = OFF_QRV + 2 * NQMAX + 4;
-constexpr long OFF_KKT = ((OFF_SV0 + NQMAX + 15) / 16) * 16;
+// Cache of the reduced multiplier update (update_lagrange_multipliers_reduced): everything that depends only on the
+// active set -- kept between the outer iterations of one solve, which usually end on the same active set.
+constexpr long OFF_MC = ((OFF_SV0 + NQMAX + 15) / 16) * 16;
+constexpr int MC_C0 = 0;            // [40]  d_m + W_m . t
+constexpr int MC_S0D = 40;          // [40]  diagonal of S = W W'
+constexpr int MC_S0 = 80;           // [648] strict lower triangle of S, packed
+constexpr int MC_SFD = 728;         // [40]  diagonal of the factor of S
+constexpr int MC_SFRINV = 768;      // [40]  its reciprocal
+constexpr int MC_SF = 808;          // [648] factor of S, packed
+constexpr int MC_GD = 1456;         // [40]  factor of G = Lt'Lt (rank-deficient active sets only)
+constexpr int MC_GRINV = 1496;      // [40]
+constexpr int MC_G = 1536;          // [648]
+constexpr int MC_INT = 2184;        // ints: act[40] | dep[40] | ka, version, ndep
+constexpr int MC_TOTAL = 2240;
+constexpr long OFF_KKT = OFF_MC + MC_TOTAL;
 constexpr long TOTAL = ((OFF_KKT + 2L * NQMAX * (NQMAX + 1) + 15) / 16) * 16;
 }  // namespace gl
 
@@ -173,7 +187,8 @@ struct Stats {
     int nicwork;        // final working-set size
     int kkt_dim_max;    // largest (N+K) of the multiplier update
     int flags;          // bit0: A not PD (42500); bit2: QQP -4; bit3: literal multiplier update used;
-                        // bit4: rank-deficient active set (least-norm branch); bit5: spilled to global memory
+                        // bit4: rank-deficient active set (least-norm branch); bit5: spilled to global memory;
+                        // bit6: a multiplier update reused the cached factorisation of an unchanged active set
     double flops;       // instrumented algorithmic flop count (DESIGN.md "work per solve")
 };
 
@@ -1241,6 +1256,7 @@ WBC_HDNI bool update_lagrange_multipliers_reduced(const Ex ex, const Work w, int
     double* G = big;                               // packed lower, 648: overlays Wm, which is dead by then
     double* LAs = Sm + 648;                        // packed factor of A, 450  -> 2246 <= 2640
     static_assert((KACAP + 1) * LDH + 1 + 648 + 450 <= sl::BIG, "reduced multiplier update workspace");
+    static_assert(KACAP <= 40 && ((KACAP * (KACAP - 1)) >> 1) + (KACAP >> 1) <= 648, "multiplier cache rows");
     double* vv = W_VEC(w);
     double* sd = vv;
     double* srinv = vv + VLS;
@@ -1250,49 +1266,85 @@ WBC_HDNI bool update_lagrange_multipliers_reduced(const Ex ex, const Work w, int
     double* gd = vv + 5 * VLS;
     double* grinv = vv + 6 * VLS;
     double* nu0 = vv + 7 * VLS;
-    ex.copy_in(LAs, W_LA(w), 450);
-    ex.sync();
-    // ---- forward substitutions U' y = c_m, one lane per right-hand side
-#pragma unroll 1
-    for (int m = ex.lane(); m <= ka; m += Ex::NL) {
-        double* y = &Wm[m * LDH];
-        const double* src = (m < ka) ? &C[act[m] * LDH] : W_B(w);
-#pragma unroll 1
-        for (int i = 0; i < NMAIN; i++) {
-            const double* li = LAs + zoff(i);
-            double s0 = src[i], s1 = 0.0;
-            int k = 0;
-#pragma unroll 1
-            for (; k + 1 < i; k += 2) { s0 -= li[k] * y[k]; s1 -= li[k + 1] * y[k + 1]; }
-            if (k < i) s0 -= li[k] * y[k];
-            y[i] = (s0 + s1) * larinv[i];
-        }
-        y[NMAIN] = (m < ka) ? src[NMAIN] : 0.0;
-        if (m < ka) nu0[m] = nulcest[act[m]];
-    }
-    ex.sync();
-    // ---- Schur complement S = W W' (packed lower + diagonal vector)
+    // ---- the cache: W, S = W W', its factor and (rank-deficient sets) the factor of G depend only on which rows of C
+    // are active, not on the multipliers or the point.  The outer iterations of a solve usually end on the same active
+    // set (the working set settles in the first one), so the second and third update reuse them bit for bit.
+    // Key: the active row list and the working-set version (update_working_set counts every row move).
+    double* mc = w.g + gl::OFF_MC;
+    int* mci = reinterpret_cast<int*>(mc + gl::MC_INT);
+    const int version = W_ISCR(w)[6];
     const int npairs = ka * (ka + 1) / 2;
+    const int nz = zoff(ka);
+    bool hit = (mci[80] == ka) && (mci[81] == version);
+    if (hit) {
+        double diff = 0.0;
 #pragma unroll 1
-    for (int e = ex.lane(); e < npairs; e += Ex::NL) {
-        int c, r;
-        tri_index_lower(e, c, r);
-        const double* wr = &Wm[r * LDH];
-        const double* wc = &Wm[c * LDH];
-        double s0 = 0.0, s1 = 0.0;
+        for (int m = ex.lane(); m < ka; m += Ex::NL)
+            if (mci[m] != act[m]) diff = 1.0;
+        hit = red_sum1(ex, diff) == 0.0;
+    }
 #pragma unroll 1
-        for (int k = 0; k < NMAIN; k += 2) { s0 += wr[k] * wc[k]; s1 += wr[k + 1] * wc[k + 1]; }
-        if (r == c) sd[r] = s0 + s1; else Sm[zoff(c) + r] = s0 + s1;
+    for (int m = ex.lane(); m < ka; m += Ex::NL) nu0[m] = nulcest[act[m]];
+    int ndep_i = 0;
+    if (!hit) {
+        if (ex.lane() == 0) mci[80] = -1;          // invalid until this pass completes
+        ex.copy_in(LAs, W_LA(w), 450);
+        ex.sync();
+        // ---- forward substitutions U' y = c_m, one lane per right-hand side
+#pragma unroll 1
+        for (int m = ex.lane(); m <= ka; m += Ex::NL) {
+            double* y = &Wm[m * LDH];
+            const double* src = (m < ka) ? &C[act[m] * LDH] : W_B(w);
+#pragma unroll 1
+            for (int i = 0; i < NMAIN; i++) {
+                const double* li = LAs + zoff(i);
+                double s0 = src[i], s1 = 0.0;
+                int k = 0;
+#pragma unroll 1
+                for (; k + 1 < i; k += 2) { s0 -= li[k] * y[k]; s1 -= li[k + 1] * y[k + 1]; }
+                if (k < i) s0 -= li[k] * y[k];
+                y[i] = (s0 + s1) * larinv[i];
+            }
+            y[NMAIN] = (m < ka) ? src[NMAIN] : 0.0;
+        }
+        ex.sync();
+        // ---- Schur complement S = W W' (packed lower + diagonal vector)
+#pragma unroll 1
+        for (int e = ex.lane(); e < npairs; e += Ex::NL) {
+            int c, r;
+            tri_index_lower(e, c, r);
+            const double* wr = &Wm[r * LDH];
+            const double* wc = &Wm[c * LDH];
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll 1
+            for (int k = 0; k < NMAIN; k += 2) { s0 += wr[k] * wc[k]; s1 += wr[k + 1] * wc[k + 1]; }
+            if (r == c) sd[r] = s0 + s1; else Sm[zoff(c) + r] = s0 + s1;
+        }
+        ex.sync();
+        // c0 = d + W t, and the unfactored S, for the later updates on this active set
+#pragma unroll 1
+        for (int m = ex.lane(); m < ka; m += Ex::NL) {
+            const double* wm = &Wm[m * LDH];
+            const double* wt = &Wm[ka * LDH];
+            double sacc = wm[NMAIN];
+#pragma unroll 1
+            for (int k = 0; k < NMAIN; k++) sacc += wm[k] * wt[k];
+            mc[gl::MC_C0 + m] = sacc;
+            mc[gl::MC_S0D + m] = sd[m];
+        }
+#pragma unroll 1
+        for (int e = ex.lane(); e < nz; e += Ex::NL) mc[gl::MC_S0 + e] = Sm[e];
+        flops += (double)(ka + 1) * NMAIN * NMAIN + (double)ka * ka * NMAIN + 2.0 * ka * NMAIN;
+    } else {
+        ex.copy_in(Sm, mc + gl::MC_S0, nz);
+#pragma unroll 1
+        for (int m = ex.lane(); m < ka; m += Ex::NL) sd[m] = mc[gl::MC_S0D + m];
     }
     ex.sync();
     // rho = d + W t - S nu0
 #pragma unroll 1
     for (int m = ex.lane(); m < ka; m += Ex::NL) {
-        const double* wm = &Wm[m * LDH];
-        const double* wt = &Wm[ka * LDH];
-        double sacc = wm[NMAIN];
-#pragma unroll 1
-        for (int k = 0; k < NMAIN; k++) sacc += wm[k] * wt[k];
+        const double sacc = mc[gl::MC_C0 + m];
         double sn = sd[m] * nu0[m];
 #pragma unroll 1
         for (int k = 0; k < ka; k++)
@@ -1301,42 +1353,81 @@ WBC_HDNI bool update_lagrange_multipliers_reduced(const Ex ex, const Work w, int
         dl[m] = sacc - sn;
     }
     ex.sync();
-    flops += (double)(ka + 1) * NMAIN * NMAIN + (double)ka * ka * NMAIN + 2.0 * ka * NMAIN + 2.0 * ka * ka;
-    bool ambiguous = false;
-    {
-        SrcInPlace src;
-        src.Z = Sm; src.diag = sd;
-        chol_cols<true>(ex, Sm, ka, sd, srinv, dep, pivtol, &ambiguous, src);
-    }
-    if (ambiguous) {
+    flops += 2.0 * ka * ka;
+    if (!hit) {
+        bool ambiguous = false;
+        {
+            SrcInPlace src;
+            src.Z = Sm; src.diag = sd;
+            chol_cols<true>(ex, Sm, ka, sd, srinv, dep, pivtol, &ambiguous, src);
+        }
+        if (ambiguous) {
 #ifdef WBC_EMU_DEBUG
-        printf("fallback ambiguous ka=%d\n", ka);
+            printf("fallback ambiguous ka=%d\n", ka);
 #endif
-        return false;
-    }
-    flops += (double)ka * ka * ka / 3.0 + 2.0 * ka * ka;
-    double ndep = 0.0;
+            return false;
+        }
+        flops += (double)ka * ka * ka / 3.0 + 2.0 * ka * ka;
+        double ndep = 0.0;
 #pragma unroll 1
-    for (int m = ex.lane(); m < ka; m += Ex::NL) ndep += dep[m];
-    ndep = red_sum1(ex, ndep);
-    if (ndep == 0.0) {
+        for (int m = ex.lane(); m < ka; m += Ex::NL) ndep += dep[m];
+        ndep_i = (int)red_sum1(ex, ndep);
+#pragma unroll 1
+        for (int m = ex.lane(); m < ka; m += Ex::NL) {
+            mc[gl::MC_SFD + m] = sd[m]; mc[gl::MC_SFRINV + m] = srinv[m];
+            mci[40 + m] = dep[m];
+        }
+#pragma unroll 1
+        for (int e = ex.lane(); e < nz; e += Ex::NL) mc[gl::MC_SF + e] = Sm[e];
+        if (ndep_i != 0) {
+            // G = Lt'Lt over the kept columns (identity on the skipped ones).
+            // Lt[i][a] = U[a][i] = Sm(i, a) (a < i), Lt[a][a] = sd[a]; skipped columns are exact zeros.
+#pragma unroll 1
+            for (int e = ex.lane(); e < npairs; e += Ex::NL) {
+                int c, a;
+                tri_index_lower(e, c, a);            // a <= c
+                double sacc;
+                if (dep[a] || dep[c]) sacc = (a == c) ? 1.0 : 0.0;
+                else {
+                    sacc = ((a == c) ? sd[c] : Sm[zoff(c) + a]) * sd[c];
+#pragma unroll 1
+                    for (int i = c + 1; i < ka; i++) sacc += Sm[zoff(i) + a] * Sm[zoff(i) + c];
+                }
+                if (a == c) gd[a] = sacc; else G[zoff(c) + a] = sacc;
+            }
+            ex.sync();
+            {
+                SrcInPlace src;
+                src.Z = G; src.diag = gd;
+                if (!chol_cols<false>(ex, G, ka, gd, grinv, (int*)nullptr, 0.0, (bool*)nullptr, src)) return false;
+            }
+#pragma unroll 1
+            for (int m = ex.lane(); m < ka; m += Ex::NL) { mc[gl::MC_GD + m] = gd[m]; mc[gl::MC_GRINV + m] = grinv[m]; }
+#pragma unroll 1
+            for (int e = ex.lane(); e < nz; e += Ex::NL) mc[gl::MC_G + e] = G[e];
+            flops += 2.0 * ka * ka * ka / 3.0;
+        }
+#pragma unroll 1
+        for (int m = ex.lane(); m < ka; m += Ex::NL) mci[m] = act[m];
+        ex.sync();
+        if (ex.lane() == 0) { mci[81] = version; mci[82] = ndep_i; mci[80] = ka; }
+    } else {
+        ndep_i = mci[82];
+        ex.copy_in(Sm, mc + gl::MC_SF, nz);
+#pragma unroll 1
+        for (int m = ex.lane(); m < ka; m += Ex::NL) { sd[m] = mc[gl::MC_SFD + m]; srinv[m] = mc[gl::MC_SFRINV + m]; dep[m] = mci[40 + m]; }
+        if (ndep_i != 0) {
+            ex.copy_in(G, mc + gl::MC_G, nz);
+#pragma unroll 1
+            for (int m = ex.lane(); m < ka; m += Ex::NL) { gd[m] = mc[gl::MC_GD + m]; grinv[m] = mc[gl::MC_GRINV + m]; }
+        }
+        *flags_io |= 64;
+    }
+    ex.sync();
+    if (ndep_i == 0) {
         tri_solve<false>(ex, Sm, ka, srinv, dl, true, true);
     } else {
-        // G = Lt'Lt over the kept columns (identity on the skipped ones), u = Lt' rho.
-        // Lt[i][a] = U[a][i] = Sm(i, a) (a < i), Lt[a][a] = sd[a]; skipped columns are exact zeros.
-#pragma unroll 1
-        for (int e = ex.lane(); e < npairs; e += Ex::NL) {
-            int c, a;
-            tri_index_lower(e, c, a);            // a <= c
-            double sacc;
-            if (dep[a] || dep[c]) sacc = (a == c) ? 1.0 : 0.0;
-            else {
-                sacc = ((a == c) ? sd[c] : Sm[zoff(c) + a]) * sd[c];
-#pragma unroll 1
-                for (int i = c + 1; i < ka; i++) sacc += Sm[zoff(i) + a] * Sm[zoff(i) + c];
-            }
-            if (a == c) gd[a] = sacc; else G[zoff(c) + a] = sacc;
-        }
+        // u = Lt' rho
 #pragma unroll 1
         for (int a = ex.lane(); a < ka; a += Ex::NL) {
             double sacc = sd[a] * rho_[a];
@@ -1345,11 +1436,6 @@ WBC_HDNI bool update_lagrange_multipliers_reduced(const Ex ex, const Work w, int
             u1[a] = dep[a] ? 0.0 : sacc;
         }
         ex.sync();
-        {
-            SrcInPlace src;
-            src.Z = G; src.diag = gd;
-            if (!chol_cols<false>(ex, G, ka, gd, grinv, (int*)nullptr, 0.0, (bool*)nullptr, src)) return false;
-        }
         tri_solve<false>(ex, G, ka, grinv, u1, true, true);
         // consistency: Lt u1 is the projection of rho on range(S); it must reproduce rho
         double mm[2] = {0.0, 0.0};
@@ -1377,7 +1463,7 @@ WBC_HDNI bool update_lagrange_multipliers_reduced(const Ex ex, const Work w, int
             dl[i] = sacc;
         }
         ex.sync();
-        flops += 4.0 * ka * ka * ka / 3.0;
+        flops += 2.0 * ka * ka * ka / 3.0;
         *flags_io |= 16;
     }
 #pragma unroll 1
@@ -1484,7 +1570,7 @@ WBC_HDNI void update_working_set(const Ex ex, const Work w, int nec, int nictota
     double* C = W_C(w);
     double* exxc = W_EXXC(w);
     double* nulc = W_NULC(w);
-    int extended = 0, added = 0;
+    int extended = 0, added = 0, evicted = 0;
 #pragma unroll 1
     while ((double)added < 1 + 0.20 * NMAIN && nicwork < nictotal) {
         // k = argmax_{j >= nicwork} nicerr[j], first maximum
@@ -1545,10 +1631,12 @@ WBC_HDNI void update_working_set(const Ex ex, const Work w, int nec, int nictota
                 }
                 ex.sync();
                 nicwork--;
+                evicted = 1;
             }
         }
     }
-    if (l == 0) { W_ISCR(w)[1] = nicwork; W_ISCR(w)[2] = extended; }
+    // iscr[6]: working-set version, bumped whenever rows of C moved (keys the multiplier-update cache)
+    if (l == 0) { W_ISCR(w)[1] = nicwork; W_ISCR(w)[2] = extended; if (extended || evicted) W_ISCR(w)[6] = W_ISCR(w)[6] + 1; }
     ex.sync();
 }
 
@@ -1786,6 +1874,11 @@ WBC_HDN void solve_denseaul(const Ex& ex, const Work& w, const Settings& cfg, in
     if (rc != 0) { st.termination = rc; return; }
     st.flops += 2.0 * nrows * NMAIN * NMAIN + 9000.0;
 
+    if (ex.lane() == 0) {
+        W_ISCR(w)[6] = 0;                                                        // working-set version
+        reinterpret_cast<int*>(w.g + gl::OFF_MC + gl::MC_INT)[80] = -1;          // multiplier-update cache: empty
+    }
+    ex.sync();
     int nicwork = 0;
     int allowevict = 1;
     if (!pd) { nicwork = nictotal; allowevict = 0; st.flags |= 1; }
