@@ -107,7 +107,7 @@ typedef struct wbc_outputs {
     double* x;          /* [30] QP solution, may be NULL                    lopt.cpp:108-110    */
     double* qp_obj;     /* [1]  0.5 x'Qx + c'x, may be NULL                                     */
     int* status;        /* [1]  0 ok; <0 solver failure (the reference swallows these, lopt.cpp:114), may be NULL */
-    int* qp_info;       /* [8]  ncholesky, outer its, QQP calls, working set, max KKT dim, flags, 0, 0; may be NULL */
+    int* qp_info;       /* [8]  ncholesky, outer its, QQP calls, working set, max KKT dim, flags, factorisations reused (of ncholesky), 0; may be NULL */
     double* qp_flops;   /* [1]  instrumented algorithmic flop count of the solve, may be NULL */
     long ld;
 } wbc_outputs;

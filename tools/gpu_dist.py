@@ -27,3 +27,4 @@ if fb.any():
 sp = (qi[5] & 32) != 0
 if sp.any():
     print("  spill-mode instances: %d, latency ms mean %.3f max %.3f" % (sp.sum(), ms[sp].mean(), ms[sp].max()))
+print("  Newton factorisations reused: %.2f of %.2f per solve; multiplier-cache hit in %.1f%% of solves" % (qi[6].mean(), qi[0].mean(), 100.0 * np.mean((qi[5] & 64) != 0)))

@@ -481,7 +481,7 @@ __device__ __noinline__ double2 newton_diag(int nic, double rho, unsigned fmask)
 }
 
 // One QQP solve from the point exxc (in/out) on the model (H, CI, rho, exb).  Returns the QQP termination type.
-__device__ __noinline__ int qqp_optimize_fast(const Work w, int nic, double rho, double epsx, int maxouterits, int* ncholesky, double* flops_io)
+__device__ __noinline__ int qqp_optimize_fast(const Work w, int nic, double rho, double epsx, int maxouterits, int* ncholesky, double* flops_io, int* reused_io)
 {
     const int l = threadIdx.x & 31;
     const int n = NMAIN + nic;
@@ -489,6 +489,10 @@ __device__ __noinline__ int qqp_optimize_fast(const Work w, int nic, double rho,
     const bool vA = l < NMAIN, vB = l < nic;
     int nsymv = 0;                      // products with E (2 n^2 flops each), for the instrumented flop count
     int nchol = 0, nfree = 0, cnmodelage = 0;
+    int nreused = 0;                    // factorisations skipped because the factor in memory was already the answer
+    bool fac_ok = false;
+    unsigned fac_mask = 0u;
+    double winvB = 0.0;
     int nschur = 0, nfix = 0;           // slack rows folded into Schur complements / solves, rank-one fixes (flop count)
     double* sxc = wbc_smem + sl::OFF_V + V_XC * VLS;
     double* sdc = wbc_smem + sl::OFF_V + V_DC * VLS;
@@ -568,7 +572,6 @@ __device__ __noinline__ int qqp_optimize_fast(const Work w, int nic, double rho,
         // constrained Newton phase (30353-30527)
         int newtcnt = 0;
         int freeB = 0;
-        double winvB = 0.0;
 #pragma unroll 1
         for (;;) {
             bool b;
@@ -579,11 +582,20 @@ __device__ __noinline__ int qqp_optimize_fast(const Work w, int nic, double rho,
                 nfree = NMAIN + __popc(fmask);
                 cnmodelage = 0;
                 nchol++;
-                nschur += __popc(fmask);
-                const double2 dg = newton_diag(nic, rho, fmask);
-                const double rsB = freeB ? rsqrt(dg.y) : 0.0;
-                winvB = rsB * rsB;
-                b = chol_build30(dg.x, rsB, fmask);
+                if (fac_ok && fmask == fac_mask) {
+                    // same model (H, CI, rho are fixed during this solve) and same free set as the factor in memory, which
+                    // no rank-one fix has touched: the factorisation would reproduce it bit for bit
+                    nreused++;
+                    b = true;
+                } else {
+                    nschur += __popc(fmask);
+                    const double2 dg = newton_diag(nic, rho, fmask);
+                    const double rsB = freeB ? rsqrt(dg.y) : 0.0;
+                    winvB = rsB * rsB;
+                    b = chol_build30(dg.x, rsB, fmask);
+                    fac_ok = b;
+                    fac_mask = fmask;
+                }
                 if (b) cgmax = cgminits;
             } else {
                 // qqpsolver_cnewtonupdate (31314-31426)
@@ -596,6 +608,7 @@ __device__ __noinline__ int qqp_optimize_fast(const Work w, int nic, double rho,
                 else {
 #pragma unroll 1
                     for (unsigned m = fixmask; m; m &= m - 1u) rank1_fix30(__ffs((int)m) - 1);
+                    fac_ok = false;                 // the factor no longer equals a fresh factorisation of any free set
                     if (tofix) { freeB = 0; winvB = 0.0; }
                     nfree -= ntofix;
                     cnmodelage += ntofix;
@@ -642,8 +655,9 @@ __device__ __noinline__ int qqp_optimize_fast(const Work w, int nic, double rho,
     if (vB) exxc[NMAIN + l] = (xcB < 0.0 || xcB == 0.0) ? 0.0 : xcB;
     __syncwarp();
     *ncholesky += nchol;
+    *reused_io += nreused;
     // work actually done: products with E, 30^3/3 per factorisation, 30^2 per slack row folded in, 3 * 30^2 per rank-one fix
-    *flops_io += 2.0 * n * n * (double)nsymv + (double)nchol * 9000.0 + 900.0 * (double)nschur + 2700.0 * (double)nfix;
+    *flops_io += 2.0 * n * n * (double)nsymv + (double)(nchol - nreused) * 9000.0 + 900.0 * (double)nschur + 2700.0 * (double)nfix;
     return term;
 }
 

@@ -186,6 +186,7 @@ struct Stats {
     int qqp_calls;      // inner QQP solves
     int nicwork;        // final working-set size
     int kkt_dim_max;    // largest (N+K) of the multiplier update
+    int chol_reused;    // constrained-Newton factorisations (counted in ncholesky) served by the factor already in memory
     int flags;          // bit0: A not PD (42500); bit2: QQP -4; bit3: literal multiplier update used;
                         // bit4: rank-deficient active set (least-norm branch); bit5: spilled to global memory;
                         // bit6: a multiplier update reused the cached factorisation of an unchanged active set
@@ -1790,11 +1791,11 @@ WBC_HD int model_and_qqp(const Ex& ex, const Work& w, int nec, int nicwork, doub
 #if defined(__CUDACC__)
 // device, shared-memory case: the register-resident QQP (the generic one is not instantiated: its vectors do not exist there)
 __device__ __forceinline__ int model_and_qqp_dev(const WarpEx& ex, const Work& w, int nec, int nicwork, double rho, double epsx,
-                                                 int* ncholesky, double* flops)
+                                                 int* ncholesky, double* flops, int* reused)
 {
     generate_ex_model<false>(ex, w, nec, nicwork, rho);
     *flops += (double)NMAIN * NMAIN * (nec + nicwork) + 4.0 * NMAIN * (nec + nicwork);
-    return fast::qqp_optimize_fast(w, nicwork, rho, 0.01 * epsx, 50, ncholesky, flops);
+    return fast::qqp_optimize_fast(w, nicwork, rho, 0.01 * epsx, 50, ncholesky, flops, reused);
 }
 #endif
 
@@ -1868,7 +1869,7 @@ WBC_HDN void solve_denseaul(const Ex& ex, const Work& w, const Settings& cfg, in
 {
     const int nec = neq, nictotal = nrows - neq;
     st.termination = 0; st.ncholesky = 0; st.outer_its = 0; st.qqp_calls = 0; st.nicwork = 0;
-    st.kkt_dim_max = 0; st.flags = 0; st.flops = 0.0;
+    st.kkt_dim_max = 0; st.chol_reused = 0; st.flags = 0; st.flops = 0.0;
     int pd = 0;
     const int rc = setup_problem(ex, w, nrows, &pd);
     if (rc != 0) { st.termination = rc; return; }
@@ -1908,7 +1909,7 @@ WBC_HDN void solve_denseaul(const Ex& ex, const Work& w, const Settings& cfg, in
             // shared-memory capacity: NICCAP working inequality rows, and nec + nicwork rows in the staging array
             if (nicwork > NICCAP || (nec + nicwork) * LDH > 1152) { st.flags |= 32; term = model_and_qqp<true>(ex, w, nec, nicwork, rho, epsx, &st.ncholesky, &st.flops); }
 #if defined(__CUDA_ARCH__)
-            else term = model_and_qqp_dev(ex, w, nec, nicwork, rho, epsx, &st.ncholesky, &st.flops);
+            else term = model_and_qqp_dev(ex, w, nec, nicwork, rho, epsx, &st.ncholesky, &st.flops, &st.chol_reused);
 #else
             else term = model_and_qqp<false>(ex, w, nec, nicwork, rho, epsx, &st.ncholesky, &st.flops);
 #endif

@@ -87,7 +87,7 @@ __device__ __forceinline__ void write_info(const Stats& st, long i, long ld, int
     if (info) {
         info[0 * ld + i] = st.ncholesky; info[1 * ld + i] = st.outer_its; info[2 * ld + i] = st.qqp_calls;
         info[3 * ld + i] = st.nicwork; info[4 * ld + i] = st.kkt_dim_max; info[5 * ld + i] = st.flags;
-        info[6 * ld + i] = 0; info[7 * ld + i] = 0;
+        info[6 * ld + i] = st.chol_reused; info[7 * ld + i] = 0;
     }
     if (flops) flops[i] = st.flops;
 }
