@@ -517,9 +517,38 @@ WBC_HD void tri_solve_regs(const Ex& ex, const double* Z, int n, const double* z
     for (int s = 0; s < NR; s++) if (l + Ex::NL * s < n) x[l + Ex::NL * s] = xr[s];
     ex.sync();
 }
+#if defined(__CUDACC__)
+// Device, n <= 32: one component per lane, both sweeps (same operations on the same operands as tri_solve_regs, without
+// its slot bookkeeping).  Dependent pivots (zrinv = 0) yield a zero component.
+__device__ __noinline__ void tri_solve_warp32(const double* Z, int n, const double* zrinv, double* x)
+{
+    const int l = threadIdx.x & 31;
+    const double* r0 = Z + zoff(l < n ? l : 0);
+    const double zr = (l < n) ? zrinv[l] : 0.0;
+    double x0 = (l < n) ? x[l] : 0.0;
+#pragma unroll 1
+    for (int k = 0; k < n; k++) {
+        const double yk = __shfl_sync(0xffffffffu, x0, k) * __shfl_sync(0xffffffffu, zr, k);
+        if (l == k) x0 = yk;
+        else if (l > k && l < n) x0 -= r0[k] * yk;
+    }
+#pragma unroll 1
+    for (int k = n - 1; k >= 0; k--) {
+        const double xk = __shfl_sync(0xffffffffu, x0, k) * __shfl_sync(0xffffffffu, zr, k);
+        const double* rk = Z + zoff(k);
+        if (l == k) x0 = xk;
+        else if (l < k) x0 -= rk[l] * xk;
+    }
+    if (l < n) x[l] = x0;
+    __syncwarp();
+}
+#endif
 template <bool SPILL, class Ex>
 WBC_HDNI void tri_solve(const Ex ex, const double* Z, int n, const double* zrinv, double* x, bool forward, bool backward)
 {
+#if defined(__CUDA_ARCH__)
+    if (!SPILL && Ex::NL == 32 && n <= 32 && forward && backward) { tri_solve_warp32(Z, n, zrinv, x); return; }
+#endif
     tri_solve_regs<SPILL ? 4 : 2>(ex, Z, n, zrinv, x, forward, backward);
 }
 
