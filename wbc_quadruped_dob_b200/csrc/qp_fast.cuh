@@ -286,6 +286,9 @@ __device__ __noinline__ void newton_direction(double gA, double gB, double winvB
         const int k = __ffs((int)m) - 1;
         r += CIc[k * LDH] * bshfl(u, k);
     }
+    // lanes past the slack count read a few entries of this vector as the (discarded) tail of the previous product's
+    // operand (symv reads x[30 + lane] unconditionally): order those reads before the overwrite
+    __syncwarp();
     if (l < NMAIN) sdc[l] = r;
     __syncwarp();
     tri_solve30(sdc);
