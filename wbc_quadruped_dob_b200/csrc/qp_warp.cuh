@@ -1543,6 +1543,7 @@ WBC_HDNI void generate_ex_model(const Ex ex, const Work w, int nec, int nic, dou
     for (int e = ex.lane(); e < 465; e += Ex::NL) {
         int i, j;
         tri_index30(e, i, j);
+        const double aij = A[i * LDH + j];          // global (L2): issued before the row loop so that its latency is covered
         double s0 = 0.0, s1 = 0.0;
         int r = 0;
 #pragma unroll 1
@@ -1551,7 +1552,7 @@ WBC_HDNI void generate_ex_model(const Ex ex, const Work w, int nec, int nic, dou
             s1 += Cs[(r + 1) * LDH + i] * Cs[(r + 1) * LDH + j];
         }
         if (r < kw) s0 += Cs[r * LDH + i] * Cs[r * LDH + j];
-        const double v = A[i * LDH + j] + rho * (s0 + s1);
+        const double v = aij + rho * (s0 + s1);
         H[i * LDH + j] = v;
         H[j * LDH + i] = v;
     }
