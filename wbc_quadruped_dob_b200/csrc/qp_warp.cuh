@@ -1520,6 +1520,14 @@ WBC_HD void tri_index30(int e, int& i, int& j)
     j = r + (e - (r * 30 - (r * (r - 1)) / 2));
 }
 
+// next element of the row-major 30 x 30 upper triangle, `step` positions ahead of (i, j)  (integer only; replaces a
+// tri_index30 -- sqrtf and two correction loops -- per element in the loops that walk the triangle with a lane stride)
+WBC_HD void tri_advance30(int& i, int& j, int step)
+{
+    j += step;
+    while (j >= NMAIN && i < NMAIN - 1) { j = j - NMAIN + i + 1; i++; }      // past the last element: (i, j) is left invalid, unused
+}
+
 template <bool SPILL, class Ex>
 WBC_HDNI void generate_ex_model(const Ex ex, const Work w, int nec, int nic, double rho)
 {
@@ -1539,10 +1547,10 @@ WBC_HDNI void generate_ex_model(const Ex ex, const Work w, int nec, int nic, dou
         Cs = st;
     }
     // quadratic term, main block: A + rho * C'C
+    int i, j;
+    tri_index30(ex.lane(), i, j);
 #pragma unroll 1
-    for (int e = ex.lane(); e < 465; e += Ex::NL) {
-        int i, j;
-        tri_index30(e, i, j);
+    for (int e = ex.lane(); e < 465; e += Ex::NL, tri_advance30(i, j, Ex::NL)) {
         const double aij = A[i * LDH + j];          // global (L2): issued before the row loop so that its latency is covered
         double s0 = 0.0, s1 = 0.0;
         int r = 0;
@@ -1696,10 +1704,10 @@ WBC_HDNI int setup_problem(const Ex ex, const Work w, int nrows, int* pd_out)
     if (bad != 0.0) return -9;
     // A <- S A S from the lower triangle, mirrored; Frobenius norm
     double an = 0.0;
+    int i, j;
+    tri_index30(ex.lane(), i, j);                       // i <= j: element (j, i) of the lower triangle
 #pragma unroll 1
-    for (int e = ex.lane(); e < 465; e += Ex::NL) {
-        int i, j;
-        tri_index30(e, i, j);                           // i <= j: element (j, i) of the lower triangle
+    for (int e = ex.lane(); e < 465; e += Ex::NL, tri_advance30(i, j, Ex::NL)) {
         const double v = As[j * LDH + i] * sc[i] * sc[j];
         As[i * LDH + j] = v;
         As[j * LDH + i] = v;
@@ -1748,6 +1756,13 @@ WBC_HDNI int setup_problem(const Ex ex, const Work w, int nrows, int* pd_out)
                 const int j = ex.lane();
                 const double cj = (j < NMAIN) ? row[j] : 0.0;
                 unsigned nz = ex.ballot(cj != 0.0);
+                if ((nz & (nz - 1u)) == 0u && nz != 0u) {
+                    // one non-zero (the 24 joint-limit rows): the sum over the lanes is the single term (c_k A_kk) c_k
+                    const int k = lowest_bit(nz);
+                    const double ck = row[k];
+                    maxcac = fmax(maxcac, fabs((ck * As[k * LDH + k]) * ck));
+                    continue;
+                }
                 double t = 0.0;
 #pragma unroll 1
                 while (nz) {
