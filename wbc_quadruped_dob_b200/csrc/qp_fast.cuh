@@ -29,12 +29,7 @@ __device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_ca
 __device__ __noinline__ double ddiv(double a, double b) { return a / b; }
 __device__ __noinline__ double dsqrt(double a) { return sqrt(a); }
 // warp sum, every lane gets the same bits
-__device__ __noinline__ double wsum(double v)
-{
-#pragma unroll 1
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-    return v;
-}
+__device__ __forceinline__ double wsum(double v) { return warp_sum_ni(v); }      // one shared copy of the butterfly (unrolled inside)
 // warp maximum of non-negative doubles (bit patterns order like the values)
 __device__ __forceinline__ double wmax_nn(double v)
 {

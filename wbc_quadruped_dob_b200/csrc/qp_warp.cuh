@@ -241,7 +241,7 @@ struct WarpEx {
 #if defined(__CUDACC__)
 __device__ __noinline__ double warp_sum_ni(double v)
 {
-#pragma unroll 1
+#pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
