@@ -177,6 +177,12 @@ struct Settings {
     // pivtol = 1e-9 the reduced form keeps those rows and the fallback disappears -- and 1 in 1000 swing torques is off
     // by 1e-5: on exactly these components the literal form's Tikhonov term is not negligible.  So the band stays.
     double kkt_pivtol = 1.0e-5;
+    // Hint from the caller that assembled L: rows [dup_start[t], dup_start[t] + dup_count[t]) have, coefficient for
+    // coefficient, the negatives of the dup_count[t] rows just before them (upper / lower limits on the same
+    // quantity).  c'Ac of a row and of its negative are the same number bit for bit, so set-up's maximum over the
+    // rows skips them.  Zero counts (the default, and the dense OPT operator): nothing is assumed.
+    int dup_start[2] = {0, 0};
+    int dup_count[2] = {0, 0};
 };
 
 struct Stats {
@@ -1684,7 +1690,7 @@ WBC_HDNI void update_working_set(const Ex ex, const Work w, int nec, int nictota
 // (42374-42446), selectinitialworkingset (42474-42523).  On entry: Q (lower triangle used, opt.cpp:4962/18959) in the H
 // array (ld 31), c in exb[0..30), L rows in the global C array.  Returns 0, or -9 for a non-positive diagonal.
 template <class Ex>
-WBC_HDNI int setup_problem(const Ex ex, const Work w, int nrows, int* pd_out)
+WBC_HDNI int setup_problem(const Ex ex, const Work w, int nrows, int* pd_out, int dup0s, int dup0c, int dup1s, int dup1c)
 {
     double* As = W_H(w);
     double* sc = W_SC(w);
@@ -1750,6 +1756,8 @@ WBC_HDNI int setup_problem(const Ex ex, const Work w, int nrows, int* pd_out)
         // 12..24 (dynamics, torque limits) of them out of 30.
 #pragma unroll 1
         for (int r = 0; r < nr; r++) {
+            const int gr = r0 + r;
+            if ((gr >= dup0s && gr < dup0s + dup0c) || (gr >= dup1s && gr < dup1s + dup1c)) continue;   // negated twin of an earlier row
             const double* row = stage + r * LDH;
             double part = 0.0;
             if (Ex::NL >= NMAIN) {
@@ -1916,7 +1924,7 @@ WBC_HDN void solve_denseaul(const Ex& ex, const Work& w, const Settings& cfg, in
     st.termination = 0; st.ncholesky = 0; st.outer_its = 0; st.qqp_calls = 0; st.nicwork = 0;
     st.kkt_dim_max = 0; st.chol_reused = 0; st.flags = 0; st.flops = 0.0;
     int pd = 0;
-    const int rc = setup_problem(ex, w, nrows, &pd);
+    const int rc = setup_problem(ex, w, nrows, &pd, cfg.dup_start[0], cfg.dup_count[0], cfg.dup_start[1], cfg.dup_count[1]);
     if (rc != 0) { st.termination = rc; return; }
     st.flops += 2.0 * nrows * NMAIN * NMAIN + 9000.0;
 

@@ -125,6 +125,12 @@ __global__ void __launch_bounds__(SOLVE_T) wbc_solve_kernel(Params P, int n, con
         const QpShape sh = qp_shape((int)rec[QR_MODE]);
         // Q -> H array (ld 31), c -> exb, L -> the warp's global C array (scaled in place by the solver)
         assemble_qp<LDH>(ex, P, rec, sh, W_H(w), W_EXB(w), W_C(w));
+        // the lower torque limits and the lower joint-acceleration limits are the negated upper ones (wbc_assemble.cuh)
+        {
+            const int rt = sh.neq + 5 * sh.nst, rq = rt + 24 + (sh.nst == 2 ? 12 : 0);
+            cfg.dup_start[0] = rt + 12; cfg.dup_count[0] = 12;
+            cfg.dup_start[1] = rq + 12; cfg.dup_count[1] = 12;
+        }
         Stats st;
         solve_denseaul(ex, w, cfg, sh.nrows, sh.neq, st);
         double* xs = W_XS(w);
