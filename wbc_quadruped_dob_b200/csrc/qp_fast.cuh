@@ -211,26 +211,37 @@ __device__ __noinline__ bool chol_build30(double diagA, double rsB, unsigned fma
 }
 
 // Solve U'U x = rhs (30 x 30 packed factor); rhs and result in shared memory at x[0..30).
+// Two columns per step: both pivot components are broadcast at once and the second one is finished redundantly by every
+// lane (y_{k+1} = (x_{k+1} - U_{k,k+1} y_k) / U_{k+1,k+1}), so the dependent chain is one shuffle per two columns instead
+// of one per column.  The operations on every component are the ones of the one-column sweep, in the same order.
 __device__ __noinline__ void tri_solve30(double* x)
 {
     const int l = threadIdx.x & 31;
     const double* Z = wbc_smem + sl::OFF_Z;
+    const double* zrinv = wbc_smem + sl::OFF_V + V_ZRINV * VLS;
     const double* r0 = Z + zoff(l < NMAIN ? l : NMAIN - 1);
-    const double zr0 = wbc_smem[sl::OFF_V + V_ZRINV * VLS + l];
     double x0 = x[l];                                       // lanes 30, 31 carry finite values that are never broadcast
 #pragma unroll 1
-    for (int k = 0; k < NMAIN; k++) {                       // forward: U' y = rhs, column oriented
-        const double yk = bshfl(x0 * zr0, k);
+    for (int k = 0; k < NMAIN; k += 2) {                    // forward: U' y = rhs, column oriented
+        const double2 zr = ld2(zrinv + k);
+        const double c = Z[zoff(k + 1) + k];                // U_{k,k+1}
+        const double yk = bshfl(x0, k) * zr.x;
+        const double yk1 = (bshfl(x0, k + 1) - c * yk) * zr.y;
         if (l > k) x0 -= r0[k] * yk;
+        if (l > k + 1) x0 -= r0[k + 1] * yk1;
     }
-    x0 *= zr0;
+    x0 *= zrinv[l < NMAIN ? l : 0];
 #pragma unroll 1
-    for (int k = NMAIN - 1; k >= 0; k--) {                  // backward: U x = y
-        const double xk = bshfl(x0 * zr0, k);
+    for (int k = NMAIN - 1; k > 0; k -= 2) {                // backward: U x = y
+        const double2 zr = ld2(zrinv + k - 1);
         const double* rk = Z + zoff(k);
+        const double c = rk[k - 1];                         // U_{k-1,k}
+        const double xk = bshfl(x0, k) * zr.y;
+        const double xk1 = (bshfl(x0, k - 1) - c * xk) * zr.x;
         if (l < k) x0 -= rk[l] * xk;
+        if (l < k - 1) x0 -= Z[zoff(k - 1) + l] * xk1;
     }
-    x0 *= zr0;
+    x0 *= zrinv[l < NMAIN ? l : 0];
     __syncwarp();
     if (l < NMAIN) x[l] = x0;
     __syncwarp();
