@@ -190,14 +190,17 @@ __device__ __noinline__ bool chol_build30(double diagA, double rsB, unsigned fma
         }
         double v0 = ((c == k) ? diagA : H[k * LDH]) - s0 - (p0 + q0);
         double v1 = ((c == k + 1) ? diagA : H[(k + 1) * LDH]) - s1 - (p1 + q1);
+        // the three values the two pivots depend on are broadcast at once and every lane finishes both pivots itself
+        // (same operations as lane k + 1 performs on its own entries): one shuffle latency on the chain instead of three
         const double piv0 = bshfl(v0, k);
+        const double v0n = bshfl(v0, k + 1), v1n = bshfl(v1, k + 1);
         if (!(piv0 > 0.0)) return false;
         const double ri0 = rsqrt(piv0);
         const double z0k = v0 * ri0;
         if (c > k && c < NMAIN) r0[k] = z0k;
-        const double zk1k = bshfl(z0k, k + 1);
+        const double zk1k = v0n * ri0;
         v1 -= z0k * zk1k;
-        const double piv1 = bshfl(v1, k + 1);
+        const double piv1 = v1n - zk1k * zk1k;
         if (!(piv1 > 0.0)) return false;
         const double ri1 = rsqrt(piv1);
         if (c > k + 1 && c < NMAIN) r0[k + 1] = v1 * ri1;
