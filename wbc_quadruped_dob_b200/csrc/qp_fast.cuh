@@ -546,7 +546,7 @@ __device__ __noinline__ int qqp_optimize_fast(const Work w, int nic, double rho,
         }
         outerits++;
         xpA = xcA; xpB = xcB;
-        double cgpA = 0.0, cgpB = 0.0, dpA = 0.0, dpB = 0.0;
+        double dpA = 0.0, dpB = 0.0, vprev = 0.0;       // previous direction, |previous constrained gradient|^2
 #pragma unroll 1
         for (int cgcnt = 0; cgcnt <= cgmax - 1; cgcnt++) {
             const double2 ex = symv(sxc, nic2, rho);                            // targetgradient
@@ -556,7 +556,8 @@ __device__ __noinline__ int qqp_optimize_fast(const Work w, int nic, double rho,
             const bool act = atb && gB >= 0.0;
             csB = act ? 1 : -1;
             const double cgA = gA, cgB = act ? 0.0 : gB;
-            const double v = wsum(cgA * cgA + cgB * cgB), vv = wsum(cgpA * cgpA + cgpB * cgpB);
+            // |cg_prev|^2 is the previous iteration's |cg|^2 (the same sum of the same numbers), 0 at the start of the phase
+            const double v = wsum(cgA * cgA + cgB * cgB), vv = vprev;
             const bool bf = __any_sync(FULL, atb && dpB != 0.0);
             if (v <= 0.0) { term = 4; break; }      // sqrt(v) <= 0 with v a sum of squares
             const bool brst = bf || (vv == 0.0) || (cgcnt % 50 == 0);
@@ -577,7 +578,7 @@ __device__ __noinline__ int qqp_optimize_fast(const Work w, int nic, double rho,
             csB = step_and_move(dA, dB, exbA, exbB, nic, rho, d2est > 0 ? 0 : 1, cidx, csB);
             xcA = vA ? sxc[l] : 0.0; xcB = vB ? sxc[NMAIN + l] : 0.0;
             if (spare[7] > 0.0) nsymv += 1 + (int)spare[7];
-            dpA = dA; dpB = dB; cgpA = cgA; cgpB = cgB;
+            dpA = dA; dpB = dB; vprev = v;
         }
         if (term != 0) break;
         cgmax = cgmaxits;
