@@ -213,6 +213,9 @@ struct HostEx {
     WBC_HD int popc(unsigned m) const { return (int)m; }
     // bulk copy into the instance's fast storage (device: global -> shared)
     WBC_HD void copy_in(double* dst, const double* src, int n) const { for (int e = 0; e < n; e++) dst[e] = src[e]; }
+    // several copies in flight at once: copy_start ... copy_start, then one copy_wait
+    WBC_HD void copy_start(double* dst, const double* src, int n) const { copy_in(dst, src, n); }
+    WBC_HD void copy_wait() const {}
 };
 #if defined(__CUDACC__)
 struct WarpEx {
@@ -236,6 +239,20 @@ struct WarpEx {
 #pragma unroll 4
         for (int e = l; e < n; e += 32, d += 256u, g += 32)
             asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(g) : "memory");
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncwarp();
+    }
+    __device__ __forceinline__ void copy_start(double* dst, const double* src, int n) const
+    {
+        const int l = threadIdx.x & 31;
+        unsigned d = (unsigned)__cvta_generic_to_shared(dst) + 8u * l;
+        const double* g = src + l;
+#pragma unroll 4
+        for (int e = l; e < n; e += 32, d += 256u, g += 32)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(g) : "memory");
+    }
+    __device__ __forceinline__ void copy_wait() const
+    {
         asm volatile("cp.async.wait_all;" ::: "memory");
         __syncwarp();
     }
@@ -1292,6 +1309,8 @@ WBC_HDNI bool update_lagrange_multipliers_reduced(const Ex ex, const Work w, int
     double* G = big;                               // packed lower, 648: overlays Wm, which is dead by then
     double* LAs = Sm + 648;                        // packed factor of A, 450  -> 2246 <= 2640
     static_assert((KACAP + 1) * LDH + 1 + 648 + 450 <= sl::BIG, "reduced multiplier update workspace");
+    double* Sfac = Sm;                             // where the factor of S / of G is read from (a cache hit puts them elsewhere)
+    double* Gfac = G;
     static_assert(KACAP <= 40 && ((KACAP * (KACAP - 1)) >> 1) + (KACAP >> 1) <= 648, "multiplier cache rows");
     double* vv = W_VEC(w);
     double* sd = vv;
@@ -1372,7 +1391,15 @@ WBC_HDNI bool update_lagrange_multipliers_reduced(const Ex ex, const Work w, int
         for (int e = ex.lane(); e < nz; e += Ex::NL) mc[gl::MC_S0 + e] = Sm[e];
         flops += (double)(ka + 1) * NMAIN * NMAIN + (double)ka * ka * NMAIN + 2.0 * ka * NMAIN;
     } else {
-        ex.copy_in(Sm, mc + gl::MC_S0, nz);
+        // every cached block is fetched in one round trip: S into its usual place, the factors into the (unused) W area
+        ndep_i = mci[82];
+        Sfac = big;
+        Gfac = big + 1796;
+        static_assert(1796 + 648 <= sl::BIG && 648 <= (KACAP + 1) * LDH + 1, "cached factors fit around S");
+        ex.copy_start(Sm, mc + gl::MC_S0, nz);
+        ex.copy_start(Sfac, mc + gl::MC_SF, nz);
+        if (ndep_i != 0) ex.copy_start(Gfac, mc + gl::MC_G, nz);
+        ex.copy_wait();
 #pragma unroll 1
         for (int m = ex.lane(); m < ka; m += Ex::NL) sd[m] = mc[gl::MC_S0D + m];
     }
@@ -1448,12 +1475,9 @@ WBC_HDNI bool update_lagrange_multipliers_reduced(const Ex ex, const Work w, int
         ex.sync();
         if (ex.lane() == 0) { mci[81] = version; mci[82] = ndep_i; mci[80] = ka; }
     } else {
-        ndep_i = mci[82];
-        ex.copy_in(Sm, mc + gl::MC_SF, nz);
 #pragma unroll 1
         for (int m = ex.lane(); m < ka; m += Ex::NL) { sd[m] = mc[gl::MC_SFD + m]; srinv[m] = mc[gl::MC_SFRINV + m]; dep[m] = mci[40 + m]; }
         if (ndep_i != 0) {
-            ex.copy_in(G, mc + gl::MC_G, nz);
 #pragma unroll 1
             for (int m = ex.lane(); m < ka; m += Ex::NL) { gd[m] = mc[gl::MC_GD + m]; grinv[m] = mc[gl::MC_GRINV + m]; }
         }
@@ -1461,25 +1485,25 @@ WBC_HDNI bool update_lagrange_multipliers_reduced(const Ex ex, const Work w, int
     }
     ex.sync();
     if (ndep_i == 0) {
-        tri_solve<false>(ex, Sm, ka, srinv, dl, true, true);
+        tri_solve<false>(ex, Sfac, ka, srinv, dl, true, true);
     } else {
         // u = Lt' rho
 #pragma unroll 1
         for (int a = ex.lane(); a < ka; a += Ex::NL) {
             double sacc = sd[a] * rho_[a];
 #pragma unroll 1
-            for (int i = a + 1; i < ka; i++) sacc += Sm[zoff(i) + a] * rho_[i];
+            for (int i = a + 1; i < ka; i++) sacc += Sfac[zoff(i) + a] * rho_[i];
             u1[a] = dep[a] ? 0.0 : sacc;
         }
         ex.sync();
-        tri_solve<false>(ex, G, ka, grinv, u1, true, true);
+        tri_solve<false>(ex, Gfac, ka, grinv, u1, true, true);
         // consistency: Lt u1 is the projection of rho on range(S); it must reproduce rho
         double mm[2] = {0.0, 0.0};
 #pragma unroll 1
         for (int i = ex.lane(); i < ka; i += Ex::NL) {
             double sacc = sd[i] * u1[i];
 #pragma unroll 1
-            for (int a = 0; a < i; a++) sacc += Sm[zoff(i) + a] * u1[a];
+            for (int a = 0; a < i; a++) sacc += Sfac[zoff(i) + a] * u1[a];
             mm[0] = fmax(mm[0], fabs(sacc - rho_[i]));
             mm[1] = fmax(mm[1], fabs(C[act[i] * LDH + NMAIN]));
         }
@@ -1490,12 +1514,12 @@ WBC_HDNI bool update_lagrange_multipliers_reduced(const Ex ex, const Work w, int
 #endif
             return false;
         }
-        tri_solve<false>(ex, G, ka, grinv, u1, true, true);
+        tri_solve<false>(ex, Gfac, ka, grinv, u1, true, true);
 #pragma unroll 1
         for (int i = ex.lane(); i < ka; i += Ex::NL) {
             double sacc = sd[i] * u1[i];
 #pragma unroll 1
-            for (int a = 0; a < i; a++) sacc += Sm[zoff(i) + a] * u1[a];
+            for (int a = 0; a < i; a++) sacc += Sfac[zoff(i) + a] * u1[a];
             dl[i] = sacc;
         }
         ex.sync();
