@@ -74,3 +74,22 @@ def test_failure_is_reported_not_swallowed(emu):
     Q[3, 3] = 0.0
     _, ist, _ = emu.qp_solve(Q, z["c"][0], z["L"][0], int(z["neq"]))
     assert ist[0] == -9
+
+
+def test_multiplier_update_cache_is_exact(emu):
+    """The reduced multiplier update reuses W, S = WW' and the factors while the active set is unchanged; a build that
+    always recomputes (-DWBC_NO_REUSE) must give the same bits, and the cache must actually be hit."""
+    import ctypes as C
+    import os
+    import subprocess
+    so = os.path.join(util.EMU_DIR, "libwbc_emu_noreuse.so")
+    src = os.path.join(util.EMU_DIR, "wbc_emu.cpp")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-DWBC_NO_REUSE", "-o", so, src])
+    plain = util.Emu()
+    plain.lib = C.CDLL(so)
+    sc = S.make(300, mode_mix=(0.34, 0.33, 0.33), pushes=True, terrain=True, seed=4321)
+    a, b = emu.cycle(sc), plain.cycle(sc)
+    for k in ("tau", "w", "x", "qp_obj", "status"):
+        assert np.array_equal(a[k], b[k]), k
+    assert np.array_equal(a["qp_info"][0], b["qp_info"][0])
+    assert np.mean((a["qp_info"][5] & 64) != 0) > 0.9 and not ((b["qp_info"][5] & 64) != 0).any()

@@ -1338,6 +1338,9 @@ WBC_HDNI bool update_lagrange_multipliers_reduced(const Ex ex, const Work w, int
             if (mci[m] != act[m]) diff = 1.0;
         hit = red_sum1(ex, diff) == 0.0;
     }
+#ifdef WBC_NO_REUSE
+    hit = false;                                   // test builds: always recompute (tests/test_emulation.py compares the two)
+#endif
 #pragma unroll 1
     for (int m = ex.lane(); m < ka; m += Ex::NL) nu0[m] = nulcest[act[m]];
     int ndep_i = 0;
