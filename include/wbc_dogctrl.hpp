@@ -226,8 +226,18 @@ public:
     {
         for (int i = 0; i < 6; i++) { b_.sw_des_pos[i] = pos(i); b_.sw_des_vel[i] = vel(i); b_.sw_des_acc[i] = acc(i); }
     }
-    void cycle_stance() { b_.mode[0] = WBC_MODE_STANCE; b_.cycle(); }
-    void cycle_swing(bool first_half) { b_.mode[0] = first_half ? WBC_MODE_SWING_BR_FL : WBC_MODE_SWING_BL_FR; b_.cycle(); }
+    // Planner hand-over (after get_trajectory(), main.cpp:900-960): the four solution splines of this robot -- base_linear_,
+    // base_angular_, ee_motion_ of the two swing feet -- as `nseg` cubic-Hermite polynomials each.  durations [4][nseg],
+    // nodes [4][nseg+1][6] (position 3, velocity 3).  Then sample_trajectory(t) + cycle_*(true) replace set_com_desired /
+    // set_swing_desired: solution.*->GetPoint(t) is evaluated on the GPU (main.cpp:1004-1010, 1333-1368).
+    void set_trajectory(int nseg, const double* durations, const double* nodes) { b_.set_trajectory(nseg, durations, nodes); }
+    void sample_trajectory(double t) { b_.sample_trajectory(t); }
+    void cycle_stance(bool sampled_trajectory = false) { b_.mode[0] = WBC_MODE_STANCE; b_.cycle(sampled_trajectory); }
+    void cycle_swing(bool first_half, bool sampled_trajectory = false)
+    {
+        b_.mode[0] = first_half ? WBC_MODE_SWING_BR_FL : WBC_MODE_SWING_BL_FR;
+        b_.cycle(sampled_trajectory);
+    }
 
     const double* tau() const { return b_.tau.data(); }     // [12]  main.cpp:1126, 1396
     const double* w() const { return b_.w.data(); }         // [6]   main.cpp:718

@@ -57,6 +57,34 @@ def test_dogctrl_trot_replay_matches_golden(exe, tmp_path):
     assert eo.max() <= util.TOL_OBJ
 
 
+def _write_replay(fin, sc, idx):
+    with open(fin, "wb") as f:
+        f.write(struct.pack("i", len(idx)))
+        for i in idx:
+            H = np.eye(4)
+            H[:3, :3] = sc["base_rot"][:, i].reshape(3, 3)
+            H[:3, 3] = sc["base_pos"][:, i]
+            rec = [H.ravel(), sc["q"][:, i], sc["dq"][:, i], sc["base_vel"][:, i], np.array([0.0, 0.0, -9.8]), sc["base_rpy"][:, i],
+                   sc["com_des_pos"][:, i], sc["com_des_vel"][:, i], sc["com_des_acc"][:, i], sc["foot_force"][:, i],
+                   sc["sw_des_pos"][:, i], sc["sw_des_vel"][:, i], sc["sw_des_acc"][:, i], np.array([float(sc["mode"][i])])]
+            f.write(np.concatenate(rec).astype(np.float64).tobytes())
+
+
+@pytest.mark.gpu
+def test_dogctrl_plan_on_the_device_matches_host_fed_samples(exe, tmp_path):
+    """DogCtrl::set_trajectory / sample_trajectory / cycle_*(true) (SURVEY 8f-1): a cycle fed from the samples that stay
+    on the GPU gives the torques of the same cycle fed those samples from the host, bit for bit, in all three modes."""
+    sc, _ = util.load_golden("cycle_trot_replay")
+    idx = [0, 5, 12, 20, 30, 36, 47]
+    fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    _write_replay(fin, sc, idx)
+    subprocess.run([exe, "traj", fin, fout], check=True)
+    out = np.fromfile(fout, dtype=np.float64).reshape(len(idx), 24)
+    assert np.isfinite(out).all() and np.abs(out[:, :12]).max() > 0.1
+    assert np.array_equal(out[:, :12], out[:, 12:])
+    assert {int(sc["mode"][i]) for i in idx} == {0, 1, 2}
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["qp_stance", "qp_swing"])
 def test_opt_mirror_matches_reference_alglib(exe, tmp_path, name):
