@@ -70,7 +70,7 @@ def cpu_reference_run(sc, steps, warmup, sample, cores):
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons of one GPU during the timed region (NVML, else nvidia-smi)."""
 
-    def __init__(self, index, period=0.05):
+    def __init__(self, index, period=0.01):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
