@@ -206,7 +206,8 @@ int wbc_set_trajectory(wbc_ctx* ctx, int n, const wbc_trajectory* tr, void* cuda
 /* Sample the ctx's plan at time t[i] per instance (t == NULL: t_all for every instance).  One kernel launch.
  * out == NULL: the samples stay in the ctx, for a following wbc_cycle(..., WBC_SAMPLED_TRAJ);
  * out != NULL: written to the caller's arrays -- device arrays with WBC_DEVICE_PTRS (e.g. the ones handed to
- * wbc_cycle as device inputs), else host arrays (a D2H copy; for inspection and tests).  t follows the same flag. */
+ * wbc_cycle as device inputs), else host arrays (a D2H copy; for inspection and tests).  t follows the same flag.
+ * The sampling and the cycle that consumes it must be ordered: pass both the same stream (NULL = the ctx's own). */
 int wbc_sample_trajectory(wbc_ctx* ctx, int n, const double* t, double t_all, const wbc_traj_samples* out, void* cuda_stream, unsigned flags);
 
 /* Page-locked host memory for the SoA arrays handed to wbc_cycle with WBC_HOST_PTRS.  Arrays that are page-locked
