@@ -312,7 +312,8 @@ struct wbc_ctx {
     double* yw;
     double* w_dev;       // [6][max_batch] (when the caller passes no w)
     double* scratch;     // [nblocks][gl::TOTAL]
-    int* queue;          // work-queue counter [0], dispatch cursors [1, 1+ORD_NB), cost histograms [2][ORD_NB] after them
+    int* queue;          // [cost histogram A | work-queue counter | dispatch cursors | cost histogram B]: counter and cursors sit between
+                         // the two histograms so that "counter + cursors + the histogram being filled" is one contiguous memset either way
     unsigned* cost;      // [max_batch] duration of each instance's last solve (1024-cycle units)
     int* order;          // [max_batch] dispatch order built by the front kernel
     int order_n;         // batch size `cost` and the current histogram describe (0 = none)
@@ -603,19 +604,21 @@ int wbc_cycle(wbc_ctx* c, int n, const wbc_inputs* in, const wbc_outputs* out, v
     DevDebug nodbg;
     memset(&nodbg, 0, sizeof(nodbg));
     // dispatch order: longest solve first, predicted by each instance's previous solve (same batch size only)
-    int* hist_prev = c->queue + 1 + ORD_NB + c->hist_sel * ORD_NB;
-    int* hist_next = c->queue + 1 + ORD_NB + (c->hist_sel ^ 1) * ORD_NB;
+    int* hist_ab[2] = {c->queue, c->queue + 2 * ORD_NB + 1};
+    int* counter = c->queue + ORD_NB;
+    int* hist_prev = hist_ab[c->hist_sel];
+    int* hist_next = hist_ab[c->hist_sel ^ 1];
     const bool ordered = !(flags & WBC_FIFO_DISPATCH) && c->order_n == n && n > 1;
     DispatchOrder ord;
-    ord.cost = ordered ? c->cost : nullptr; ord.hist = hist_prev; ord.cursor = c->queue + 1; ord.order = c->order;
-    CU(cudaMemsetAsync(c->queue, 0, (1 + ORD_NB) * sizeof(int), s));
-    CU(cudaMemsetAsync(hist_next, 0, ORD_NB * sizeof(int), s));
+    ord.cost = ordered ? c->cost : nullptr; ord.hist = hist_prev; ord.cursor = counter + 1; ord.order = c->order;
+    // one memset: counter, cursors and the histogram this cycle fills (A lies just before the counter, B just after the cursors)
+    CU(cudaMemsetAsync((c->hist_sel ^ 1) == 0 ? c->queue : counter, 0, (1 + 2 * ORD_NB) * sizeof(int), s));
     CU(cudaEventRecord(c->ev0, s));
     const int fthreads = front_threads(c, n);
     wbc_front_kernel<<<(n + fthreads - 1) / fthreads, fthreads, 0, s>>>(c->params, din, st, n, c->recs, w_ptr, w_ld, nodbg, 0, ord);
     CU(cudaEventRecord(c->ev1, s));
     const int nblocks = n < c->nblocks ? n : c->nblocks;
-    wbc_solve_kernel<<<nblocks, c->threads, c->solve_smem, s>>>(c->params, n, c->recs, so, c->scratch, c->queue, ordered ? c->order : nullptr,
+    wbc_solve_kernel<<<nblocks, c->threads, c->solve_smem, s>>>(c->params, n, c->recs, so, c->scratch, counter, ordered ? c->order : nullptr,
                                                            c->cost, hist_next);
     CU(cudaEventRecord(c->ev2, s));
     CU(cudaGetLastError());
@@ -895,11 +898,11 @@ int wbc_qp_solve(wbc_ctx* c, int n, const double* Q, const double* cvec, const d
         dstatus = status ? ip : nullptr;
         dinfo = info ? ip + n : nullptr;
     }
-    CU(cudaMemsetAsync(c->queue, 0, sizeof(int), s));
+    CU(cudaMemsetAsync(c->queue + ORD_NB, 0, sizeof(int), s));
     const int nblocks = n < c->nblocks ? n : c->nblocks;
     CU(cudaEventRecord(c->ev0, s));
     CU(cudaEventRecord(c->ev1, s));
-    wbc_dense_qp_kernel<<<nblocks, c->threads, c->solve_smem, s>>>(c->params, n, dQ, dc, dL, nrows, neq, dx, dstatus, dinfo, dflops, c->scratch, c->queue);
+    wbc_dense_qp_kernel<<<nblocks, c->threads, c->solve_smem, s>>>(c->params, n, dQ, dc, dL, nrows, neq, dx, dstatus, dinfo, dflops, c->scratch, c->queue + ORD_NB);
     CU(cudaEventRecord(c->ev2, s));
     CU(cudaGetLastError());
     c->launches = 1;
