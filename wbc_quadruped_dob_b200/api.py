@@ -88,9 +88,10 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(_build.LIB):
+    path = os.environ.get("WBC_B200_LIB") or _build.LIB          # A/B experiments: a variant build of the same library
+    if path == _build.LIB and not os.path.exists(_build.LIB):
         _build.build()
-    lib = C.CDLL(_build.LIB)
+    lib = C.CDLL(path)
     lib.wbc_default_params.argtypes = [C.POINTER(Params)]
     lib.wbc_last_error.restype = C.c_char_p
     lib.wbc_version.restype = C.c_char_p
