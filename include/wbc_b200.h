@@ -39,6 +39,9 @@ extern "C" {
 #define WBC_ENODEV (-2)     /* no usable CUDA device */
 #define WBC_ECUDA (-3)      /* CUDA runtime error (see wbc_last_error) */
 #define WBC_ENOMEM (-4)
+/* per-instance status words (wbc_outputs.status) for inputs the cycle refuses to process */
+#define WBC_ST_BAD_MODE (-20)    /* contact mode outside {0, 1, 2} */
+#define WBC_ST_NONFINITE (-21)   /* a NaN or infinity among the inputs, or produced from them before the QP */
 
 /* contact modes: which feet swing */
 #define WBC_MODE_STANCE 0        /* main.cpp:979-1148, 1516-1675 */
@@ -77,6 +80,9 @@ typedef struct wbc_params {
     int observer_enabled;     /* 1: call estimate() at main.cpp:1029/1220/1569/1767 (reference ships 0) */
     int fix_swing_rhs;        /* 0: keep the reference's zero swing-equality rhs (main.cpp:1238-1241) */
     int qp_literal_kkt;       /* 0 (default): reduced multiplier update with the literal form as fallback; 1: always the literal stacked-KKT QR (opt.cpp:41803-42032) */
+    int hold_tau_on_failure;  /* 0 (default): a failed instance gets tau from x = 0 (tau = 0 when its inputs are invalid);
+                                 1: it gets the last good tau this ctx produced for that instance index -- the reference
+                                 keeps publishing its `tau` member when the QP throws (lopt.cpp:114-116, main.cpp:242, 1126) */
 } wbc_params;
 
 /* One control cycle's inputs for n instances (what update() receives plus the members it reads). */
@@ -106,7 +112,9 @@ typedef struct wbc_outputs {
     double* w;          /* [6]  estimated disturbance wrench w[0]           main.cpp:718        */
     double* x;          /* [30] QP solution, may be NULL                    lopt.cpp:108-110    */
     double* qp_obj;     /* [1]  0.5 x'Qx + c'x, may be NULL                                     */
-    int* status;        /* [1]  0 ok; <0 solver failure (the reference swallows these, lopt.cpp:114), may be NULL */
+    int* status;        /* [1]  0 ok; <0 failure (the reference swallows these, lopt.cpp:114), may be NULL:
+                               WBC_ST_BAD_MODE / WBC_ST_NONFINITE = invalid inputs (nothing is solved, the observer state of the
+                               instance is left as it was), -9 = non-positive diagonal of Q (opt.cpp:48178), -100 = other */
     int* qp_info;       /* [8]  ncholesky, outer its, QQP calls, working set, max KKT dim, flags, factorisations reused (of ncholesky), 0; may be NULL */
     double* qp_flops;   /* [1]  instrumented algorithmic flop count of the solve, may be NULL */
     long ld;
@@ -151,13 +159,15 @@ int wbc_get_observer_state(wbc_ctx* ctx, int n, double* yd, double* yw, long ld)
  * `cuda_stream` is a cudaStream_t (NULL = the ctx's own stream). */
 int wbc_cycle(wbc_ctx* ctx, int n, const wbc_inputs* in, const wbc_outputs* out, void* cuda_stream, unsigned flags);
 
-/* update() only, with intermediates dumped (does not touch the observer state). */
+/* update() only, with intermediates dumped.  Runs on a copy of the ctx's observer state (so Fgrf / Wcom_des are what the next
+ * wbc_cycle would compute) and changes neither that state nor the records wbc_plant_step reads. */
 int wbc_debug_update(wbc_ctx* ctx, int n, const wbc_inputs* in, const wbc_debug* dbg, unsigned flags);
 
 /* The OPT operator (lopt.h:5-36): n dense QPs of the controller's shape, instance-major:
  *   Q [n][30*30] row-major (lower triangle used, opt.cpp:4962), c [n][30], L [n][nrows*31] row-major,
  *   first neq rows "=", the rest "<=" (lopt.cpp:35-66); x [n][30].  nrows <= 86.
- *   info [n][8] and flops [n] may be NULL. */
+ *   info [n][8] (ncholesky, outer its, QQP calls, working-set size, KKT dimension, flags, Newton factorisations reused, 0)
+ *   and flops [n] may be NULL.  A failed instance (status < 0) returns x = 0. */
 int wbc_qp_solve(wbc_ctx* ctx, int n, const double* Q, const double* c, const double* L, int nrows, int neq, double* x,
                  int* status, int* info, double* flops, void* cuda_stream, unsigned flags);
 
@@ -183,6 +193,10 @@ int wbc_last_timing(wbc_ctx* ctx, float* front_ms, float* solve_ms);
 int wbc_last_solve_cycles(wbc_ctx* ctx, int n, unsigned long long* cycles);
 /* Number of kernels launched by the last wbc_cycle / wbc_qp_solve. */
 int wbc_last_launches(wbc_ctx* ctx);
+/* Launch shape of the persistent solver kernel: resident CTAs (= warps) per SM as the occupancy calculator reports them
+ * for this device, dynamic shared memory per CTA in bytes, and the grid (SMs x resident CTAs).  Any pointer may be NULL.
+ * Measurement only (bench.py reports it beside the roofline); the reference has no counterpart. */
+int wbc_solver_shape(wbc_ctx* ctx, int* ctas_per_sm, int* smem_bytes, int* grid);
 
 /* ---- On-device trajectory sampling -------------------------------------------------------------
  * The reference samples four towr::Spline objects at wall-clock time t on the host every cycle: base_linear_ and

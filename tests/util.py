@@ -45,7 +45,8 @@ class EmuParams(C.Structure):
     _fields_ = [(n, C.c_double) for n in
                 "kcom dcom q1_weight slack_weight mu tau_max joint_dt kp_sw kd_sw g_acc obs_gain obs_dt".split()] + \
                [("gravity", C.c_double * 3), ("qp_epsx", C.c_double), ("qp_rho", C.c_double), ("qp_outerits", C.c_int),
-                ("observer_enabled", C.c_int), ("fix_swing_rhs", C.c_int), ("qp_literal_kkt", C.c_int)]
+                ("observer_enabled", C.c_int), ("fix_swing_rhs", C.c_int), ("qp_literal_kkt", C.c_int),
+                ("hold_tau_on_failure", C.c_int)]
 
 
 class _EmuIO(C.Structure):
@@ -56,7 +57,7 @@ class _EmuIO(C.Structure):
 
 def emu_default_params():
     return EmuParams(2500, 50, 50, 1e8, 0.6, 60, 0.025, 300, 20, 9.81, 10, 0.0025, (C.c_double * 3)(0, 0, -9.8),
-                     1e-2, 1e4, 5, 1, 0, 0)
+                     1e-2, 1e4, 5, 1, 0, 0, 0)
 
 
 class Emu:

@@ -21,3 +21,8 @@ if mode == "dump":
 else:
     ref = np.load(path); bad = [k for k in res if not np.array_equal(res[k], ref[k])]
     print("BIT-IDENTICAL" if not bad else "DIFFERENT: %s" % bad[:6])
+    for k in bad:
+        a, r = np.asarray(res[k], dtype=np.float64), np.asarray(ref[k], dtype=np.float64)
+        d = (a != r) & ~(np.isnan(a) & np.isnan(r))
+        inst = d.any(axis=0) if d.ndim > 1 else d
+        print("  %-28s instances differing %d of %d, max abs diff %.3e" % (k, int(inst.sum()), inst.size, float(np.nanmax(np.abs(a - r)))))

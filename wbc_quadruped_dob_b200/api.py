@@ -39,7 +39,8 @@ class Params(C.Structure):
                 ("kcom", "dcom", "q1_weight", "slack_weight", "mu", "tau_max", "joint_dt", "kp_sw", "kd_sw", "g_acc",
                  "obs_gain", "obs_dt")] + [("gravity", C.c_double * 3), ("qp_epsx", C.c_double), ("qp_rho", C.c_double),
                                            ("qp_outerits", C.c_int), ("observer_enabled", C.c_int),
-                                           ("fix_swing_rhs", C.c_int), ("qp_literal_kkt", C.c_int)]
+                                           ("fix_swing_rhs", C.c_int), ("qp_literal_kkt", C.c_int),
+                                           ("hold_tau_on_failure", C.c_int)]
 
 
 class _Inputs(C.Structure):
@@ -74,7 +75,8 @@ _lib = None
 
 EXPORTS = ["wbc_default_params", "wbc_last_error", "wbc_version", "wbc_create", "wbc_destroy", "wbc_set_params",
            "wbc_set_observer_state", "wbc_get_observer_state", "wbc_cycle", "wbc_debug_update", "wbc_qp_solve",
-           "wbc_plant_step", "wbc_last_timing", "wbc_last_solve_cycles", "wbc_last_launches", "wbc_host_alloc", "wbc_host_free",
+           "wbc_plant_step", "wbc_last_timing", "wbc_last_solve_cycles", "wbc_last_launches", "wbc_solver_shape", "wbc_host_alloc",
+           "wbc_host_free",
            "wbc_set_trajectory", "wbc_sample_trajectory",
            "wbc_measure_dfma_peak"]
 
@@ -89,8 +91,11 @@ def load():
     if _lib is not None:
         return _lib
     path = os.environ.get("WBC_B200_LIB") or _build.LIB          # A/B experiments: a variant build of the same library
-    if path == _build.LIB and not os.path.exists(_build.LIB):
-        _build.build()
+    if path == _build.LIB:
+        # rebuild when the library is missing or older than its sources (a no-op otherwise); on a box without nvcc the
+        # shipped library is used as it is, and a missing one is an error: there is no CPU fallback
+        if _build.have_nvcc() or not os.path.exists(_build.LIB):
+            _build.build()
     lib = C.CDLL(path)
     lib.wbc_default_params.argtypes = [C.POINTER(Params)]
     lib.wbc_last_error.restype = C.c_char_p
@@ -109,6 +114,7 @@ def load():
     lib.wbc_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     lib.wbc_last_solve_cycles.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_ulonglong)]
     lib.wbc_last_launches.argtypes = [C.c_void_p]
+    lib.wbc_solver_shape.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.wbc_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
     lib.wbc_host_free.argtypes = [C.c_void_p]
     lib.wbc_set_trajectory.argtypes = [C.c_void_p, C.c_int, C.POINTER(_Trajectory), C.c_void_p, C.c_uint]
@@ -295,8 +301,23 @@ class WbcBatch:
         _check(self.lib.wbc_cycle(self.h, n, C.byref(ins), C.byref(o), None, HOST_PTRS | (FIFO_DISPATCH if self.fifo_dispatch else 0) | (HOST_SLAB if sc.get("_slab") else 0) | (SAMPLED_TRAJ if sampled_traj else 0)), "wbc_cycle")
         return out
 
-    def cycle_device(self, dev_in, dev_out, n, ld, stream=None, sync=True):
-        """One control cycle on DEVICE-resident SoA buffers (dicts of torch CUDA tensors or raw pointers)."""
+    def cycle_device(self, dev_in, dev_out, n, ld, stream=None, sync=True, out_ld=None):
+        """One control cycle on DEVICE-resident SoA buffers (dicts of torch CUDA tensors or raw pointers).
+        `ld` is the leading dimension of the input arrays, `out_ld` that of the output arrays (default: the outputs' own
+        second dimension when they are tensors, else `ld`)."""
+        if out_ld is None:
+            t = dev_out.get("tau")
+            out_ld = int(t.stride(0)) if hasattr(t, "stride") and t.dim() == 2 else ld
+        # element (k, i) of an array is read or written at k * ld + i: refuse tensors whose row stride is not the leading
+        # dimension they are passed with, or that are narrower than the batch (out-of-bounds accesses otherwise)
+        for d, want_ld in ((dev_in, ld), (dev_out, out_ld)):
+            for k, v in d.items():
+                if hasattr(v, "stride") and hasattr(v, "dim"):
+                    if v.dim() == 2 and (int(v.shape[1]) < n or (int(v.shape[0]) > 1 and int(v.stride(0)) != want_ld)):
+                        raise WbcError("cycle_device: array %r has shape %s / row stride %d, expected >= %d columns and leading dimension %d"
+                                       % (k, tuple(v.shape), int(v.stride(0)), n, want_ld))
+                    if v.dim() == 1 and int(v.shape[0]) < n:
+                        raise WbcError("cycle_device: array %r has %d entries, batch is %d" % (k, int(v.shape[0]), n))
         ins = _Inputs()
         for name, _ in IN_FIELDS:
             setattr(ins, name, _ptr(dev_in.get(name)))
@@ -306,7 +327,7 @@ class WbcBatch:
         o = _Outputs()
         for k in ("tau", "w", "x", "qp_obj", "status", "qp_info", "qp_flops"):
             setattr(o, k, _ptr(dev_out.get(k)))
-        o.ld = ld
+        o.ld = out_ld
         flags = DEVICE_PTRS | (0 if sync else NO_SYNC) | (FIFO_DISPATCH if self.fifo_dispatch else 0)
         _check(self.lib.wbc_cycle(self.h, n, C.byref(ins), C.byref(o), stream, flags), "wbc_cycle")
 
@@ -369,6 +390,12 @@ class WbcBatch:
 
     def last_launches(self):
         return int(self.lib.wbc_last_launches(self.h))
+
+    def solver_shape(self):
+        """(resident solver CTAs per SM, shared-memory bytes per CTA, grid) of the persistent solver kernel."""
+        a, b, g = C.c_int(0), C.c_int(0), C.c_int(0)
+        _check(self.lib.wbc_solver_shape(self.h, C.byref(a), C.byref(b), C.byref(g)), "wbc_solver_shape")
+        return a.value, b.value, g.value
 
     def measure_dfma_peak(self):
         v = C.c_double(0)

@@ -20,6 +20,10 @@ def _nvcc():
     raise RuntimeError("nvcc not found: libwbc_b200.so cannot be built (there is no CPU fallback)")
 
 
+def have_nvcc():
+    return any(c and os.path.exists(c) for c in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"))
+
+
 def stale():
     if not os.path.exists(LIB):
         return True

@@ -8,8 +8,8 @@
 //   * the products with E = [H, CI'; CI, rho I] are straight-line code over the 30 main columns, with
 //     128-bit loads of the vector, four independent accumulation chains, and no predicates on loads (out-of-
 //     range lanes read finite in-bounds values and drop the result);
-//   * the constrained-Newton factorisation handles two columns per step on the packed factor with 128-bit
-//     loads; triangular solves keep the running right-hand side in registers.
+//   * the constrained-Newton factorisation handles two columns per step on a transposed, pair-interleaved factor
+//     (conflict-free 128-bit loads); triangular solves keep the running right-hand side in registers.
 // Included by qp_warp.cuh; uses its layout constants.
 #pragma once
 #if defined(__CUDACC__)
@@ -45,7 +45,7 @@ __device__ __noinline__ double2 symv(const double* __restrict__ x, int nic2, dou
 {
     const int l = threadIdx.x & 31;
     const double* H = wbc_smem + sl::OFF_H + l;             // column walk of row l (H symmetric)
-    const double* Crow = wbc_smem + sl::OFF_CI + l * LDH;   // slack row l
+    const double* Crow = wbc_smem + sl::OFF_CI + (l < NICCAP ? l : NICCAP - 1) * LDH;   // slack row l (lanes past the array: any row, result dropped)
     const double* Ccol = wbc_smem + sl::OFF_CI + l;         // column l of the slack rows
     double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
 #pragma unroll 5
@@ -69,13 +69,18 @@ __device__ __noinline__ double2 symv(const double* __restrict__ x, int nic2, dou
 }
 
 // f_k = exb . t_k + 0.5 t_k . (E t_k) for the four projected points t_k = P(xc + s_k d) (opt.cpp:30582-30652).
-// xc, d, exb in two-slot registers.  Results to V_SPARE[0..3] (shared) -- every lane also returns them in f[].
+// xc, d, exb in two-slot registers.  Results to SP[0..3] (shared).
+// The candidates are broadcast from shared memory, interleaved four to an entry: the 30 main entries overlay the mirrors
+// of x and d (and the head of EXB), the slack entries overlay EXXC -- all four are dead here (x, exb and the point of the
+// extended model live in registers during a QQP call, d is rewritten before its next use); the CALLER restores the mirror of x.
 __device__ __noinline__ void eval4(double xcA, double xcB, double dA, double dB, double exbA, double exbB, int nic, double rho, double s0,
                                   double s1, double s2, double s3)
 {
     const int l = threadIdx.x & 31;
     const int nic2 = (nic + 1) & ~1;
-    double* t4 = wbc_smem + sl::OFF_V + V_T0 * VLS;          // [48][4] interleaved candidates (T0..T3 are contiguous)
+    double* t4m = wbc_smem + sl::OFF_XC;                     // [30][4]
+    double* t4s = wbc_smem + sl::OFF_EXXC;                   // [NICCAP][4]
+    static_assert(NMAIN * 4 <= 3 * 48 && NICCAP * 4 <= 104, "trial points fit the idle arrays");
     const bool vA = l < NMAIN, vB = l < nic;
     double tA[4], tB[4];
     const double s[4] = {s0, s1, s2, s3};
@@ -87,29 +92,30 @@ __device__ __noinline__ void eval4(double xcA, double xcB, double dA, double dB,
         tB[k] = vB ? v : 0.0;
         if (!vA) tA[k] = 0.0;
     }
+    __syncwarp();                                            // every lane is done reading the arrays the candidates overlay
     if (vA) {
-        *reinterpret_cast<double2*>(t4 + l * 4) = make_double2(tA[0], tA[1]);
-        *reinterpret_cast<double2*>(t4 + l * 4 + 2) = make_double2(tA[2], tA[3]);
+        *reinterpret_cast<double2*>(t4m + l * 4) = make_double2(tA[0], tA[1]);
+        *reinterpret_cast<double2*>(t4m + l * 4 + 2) = make_double2(tA[2], tA[3]);
     }
     if (l < nic2) {      // includes the zero pad entry when nic is odd
-        *reinterpret_cast<double2*>(t4 + (NMAIN + l) * 4) = make_double2(tB[0], tB[1]);
-        *reinterpret_cast<double2*>(t4 + (NMAIN + l) * 4 + 2) = make_double2(tB[2], tB[3]);
+        *reinterpret_cast<double2*>(t4s + l * 4) = make_double2(tB[0], tB[1]);
+        *reinterpret_cast<double2*>(t4s + l * 4 + 2) = make_double2(tB[2], tB[3]);
     }
     __syncwarp();
     const double* H = wbc_smem + sl::OFF_H + l;
-    const double* Crow = wbc_smem + sl::OFF_CI + l * LDH;
+    const double* Crow = wbc_smem + sl::OFF_CI + (l < NICCAP ? l : NICCAP - 1) * LDH;
     const double* Ccol = wbc_smem + sl::OFF_CI + l;
     double a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
 #pragma unroll 1
     for (int j = 0; j < NMAIN; j++) {
-        const double2 t01 = ld2(t4 + j * 4), t23 = ld2(t4 + j * 4 + 2);
+        const double2 t01 = ld2(t4m + j * 4), t23 = ld2(t4m + j * 4 + 2);
         const double h = H[j * LDH], c = Crow[j];
         a[0] += h * t01.x; a[1] += h * t01.y; a[2] += h * t23.x; a[3] += h * t23.y;
         b[0] += c * t01.x; b[1] += c * t01.y; b[2] += c * t23.x; b[3] += c * t23.y;
     }
 #pragma unroll 1
     for (int k = 0; k < nic2; k++) {
-        const double2 t01 = ld2(t4 + (NMAIN + k) * 4), t23 = ld2(t4 + (NMAIN + k) * 4 + 2);
+        const double2 t01 = ld2(t4s + k * 4), t23 = ld2(t4s + k * 4 + 2);
         const double c = Ccol[k * LDH];
         a[0] += c * t01.x; a[1] += c * t01.y; a[2] += c * t23.x; a[3] += c * t23.y;
     }
@@ -127,7 +133,7 @@ __device__ __noinline__ void eval4(double xcA, double xcB, double dA, double dB,
     }
     __syncwarp();
     if (l == 0) {
-        double* f = wbc_smem + sl::OFF_V + V_SPARE * VLS;
+        double* f = wbc_smem + sl::OFF_SP;
         f[0] = r8[0] + 0.5 * r8[4]; f[1] = r8[1] + 0.5 * r8[5]; f[2] = r8[2] + 0.5 * r8[6]; f[3] = r8[3] + 0.5 * r8[7];
     }
     __syncwarp();
@@ -141,52 +147,56 @@ __device__ __noinline__ void eval4(double xcA, double xcB, double dA, double dB,
 //     M = Hreg - T'T = U'U
 // is factored densely.  Same matrix, same solution of E_FF d = -g up to rounding; a third of the flops of the
 // (30 + nic)^3/3 factorisation, every row owned by exactly one lane, and no dependence on nic in the code shape.
-//   * T [nic][32] lives behind the packed 30 x 30 factor in the Z array (rows of fixed variables are not used);
+//   * T is not stored: its entries T_ik = CI_ik / sqrt(d_i) are formed where they are used from CI and the vector RS of
+//     1/sqrt(d_i) (shared memory is what limits the resident warps, and T would be a fifth of it);
 //   * fixing slack k after the build (qqpsolver_cnewtonupdate, opt.cpp:31314-31426) turns row/column k of E_FF into
 //     the identity, i.e. M <- M + T_k T_k': a rank-one update of U;
 //   * the Newton direction:  dx = M^-1 (-g_x + B' D^-1 g_s),  ds = -D^-1 (g_s + B dx).
-constexpr int OFF_T = 464;      // offset of T in the Z array (zoff(30) = 450, 16-byte aligned rows of 32)
-static_assert(OFF_T + NICCAP * 32 <= 1152, "T fits behind the 30 x 30 factor");
+//
+// Storage of the factor Z = U' (lower triangular, row c = lane c's row): TRANSPOSED AND PAIR-INTERLEAVED.  Pair-row p
+// holds, for every c >= 2p, the two entries (Z[c][2p], Z[c][2p+1]) as one 16-byte word at
+//     zt_base(p) + 2 (c - 2p),      zt_base(p) = 62 p - 2 p^2      (30 - 2p words per pair-row, 480 doubles in all).
+// For a fixed column pair the 30 lanes read consecutive words (conflict-free 128-bit loads: the factorisation's dot
+// products, the forward sweep); the words of rows 2p and 2p+1 sit at the head of pair-row p, where the slots on and above
+// the diagonal carry the reciprocal diagonal:  head = [1/Z[2p][2p], -, Z[2p+1][2p], 1/Z[2p+1][2p+1]].
+// The diagonal itself (used by the rank-one update only) is the vector ZD.
+__device__ __forceinline__ int zt_base(int p) { return (62 - 2 * p) * p; }
+static_assert(sl::Z_DOUBLES >= 480, "pair-interleaved 30 x 30 factor");
 
-// rsB: 1/sqrt(d_k) of slack lane k (free variables only); diagA: regularised diagonal of main variable `lane`.
+// rsB: 1/sqrt(d_k) of slack lane k (0 when the variable is not free); diagA: regularised diagonal of main variable `lane`.
 // Returns false on a non-positive pivot.
 __device__ __noinline__ bool chol_build30(double diagA, double rsB, unsigned fmask)
 {
     const int l = threadIdx.x & 31;
     double* Z = wbc_smem + sl::OFF_Z;
-    double* T = Z + OFF_T;
-    double* zd = wbc_smem + sl::OFF_V + V_ZD * VLS;
-    double* zrinv = wbc_smem + sl::OFF_V + V_ZRINV * VLS;
+    double* zd = wbc_smem + sl::OFF_ZD;
+    double* rs = wbc_smem + sl::OFF_RS;
     const double* H = wbc_smem + sl::OFF_H + l;             // column l (H symmetric); lanes 30, 31 read finite in-bounds values
-    const double* CI = wbc_smem + sl::OFF_CI + l;
-#pragma unroll 1
-    for (unsigned m = fmask; m; m &= m - 1u) {
-        const int k = __ffs((int)m) - 1;
-        const double rs = bshfl(rsB, k);
-        T[k * 32 + l] = (l < NMAIN) ? CI[k * LDH] * rs : 0.0;
-    }
+    const double* CIb = wbc_smem + sl::OFF_CI;
+    const double* CIc = CIb + l;
+    if (l < NICCAP) rs[l] = rsB;
     __syncwarp();
     const int c = l;
-    double* r0 = Z + zoff(c < NMAIN ? c : NMAIN - 1);
-    const double* Tc = T + l;
 #pragma unroll 1
     for (int k = 0; k < NMAIN; k += 2) {
-        const double* rk = Z + zoff(k);
-        const double* rk1 = Z + zoff(k + 1);
+        // dot products of row c with rows k and k + 1 over the finished columns, one pair-row per step
         double p0 = 0.0, q0 = 0.0, p1 = 0.0, q1 = 0.0;
+        double* zq = Z;                                      // zq + 2 r = the word of row r in pair-row q:  Z + zt_base(q) - 4 q
 #pragma unroll 1
-        for (int m = 0; m < k; m += 2) {
-            const double2 zk = ld2(rk + m), zk1 = ld2(rk1 + m), z0 = ld2(r0 + m);
+        for (int q = 0; 2 * q < k; q++) {
+            const double2 z0 = ld2(zq + 2 * c), zk = ld2(zq + 2 * k), zk1 = ld2(zq + 2 * k + 2);
             p0 += z0.x * zk.x; q0 += z0.y * zk.y;
             p1 += z0.x * zk1.x; q1 += z0.y * zk1.y;
+            zq += 56 - 4 * q;                                // zt_base(q + 1) - 4 (q + 1) - (zt_base(q) - 4 q)
         }
         double s0 = 0.0, s1 = 0.0;
 #pragma unroll 1
         for (unsigned m = fmask; m; m &= m - 1u) {
             const int i = __ffs((int)m) - 1;
-            const double tc = Tc[i * 32];
-            const double2 tk = ld2(T + i * 32 + k);
-            s0 += tc * tk.x; s1 += tc * tk.y;
+            const double r = rs[i];
+            const double tc = CIc[i * LDH] * r;              // T_ic, T_ik, T_i,k+1
+            const double tk0 = CIb[i * LDH + k] * r, tk1 = CIb[i * LDH + k + 1] * r;
+            s0 += tc * tk0; s1 += tc * tk1;
         }
         double v0 = ((c == k) ? diagA : H[k * LDH]) - s0 - (p0 + q0);
         double v1 = ((c == k + 1) ? diagA : H[(k + 1) * LDH]) - s1 - (p1 + q1);
@@ -197,23 +207,25 @@ __device__ __noinline__ bool chol_build30(double diagA, double rsB, unsigned fma
         if (!(piv0 > 0.0)) return false;
         const double ri0 = rsqrt(piv0);
         const double z0k = v0 * ri0;
-        if (c > k && c < NMAIN) r0[k] = z0k;
         const double zk1k = v0n * ri0;
         v1 -= z0k * zk1k;
         const double piv1 = v1n - zk1k * zk1k;
         if (!(piv1 > 0.0)) return false;
         const double ri1 = rsqrt(piv1);
-        if (c > k + 1 && c < NMAIN) r0[k + 1] = v1 * ri1;
-        if (l == 0) {
-            *reinterpret_cast<double2*>(zd + k) = make_double2(piv0 * ri0, piv1 * ri1);
-            *reinterpret_cast<double2*>(zrinv + k) = make_double2(ri0, ri1);
+        // lane c writes its word of pair-row k/2: rows k and k + 1 put the reciprocal pivots on their diagonal slots
+        if (c >= k && c < NMAIN) {
+            double2 wv;
+            wv.x = (c == k) ? ri0 : z0k;
+            wv.y = (c == k) ? 0.0 : ((c == k + 1) ? ri1 : v1 * ri1);
+            *reinterpret_cast<double2*>(zq + 2 * c) = wv;   // zq has arrived at pair-row k/2
         }
+        if (l == 0) *reinterpret_cast<double2*>(zd + k) = make_double2(piv0 * ri0, piv1 * ri1);
         __syncwarp();
     }
     return true;
 }
 
-// Solve U'U x = rhs (30 x 30 packed factor); rhs and result in shared memory at x[0..30).
+// Solve U'U x = rhs (30 x 30 factor); rhs and result in shared memory at x[0..30).
 // Two columns per step: both pivot components are broadcast at once and the second one is finished redundantly by every
 // lane (y_{k+1} = (x_{k+1} - U_{k,k+1} y_k) / U_{k+1,k+1}), so the dependent chain is one shuffle per two columns instead
 // of one per column.  The operations on every component are the ones of the one-column sweep, in the same order.
@@ -221,30 +233,39 @@ __device__ __noinline__ void tri_solve30(double* x)
 {
     const int l = threadIdx.x & 31;
     const double* Z = wbc_smem + sl::OFF_Z;
-    const double* zrinv = wbc_smem + sl::OFF_V + V_ZRINV * VLS;
-    const double* r0 = Z + zoff(l < NMAIN ? l : NMAIN - 1);
+    const int ql = (l < NMAIN ? l : NMAIN - 1) >> 1, lo = l & 1;
+    const double zri = Z[zt_base(ql) + 3 * lo];             // 1 / diagonal of this lane's row
     double x0 = x[l];                                       // lanes 30, 31 carry finite values that are never broadcast
+    {
+        const double* hd = Z;                               // head of pair-row k/2
 #pragma unroll 1
-    for (int k = 0; k < NMAIN; k += 2) {                    // forward: U' y = rhs, column oriented
-        const double2 zr = ld2(zrinv + k);
-        const double c = Z[zoff(k + 1) + k];                // U_{k,k+1}
-        const double yk = bshfl(x0, k) * zr.x;
-        const double yk1 = (bshfl(x0, k + 1) - c * yk) * zr.y;
-        if (l > k) x0 -= r0[k] * yk;
-        if (l > k + 1) x0 -= r0[k + 1] * yk1;
+        for (int k = 0; k < NMAIN; k += 2) {                // forward: U' y = rhs, column oriented
+            const double2 h0 = ld2(hd), h1 = ld2(hd + 2);   // (1/U_kk, -), (U_{k,k+1}, 1/U_{k+1,k+1})
+            const double2 zz = ld2(hd + 2 * (l - k));       // this lane's entries of columns k, k + 1 (lanes < k: finite, unused)
+            const double yk = bshfl(x0, k) * h0.x;
+            const double yk1 = (bshfl(x0, k + 1) - h1.x * yk) * h1.y;
+            if (l > k) x0 -= zz.x * yk;
+            if (l > k + 1) x0 -= zz.y * yk1;
+            hd += 60 - 2 * k;                               // zt_base(p + 1) - zt_base(p) = 60 - 4 p
+        }
     }
-    x0 *= zrinv[l < NMAIN ? l : 0];
+    x0 *= zri;
+    {
+        // backward: U x = y.  Column k of U is row k of Z: lane l needs Z[k][l] = word of row k in pair-row l/2, entry l & 1
+        const double* own = Z + zt_base(ql) - 4 * ql + lo;  // own[2 r] = Z[r][l]
+        const double* hd = Z + zt_base(NMAIN / 2 - 1);
 #pragma unroll 1
-    for (int k = NMAIN - 1; k > 0; k -= 2) {                // backward: U x = y
-        const double2 zr = ld2(zrinv + k - 1);
-        const double* rk = Z + zoff(k);
-        const double c = rk[k - 1];                         // U_{k-1,k}
-        const double xk = bshfl(x0, k) * zr.y;
-        const double xk1 = (bshfl(x0, k - 1) - c * xk) * zr.x;
-        if (l < k) x0 -= rk[l] * xk;
-        if (l < k - 1) x0 -= Z[zoff(k - 1) + l] * xk1;
+        for (int k = NMAIN - 1; k > 0; k -= 2) {
+            const double2 h0 = ld2(hd), h1 = ld2(hd + 2);   // (1/U_{k-1,k-1}, -), (U_{k-1,k}, 1/U_kk)
+            const double zk = own[2 * k], zk1 = own[2 * k - 2];
+            const double xk = bshfl(x0, k) * h1.y;
+            const double xk1 = (bshfl(x0, k - 1) - h1.x * xk) * h0.x;
+            if (l < k) x0 -= zk * xk;
+            if (l < k - 1) x0 -= zk1 * xk1;
+            hd -= 66 - 2 * k;                               // zt_base(p) - zt_base(p - 1) = 64 - 4 p,  p = (k - 1) / 2
+        }
     }
-    x0 *= zrinv[l < NMAIN ? l : 0];
+    x0 *= zri;
     __syncwarp();
     if (l < NMAIN) x[l] = x0;
     __syncwarp();
@@ -255,28 +276,30 @@ __device__ __noinline__ void rank1_fix30(int k)
 {
     const int l = threadIdx.x & 31;
     double* Z = wbc_smem + sl::OFF_Z;
-    double* zd = wbc_smem + sl::OFF_V + V_ZD * VLS;
-    double* zrinv = wbc_smem + sl::OFF_V + V_ZRINV * VLS;
-    double x = (l < NMAIN) ? Z[OFF_T + k * 32 + l] : 0.0;
+    double* zd = wbc_smem + sl::OFF_ZD;
+    double x = (l < NMAIN) ? wbc_smem[sl::OFF_CI + k * LDH + l] * wbc_smem[sl::OFF_RS + k] : 0.0;      // T_k
     const unsigned nz = __ballot_sync(FULL, x != 0.0);
     if (nz == 0u) return;
-    double* r0 = Z + zoff(l < NMAIN ? l : NMAIN - 1);
+    double* own = Z + 2 * (l < NMAIN ? l : NMAIN - 1);      // own[zt_base(q) - 4 q + (j & 1)] = Z[l][j],  q = j / 2
 #pragma unroll 1
     for (int j = __ffs((int)nz) - 1; j < NMAIN; j++) {
         const double xj = bshfl(x, j);
         if (xj == 0.0) continue;
-        const double ljj = zd[j], zri = zrinv[j];
+        const int q = j >> 1;
+        const int e = (58 - 2 * q) * q + (j & 1);
+        double* dslot = Z + zt_base(q) + 3 * (j & 1);       // 1 / Z[j][j]
+        const double ljj = zd[j], zri = *dslot;
         const double rr = ljj * ljj + xj * xj;
         const double rinv = rsqrt(rr);
         const double r = rr * rinv;
         const double s = xj * zri, ci = ljj * rinv, cc = r * zri;
         if (l > j && l < NMAIN) {
-            const double lcj = (r0[j] + s * x) * ci;
+            const double lcj = (own[e] + s * x) * ci;
             x = cc * x - s * lcj;
-            r0[j] = lcj;
+            own[e] = lcj;
         }
         __syncwarp();
-        if (l == 0) { zd[j] = r; zrinv[j] = rinv; }
+        if (l == 0) { zd[j] = r; *dslot = rinv; }
     }
     __syncwarp();
 }
@@ -286,7 +309,7 @@ __device__ __noinline__ void rank1_fix30(int k)
 __device__ __noinline__ void newton_direction(double gA, double gB, double winvB, unsigned freemask, int nic)
 {
     const int l = threadIdx.x & 31;
-    double* sdc = wbc_smem + sl::OFF_V + V_DC * VLS;
+    double* sdc = wbc_smem + sl::OFF_DC;
     const double* CIc = wbc_smem + sl::OFF_CI + l;
     const double u = gB * winvB;
     double r = -gA;
@@ -328,12 +351,12 @@ __device__ __forceinline__ double red1(double a)
     return a;
 }
 
-// qqpsolver_quadraticmodel (opt.cpp:30753-30821) on two-slot registers.  d is mirrored at V_DC.  Returns the packed sign
-// estimates (see estimateparabolicmodel); d1, d2 are left in V_SPARE[4..5].
+// qqpsolver_quadraticmodel (opt.cpp:30753-30821) on two-slot registers.  d is mirrored at DC.  Returns the packed sign
+// estimates (see estimateparabolicmodel); d1, d2 are left in SP[4..5].
 __device__ __noinline__ int quadratic_model(double dA, double dB, double gA, double gB, double xcA, double xcB, int nic2, double rho,
                                             double absasum, double absasum2, double mb)
 {
-    const double2 ed = symv(wbc_smem + sl::OFF_V + V_DC * VLS, nic2, rho);
+    const double2 ed = symv(wbc_smem + sl::OFF_DC, nic2, rho);
     double s0 = dA * ed.x + dB * ed.y;       // invalid lanes carry d = 0
     double s1 = dA * gA + dB * gB;
 #pragma unroll 1
@@ -344,15 +367,15 @@ __device__ __noinline__ int quadratic_model(double dA, double dB, double gA, dou
     const double m0 = wmax_nn(fmax(fabs(xcA), fabs(xcB))), m1 = wmax_nn(fmax(fabs(dA), fabs(dB)));
     const double d2 = 0.5 * s0, d1 = s1;
     if ((threadIdx.x & 31) == 0) {
-        wbc_smem[sl::OFF_V + V_SPARE * VLS + 4] = d1;
-        wbc_smem[sl::OFF_V + V_SPARE * VLS + 5] = d2;
+        wbc_smem[sl::OFF_SP + 4] = d1;
+        wbc_smem[sl::OFF_SP + 5] = d2;
     }
     __syncwarp();
     return estimateparabolicmodel(absasum, absasum2, m0, mb, m1, d1, d2);
 }
 
 // sasexploredirection (opt.cpp:27433-27528) on slot B registers (see sas_explore_direction in qp_warp.cuh).
-// Returns cidx (-1: no blocking bound); the step is left in V_SPARE[6].
+// Returns cidx (-1: no blocking bound); the step is left in SP[6].
 __device__ __noinline__ int explore(double xcB, double dB, int candB)
 {
     const int l = threadIdx.x & 31;
@@ -371,21 +394,22 @@ __device__ __noinline__ int explore(double xcB, double dB, int candB)
     const unsigned ml = __reduce_min_sync(FULL, hi == mh ? lo : 0xffffffffu);
     const unsigned bi = __reduce_min_sync(FULL, (hi == mh && lo == ml) ? (unsigned)(NMAIN + l) : 0x7fffffffu);
     const double bestall = __hiloint2double((int)mh, (int)ml);
-    if (l == 0) wbc_smem[sl::OFF_V + V_SPARE * VLS + 6] = bestall;
+    if (l == 0) wbc_smem[sl::OFF_SP + 6] = bestall;
     __syncwarp();
     return (bestall < BIGSTEP) ? (int)bi : -1;
 }
 
 // Step selection after the quadratic model (opt.cpp:30259-30302 / 30440-30487), qqpsolver_findbeststepandmove
 // (30882-31003) and sasmoveto (27574-27723) on two-slot registers; xc is read from and written back to its shared
-// mirror V_XC.  mode 0: d2est > 0 (full step unless a bound blocks); 1: non-positive curvature in the CG phase
+// mirror XC.  mode 0: d2est > 0 (full step unless a bound blocks); 1: non-positive curvature in the CG phase
 // (step to the bound); 2: the Newton phase's bound step with candidates {4 stpmax, 1, 0.25}.
-// Returns the new cstatus of slot B; *evals (register, uniform) gets the number of extra model evaluations.
+// Returns the new cstatus of slot B; SP[7] gets the number of extra model evaluations.  (The trial points of eval4 overlay
+// the mirror of x, which is read before and rewritten after.)
 __device__ __noinline__ int step_and_move(double dA, double dB, double exbA, double exbB, int nic, double rho, int mode, int cidx, int csB)
 {
     const int l = threadIdx.x & 31;
-    double* xs = wbc_smem + sl::OFF_V + V_XC * VLS;
-    const double* sp = wbc_smem + sl::OFF_V + V_SPARE * VLS;
+    double* xs = wbc_smem + sl::OFF_XC;
+    const double* sp = wbc_smem + sl::OFF_SP;
     const double d1 = sp[4], d2 = sp[5], stpmax = sp[6];
     double xcA = xs[l], xcB = (l < nic) ? xs[NMAIN + l] : 0.0;
     double stp, a0 = 0.0, a1 = 0.0, a2 = 0.0;
@@ -421,13 +445,13 @@ __device__ __noinline__ int step_and_move(double dA, double dB, double exbA, dou
     }
     if (l < NMAIN) xs[l] = xcA;
     if (l < ((nic + 1) & ~1)) xs[NMAIN + l] = xcB;
-    if (l == 0) wbc_smem[sl::OFF_V + V_SPARE * VLS + 7] = (double)addcnt;
+    if (l == 0) wbc_smem[sl::OFF_SP + 7] = (double)addcnt;
     __syncwarp();
     return csB;
 }
 
 // |A| statistics of E (opt.cpp:29893-29915, with its k = (i==v ? 1 : 2) quirk) over the upper triangle, and max|exb|.
-// Results in V_SPARE[8..10].
+// Results in SP[8..10].
 __device__ __noinline__ void qqp_stats(int nic, double rho, double exbA, double exbB)
 {
     const int l = threadIdx.x & 31;
@@ -456,7 +480,7 @@ __device__ __noinline__ void qqp_stats(int nic, double rho, double exbA, double 
     s1 = wsum(s1); s2 = wsum(s2);
     const double m1 = wmax_nn(fmax(fabs(exbA), fabs(exbB)));
     if (l == 0) {
-        double* sp = wbc_smem + sl::OFF_V + V_SPARE * VLS;
+        double* sp = wbc_smem + sl::OFF_SP;
         sp[8] = s1; sp[9] = s2; sp[10] = m1;
     }
     __syncwarp();
@@ -506,9 +530,9 @@ __device__ __noinline__ int qqp_optimize_fast(const Work w, int nic, double rho,
     unsigned fac_mask = 0u;
     double winvB = 0.0;
     int nschur = 0, nfix = 0;           // slack rows folded into Schur complements / solves, rank-one fixes (flop count)
-    double* sxc = wbc_smem + sl::OFF_V + V_XC * VLS;
-    double* sdc = wbc_smem + sl::OFF_V + V_DC * VLS;
-    const double* spare = wbc_smem + sl::OFF_V + V_SPARE * VLS;
+    double* sxc = wbc_smem + sl::OFF_XC;
+    double* sdc = wbc_smem + sl::OFF_DC;
+    const double* spare = wbc_smem + sl::OFF_SP;
     const double* exb = wbc_smem + sl::OFF_EXB;
     double* exxc = wbc_smem + sl::OFF_EXXC;
     // settings: qqploaddefaults (opt.cpp:29533-29547) + overrides (41318-41323)
@@ -655,6 +679,9 @@ __device__ __noinline__ int qqp_optimize_fast(const Work w, int nic, double rho,
                 // f(x) vs f(x + stpmax d) (30493-30503)
                 eval4(xcA, xcB, dA, dB, exbA, exbB, nic, rho, 0.0, stpmax, stpmax, stpmax);
                 const double2 f01 = ld2(spare);
+                if (vA) sxc[l] = xcA;                   // the trial points overlay the mirror of x: put it back
+                if (l < nic2) sxc[NMAIN + l] = xcB;
+                __syncwarp();
                 if (f01.y >= f01.x) { cgmax = cgmaxits; break; }
                 csB = step_and_move(dA, dB, exbA, exbB, nic, rho, 2, cidx, csB);
                 nsymv += 6;

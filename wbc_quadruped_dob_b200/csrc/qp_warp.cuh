@@ -5,7 +5,7 @@
 // 5 outer iterations, cold start, no box constraints on x).  "opt.cpp" = the reference's
 // dogbot_controller/src/alglib/optimization.cpp, "linalg.cpp" likewise.
 //
-// Execution model: ONE WARP PER QP, one warp per CTA, ~33 KB of shared memory per warp (6 resident
+// Execution model: ONE WARP PER QP, one warp per CTA, 18.3 KB of shared memory per warp (12 resident
 // per SM).  The design is driven by what ncu showed on the earlier CTA-per-instance version (profiles/):
 // the path is bound by instruction issue and instruction fetch, not by the FP64 pipe or by memory --
 // so every uniform scalar decision is executed once (one warp), there are no block barriers or
@@ -19,15 +19,18 @@
 //   * dense A, no sparse constraints, x unbounded, start point 0, origin 0;
 //   * hence in QQP the only bounds are "slack >= 0" on variables i >= NMAIN.
 //
-// Storage (shared memory is the occupancy limiter):
+// Storage (shared memory is the occupancy limiter: 18.3 KB per warp -> 12 resident warps per SM):
 //   * the QQP quadratic term E = [H, rho Ci'; rho Ci, rho I] is never formed: H = A + rho C'C (30 x 30,
 //     full symmetric, ld 31) and CI = rho * (working inequality rows) (nic x 30, ld 31) are kept and the
 //     products with E use the block structure (same number of multiply-adds as the dense n x n form);
-//   * the Cholesky factor of the constrained-Newton phase is a packed lower triangle (rows padded to even
-//     length so that pairs load as 128-bit words);
+//   * the Cholesky factor of the constrained-Newton phase is the 30 x 30 Schur complement only (qp_fast.cuh),
+//     stored transposed and pair-interleaved so that every access of the factorisation and of the forward
+//     sweep is a conflict-free 128-bit load;
 //   * the constraint matrix C (88 x 31) lives in the warp's global scratch (L2-resident) and is staged
 //     through shared memory where it is used densely;
-//   * the same shared arrays are the workspace of the set-up and of the multiplier update;
+//   * the same shared arrays are the workspace of the set-up and of the multiplier update, and the arrays that
+//     are idle inside the QQP iteration (exb, exxc, the mirrors of x and d) carry the four trial points of the
+//     line search;
 //   * instances whose working set outgrows NICCAP switch CI, the factor and the QQP vectors to a
 //     global-memory spill copy (same code, SPILL = true instantiation).
 #pragma once
@@ -58,46 +61,69 @@ constexpr int VLS = 48, VLG = 104;     // vector length: shared / spill copy
 constexpr double MACHEPS = 5.0e-16;    // ae_machineepsilon (ap.cpp: 5E-16, NOT DBL_EPSILON)
 constexpr double BIGSTEP = 1.0e50;     // opt.cpp:27458
 
-// packed lower triangle, row c holds entries (c, k), k < c, padded to an even count
-WBC_HD int zoff(int c) { return ((c * (c - 1)) >> 1) + (c >> 1); }
+// packed lower triangle, row c holds entries (c, k), k < c.  No padding: consecutive rows start at consecutive triangular
+// numbers, which are distinct modulo 16 over (almost) any 16 consecutive rows -- a lane-per-row access is conflict free.
+WBC_HD int zoff(int c) { return (c * (c - 1)) >> 1; }
 
-// ---- shared-memory layout of one warp (doubles).  The QQP vector block comes last: the device keeps only the
-// NVEC_SM vectors its register-resident QQP (qp_fast.cuh) mirrors to memory; the generic QQP (host emulation, and the
-// device's spill mode, which uses the global copy) needs all NVEC.
-#if defined(__CUDACC__)
-constexpr int NVEC_SM = 9;
-#else
-constexpr int NVEC_SM = NVEC;
-#endif
+// ---- shared-memory layout of one warp (doubles).  Order matters:
+//   [H | Z | ZD | XC | DC | EXB | SP | RS]  is one contiguous workspace (sl::BIG doubles) for the multiplier update;
+//   [Z .. RS | CI]                          is the staging area for rows of C: generate_ex_model places the working rows so
+//                                           that the inequality rows land in CI itself (scaled by rho in place);
+//   [XC | DC | EXB] and EXXC                carry the four trial points of the QQP line search (qp_fast.cuh, eval4), which
+//                                           never needs them at the same time: exb and exxc live in registers inside a
+//                                           QQP call, the mirrors of x and d are rewritten after every line search.
+// The host emulation (one lane, generic QQP) needs the full set of QQP vectors and a factor of the whole (30 + NICCAP)-
+// dimensional Newton model; they are appended behind the device layout.
 namespace sl {
-constexpr int OFF_H = 0;                               // [30][31]
-constexpr int OFF_CI = OFF_H + NMAIN * LDH;            // [18][31]
-constexpr int OFF_Z = OFF_CI + NICCAP * LDH;           // packed, zoff(48) = 1152
-constexpr int BIG = OFF_Z + 1152;                      // H | CI | Z double as one 2640-double workspace
-constexpr int OFF_LARINV = BIG;
-constexpr int OFF_EXXC = OFF_LARINV + 32;
-constexpr int OFF_EXB = OFF_EXXC + 104;
-constexpr int OFF_XS = OFF_EXB + 104;
-constexpr int OFF_INT = OFF_XS + 32;                   // ints: cstatus[104] isfree[104] iscr[8]
-constexpr int OFF_V = OFF_INT + (104 + 104 + 8) / 2;   // [NVEC_SM][48]
-constexpr int TOTAL = OFF_V + NVEC_SM * VLS;
+#if defined(__CUDACC__)
+constexpr int Z_DOUBLES = 480;                          // fast path: pair-interleaved transposed 30 x 30 factor (qp_fast.cuh)
+#else
+constexpr int Z_DOUBLES = 1152;                         // generic path: packed factor, zoff(48) = 1128
+#endif
+constexpr int OFF_H = 0;                                // [30][31]
+constexpr int OFF_Z = OFF_H + NMAIN * LDH;              // factor of the Newton model; packed factor of A during set-up
+constexpr int OFF_ZD = OFF_Z + Z_DOUBLES;               // [32] diagonal of the Newton factor (fast path)
+constexpr int OFF_XC = OFF_ZD + 32;                     // [48] mirror of the QQP point; at the end of a solve: the result x
+constexpr int OFF_DC = OFF_XC + 48;                     // [48] mirror of the QQP direction
+constexpr int OFF_EXB = OFF_DC + 48;                    // [48] linear term of the extended model (shared-memory case)
+constexpr int OFF_SP = OFF_EXB + 48;                    // [16] scalars handed between the QQP routines
+constexpr int OFF_RS = OFF_SP + 16;                     // [20] 1/sqrt(d_k) of the free slack variables (fast path)
+constexpr int OFF_CI = OFF_RS + 20;                     // [18][31]
+constexpr int OFF_EXXC = OFF_CI + NICCAP * LDH;         // [104] point of the extended model
+constexpr int OFF_INT = OFF_EXXC + 104;                 // ints: iscr[8]
+constexpr int TOTAL_DEV = OFF_INT + 4;
+constexpr int BIG = OFF_CI;                             // contiguous workspace in front of CI
+constexpr int STAGE0 = OFF_Z;                           // staging area for rows of C: [STAGE0, OFF_EXXC)
+constexpr int STAGE_EQ_CAP = OFF_CI - STAGE0;           // room for the equality rows in front of CI
+constexpr int STAGE_CAP = OFF_EXXC - STAGE0;
+#if defined(__CUDACC__)
+constexpr int TOTAL = TOTAL_DEV;
+#else
+constexpr int OFF_V = TOTAL_DEV;                        // [NVEC][48] QQP vectors of the generic path
+constexpr int TOTAL = OFF_V + NVEC * VLS;
+#endif
 constexpr int BYTES = TOTAL * 8;
-static_assert(BIG == 2640, "workspace size");
-static_assert(OFF_V % 2 == 0 && OFF_Z % 2 == 0, "16-byte alignment of the vector block and the factor");
+static_assert(OFF_Z % 2 == 0 && OFF_ZD % 2 == 0 && OFF_XC % 2 == 0 && OFF_EXXC % 2 == 0 && OFF_SP % 2 == 0, "16-byte alignment of the arrays read with 128-bit loads");
+#if defined(__CUDACC__)
+static_assert(12 * (BYTES + 1024) <= 228 * 1024, "12 resident solver warps per SM");
+#endif
 }  // namespace sl
 // ---- global scratch layout of one warp (doubles)
 namespace gl {
 constexpr int NQMAX = MAXNT + MAXK;
 constexpr long OFF_C = 0;                                        // [88][31]
 constexpr long OFF_A = OFF_C + MAXK * LDH;                       // [30][31] scaled A, full symmetric
-constexpr long OFF_LA = OFF_A + 944;                             // packed factor of A (transposed: row c = U[.][c]), zoff(30) = 450
-constexpr long OFF_B = OFF_LA + 464;                             // [32] scaled linear term
+constexpr long OFF_LA = OFF_A + 944;                             // packed factor of A (transposed: row c = U[.][c]), zoff(30) = 435, then
+constexpr int LA_DOUBLES = 436;                                  //   its reciprocal diagonal [32] at OFF_LA + LA_DOUBLES (one copy fetches both)
+constexpr long OFF_B = OFF_LA + 480;                             // [32] scaled linear term
 constexpr long OFF_SC = OFF_B + 32;                              // [32] variable scales
 constexpr long OFF_NICERR = OFF_SC + 32;                         // [72]
 constexpr long OFF_NULC = OFF_NICERR + MAXNIC;                   // [88]
 constexpr long OFF_NULCEST = OFF_NULC + MAXK;                    // [88]
 constexpr long OFF_NICNACT = OFF_NULCEST + MAXK;                 // [72] ints
-constexpr long OFF_CI = OFF_NICNACT + 40;                        // spill [72][31]
+constexpr long OFF_CSTAT = OFF_NICNACT + 40;                     // ints: cstatus[104] | isfree[104] of the generic QQP
+constexpr long OFF_EXBG = OFF_CSTAT + 104;                       // spill [104] linear term of the extended model
+constexpr long OFF_CI = OFF_EXBG + 104;                          // spill [72][31]
 constexpr long OFF_Z = OFF_CI + MAXNIC * LDH + 8;                // spill packed, zoff(102) = 5202
 constexpr long OFF_V = OFF_Z + 5216;                             // spill [16][104]
 constexpr long OFF_QRV = OFF_V + NVEC * VLG;
@@ -136,31 +162,42 @@ extern __shared__ __align__(16) double wbc_smem[];
 #define SM_(w, off) (WBC_SM(w) + (off))
 #define W_H(w) SM_(w, sl::OFF_H)
 #define W_BIG(w) SM_(w, 0)
-#define W_VEC(w) SM_(w, sl::OFF_V)
 #define W_B(w) ((w).g + gl::OFF_B)
 #define W_SC(w) ((w).g + gl::OFF_SC)
-#define W_LARINV(w) SM_(w, sl::OFF_LARINV)
+#define W_LARINV(w) ((w).g + gl::OFF_LA + gl::LA_DOUBLES)
 #define W_NICERR(w) ((w).g + gl::OFF_NICERR)
 #define W_NULC(w) ((w).g + gl::OFF_NULC)
 #define W_NULCEST(w) ((w).g + gl::OFF_NULCEST)
 #define W_EXXC(w) SM_(w, sl::OFF_EXXC)
 #define W_EXB(w) SM_(w, sl::OFF_EXB)
-#define W_XS(w) SM_(w, sl::OFF_XS)
+#define W_XS(w) SM_(w, sl::OFF_XC)
+#define W_SPARE(w) SM_(w, sl::OFF_SP)
 #define W_NICNACT(w) (reinterpret_cast<int*>((w).g + gl::OFF_NICNACT))
-#define W_CSTATUS(w) (reinterpret_cast<int*>(SM_(w, sl::OFF_INT)))
-#define W_ISFREE(w) (reinterpret_cast<int*>(SM_(w, sl::OFF_INT)) + 104)
-#define W_ISCR(w) (reinterpret_cast<int*>(SM_(w, sl::OFF_INT)) + 104 + 104)
+#define W_CSTATUS(w) (reinterpret_cast<int*>((w).g + gl::OFF_CSTAT))
+#define W_ISFREE(w) (reinterpret_cast<int*>((w).g + gl::OFF_CSTAT) + 104)
+#define W_ISCR(w) (reinterpret_cast<int*>(SM_(w, sl::OFF_INT)))
 #define W_C(w) ((w).g + gl::OFF_C)
 #define W_A(w) ((w).g + gl::OFF_A)
 #define W_LA(w) ((w).g + gl::OFF_LA)
 
-// QQP storage selector: shared memory, or the global spill copy
+// QQP storage selector: shared memory, or the global spill copy.  The generic QQP's vectors only exist on the host
+// (shared-memory case) and in the spill copy; on the device the shared-memory case is the register-resident QQP of
+// qp_fast.cuh, which uses the named arrays of `sl` directly.
 template <bool SPILL>
 struct QS {
     static constexpr int VL = SPILL ? VLG : VLS;
     static WBC_HD double* CI(const Work& w) { return SPILL ? w.g + gl::OFF_CI : SM_(w, sl::OFF_CI); }
     static WBC_HD double* Z(const Work& w) { return SPILL ? w.g + gl::OFF_Z : SM_(w, sl::OFF_Z); }
+    static WBC_HD double* EXB(const Work& w) { return SPILL ? w.g + gl::OFF_EXBG : SM_(w, sl::OFF_EXB); }
+#if defined(__CUDACC__)
+    static WBC_HD double* V(const Work& w, int k)
+    {
+        static_assert(SPILL, "the generic QQP's shared-memory vectors do not exist on the device");
+        return w.g + gl::OFF_V + k * VL;
+    }
+#else
     static WBC_HD double* V(const Work& w, int k) { return (SPILL ? w.g + gl::OFF_V : SM_(w, sl::OFF_V)) + k * VL; }
+#endif
 };
 // vector slots
 enum { V_ZD = 0, V_ZRINV, V_XC, V_DC, V_T0, V_T1, V_T2, V_T3, V_SPARE, V_XP, V_GC, V_CGC, V_CGP, V_DP, V_BUFR, V_REG };
@@ -623,7 +660,7 @@ WBC_HDNI void eval_candidates(const Ex ex, const Work w, int nic, double rho, co
     const double* H = W_H(w);
     const double* CI = QS<SPILL>::CI(w);
     const double* xc = QS<SPILL>::V(w, V_XC);
-    const double* exb = W_EXB(w);
+    const double* exb = QS<SPILL>::EXB(w);
     double* t0 = QS<SPILL>::V(w, V_T0);
     double* t1 = QS<SPILL>::V(w, V_T1);
     double* t2 = QS<SPILL>::V(w, V_T2);
@@ -910,7 +947,7 @@ WBC_HDNI int qqp_optimize(const Ex ex, const Work w, int nic, double rho, double
     double* dc = QS<SPILL>::V(w, V_DC);
     double* dp = QS<SPILL>::V(w, V_DP);
     double* spare = QS<SPILL>::V(w, V_SPARE);
-    double* exb = W_EXB(w);
+    double* exb = QS<SPILL>::EXB(w);
     double* exxc = W_EXXC(w);
     int* cstatus = W_CSTATUS(w);
     int* isfree = W_ISFREE(w);
@@ -1278,12 +1315,27 @@ template <class Ex>
 WBC_HDNI bool update_lagrange_multipliers_reduced(const Ex ex, const Work w, int nec, int nic, double pivtol, int* flags_io, double* flops_io)
 {
     const int ktotal = nec + nic;
-    int* act = W_CSTATUS(w);               // QQP is not running: reuse its integer arrays
-    int* dep = W_ISFREE(w);
+    // Workspace (the QQP is not running, so everything but EXXC and the ints is free):
+    //   big (sl::BIG doubles, in front of CI):  W [KACAP+1][31] | factor of A and its reciprocal diagonal  -- first pass on an active set
+    //                                           S, its factor, the factor of G (packed triangles)          -- afterwards
+    //   the CI array:                           eight vectors of 40, the active list and the dependency flags
+    double* big = W_BIG(w);
+    double* civ = SM_(w, sl::OFF_CI);
+    constexpr int VS = 40;
+    double* sd = civ;
+    double* srinv = civ + VS;
+    double* rho_ = civ + 2 * VS;
+    double* dl = civ + 3 * VS;
+    double* u1 = civ + 4 * VS;
+    double* gd = civ + 5 * VS;
+    double* grinv = civ + 6 * VS;
+    double* nu0 = civ + 7 * VS;
+    int* act = reinterpret_cast<int*>(civ + 8 * VS);
+    int* dep = act + VS;
+    static_assert(KACAP < VS && 9 * VS <= NICCAP * LDH, "vectors of the multiplier update fit the CI array");
     const double* exxc = W_EXXC(w);
     double* nulcest = W_NULCEST(w);
     const double* C = W_C(w);
-    const double* larinv = W_LARINV(w);
     double flops = 0.0;
     // ---- active list, in row order (ballot compaction)
     int ka = 0;
@@ -1303,24 +1355,17 @@ WBC_HDNI bool update_lagrange_multipliers_reduced(const Ex ex, const Work w, int
 #endif
         return false;
     }
-    double* big = W_BIG(w);
-    double* Wm = big;                              // [KACAP+1][31]: U^-T c_m | d_m ; last row: t        (1147)
-    double* Sm = big + (KACAP + 1) * LDH + 1;      // packed lower Schur complement / factor, zoff(36) = 648
-    double* G = big;                               // packed lower, 648: overlays Wm, which is dead by then
-    double* LAs = Sm + 648;                        // packed factor of A, 450  -> 2246 <= 2640
-    static_assert((KACAP + 1) * LDH + 1 + 648 + 450 <= sl::BIG, "reduced multiplier update workspace");
+    constexpr int WROWS = (KACAP + 1) * LDH + 1;   // 1148
+    double* Wm = big;                              // [KACAP+1][31]: U^-T c_m | d_m ; last row: t
+    double* LAs = big + WROWS;                     // packed factor of A (zoff(30) = 435) | its reciprocal diagonal [32]
+    const double* larinv = LAs + gl::LA_DOUBLES;
+    static_assert(WROWS + gl::LA_DOUBLES + 32 <= sl::BIG, "reduced multiplier update workspace (first pass)");
+    constexpr int TRI = (KACAP * (KACAP - 1)) >> 1;                      // packed triangle of the largest active set, 630
+    static_assert(2 * TRI <= sl::BIG && TRI <= 648, "reduced multiplier update workspace (S and G)");
+    double* Sm = big;                              // S = W W' (fetched back from the cache once W is dead), factored in place
+    double* G = big + TRI;                         // factor of G = Lt'Lt (rank-deficient active sets)
     double* Sfac = Sm;                             // where the factor of S / of G is read from (a cache hit puts them elsewhere)
     double* Gfac = G;
-    static_assert(KACAP <= 40 && ((KACAP * (KACAP - 1)) >> 1) + (KACAP >> 1) <= 648, "multiplier cache rows");
-    double* vv = W_VEC(w);
-    double* sd = vv;
-    double* srinv = vv + VLS;
-    double* rho_ = vv + 2 * VLS;
-    double* dl = vv + 3 * VLS;
-    double* u1 = vv + 4 * VLS;
-    double* gd = vv + 5 * VLS;
-    double* grinv = vv + 6 * VLS;
-    double* nu0 = vv + 7 * VLS;
     // ---- the cache: W, S = W W', its factor and (rank-deficient sets) the factor of G depend only on which rows of C
     // are active, not on the multipliers or the point.  The outer iterations of a solve usually end on the same active
     // set (the working set settles in the first one), so the second and third update reuse them bit for bit.
@@ -1344,9 +1389,10 @@ WBC_HDNI bool update_lagrange_multipliers_reduced(const Ex ex, const Work w, int
 #pragma unroll 1
     for (int m = ex.lane(); m < ka; m += Ex::NL) nu0[m] = nulcest[act[m]];
     int ndep_i = 0;
+    bool g_later = false;
     if (!hit) {
         if (ex.lane() == 0) mci[80] = -1;          // invalid until this pass completes
-        ex.copy_in(LAs, W_LA(w), 450);
+        ex.copy_in(LAs, W_LA(w), gl::LA_DOUBLES + 32);
         ex.sync();
         // ---- forward substitutions U' y = c_m, one lane per right-hand side
 #pragma unroll 1
@@ -1366,7 +1412,8 @@ WBC_HDNI bool update_lagrange_multipliers_reduced(const Ex ex, const Work w, int
             y[NMAIN] = (m < ka) ? src[NMAIN] : 0.0;
         }
         ex.sync();
-        // ---- Schur complement S = W W' (packed lower + diagonal vector)
+        // ---- Schur complement S = W W' (packed lower + diagonal vector).  W fills the workspace, so S goes straight to the
+        // cache (where the later updates on this active set look for it) and comes back once W is dead.
 #pragma unroll 1
         for (int e = ex.lane(); e < npairs; e += Ex::NL) {
             int c, r;
@@ -1376,10 +1423,10 @@ WBC_HDNI bool update_lagrange_multipliers_reduced(const Ex ex, const Work w, int
             double s0 = 0.0, s1 = 0.0;
 #pragma unroll 1
             for (int k = 0; k < NMAIN; k += 2) { s0 += wr[k] * wc[k]; s1 += wr[k + 1] * wc[k + 1]; }
-            if (r == c) sd[r] = s0 + s1; else Sm[zoff(c) + r] = s0 + s1;
+            if (r == c) sd[r] = s0 + s1; else mc[gl::MC_S0 + zoff(c) + r] = s0 + s1;
         }
         ex.sync();
-        // c0 = d + W t, and the unfactored S, for the later updates on this active set
+        // c0 = d + W t, for this and the later updates on this active set
 #pragma unroll 1
         for (int m = ex.lane(); m < ka; m += Ex::NL) {
             const double* wm = &Wm[m * LDH];
@@ -1390,18 +1437,18 @@ WBC_HDNI bool update_lagrange_multipliers_reduced(const Ex ex, const Work w, int
             mc[gl::MC_C0 + m] = sacc;
             mc[gl::MC_S0D + m] = sd[m];
         }
-#pragma unroll 1
-        for (int e = ex.lane(); e < nz; e += Ex::NL) mc[gl::MC_S0 + e] = Sm[e];
+        ex.sync();                                 // W is dead; every lane's part of S has been written
+        ex.copy_in(Sm, mc + gl::MC_S0, nz);
         flops += (double)(ka + 1) * NMAIN * NMAIN + (double)ka * ka * NMAIN + 2.0 * ka * NMAIN;
     } else {
-        // every cached block is fetched in one round trip: S into its usual place, the factors into the (unused) W area
+        // the cached blocks are fetched in one round trip: S, the factor of S and (when the three fit) the factor of G
         ndep_i = mci[82];
-        Sfac = big;
-        Gfac = big + 1796;
-        static_assert(1796 + 648 <= sl::BIG && 648 <= (KACAP + 1) * LDH + 1, "cached factors fit around S");
+        Sfac = big + nz;
+        Gfac = big + 2 * nz;
+        g_later = (ndep_i != 0) && (3 * nz > sl::BIG);
         ex.copy_start(Sm, mc + gl::MC_S0, nz);
         ex.copy_start(Sfac, mc + gl::MC_SF, nz);
-        if (ndep_i != 0) ex.copy_start(Gfac, mc + gl::MC_G, nz);
+        if (ndep_i != 0 && !g_later) ex.copy_start(Gfac, mc + gl::MC_G, nz);
         ex.copy_wait();
 #pragma unroll 1
         for (int m = ex.lane(); m < ka; m += Ex::NL) sd[m] = mc[gl::MC_S0D + m];
@@ -1483,6 +1530,10 @@ WBC_HDNI bool update_lagrange_multipliers_reduced(const Ex ex, const Work w, int
         if (ndep_i != 0) {
 #pragma unroll 1
             for (int m = ex.lane(); m < ka; m += Ex::NL) { gd[m] = mc[gl::MC_GD + m]; grinv[m] = mc[gl::MC_GRINV + m]; }
+            if (g_later) {                         // the three triangles did not fit: the factor of G replaces S, which is dead by now
+                Gfac = big;
+                ex.copy_in(Gfac, mc + gl::MC_G, nz);
+            }
         }
         *flags_io |= 64;
     }
@@ -1569,15 +1620,20 @@ WBC_HDNI void generate_ex_model(const Ex ex, const Work w, int nec, int nic, dou
     double* CI = QS<SPILL>::CI(w);
     const double* A = W_A(w);
     const double* nulc = W_NULC(w);
-    double* exb = W_EXB(w);
-    // the working rows of C: staged into the (idle) factor array, or read in place when spilled
+    double* exb = QS<SPILL>::EXB(w);
+    // The working rows of C are read in place when spilled.  Otherwise they are staged in front of and INTO the CI array:
+    // the equality rows end where CI begins, so the working inequality rows land in CI itself and are scaled by rho in
+    // place at the end.  EXB lies inside the staging area: the linear term is collected at the head of the (idle) factor
+    // array and moved once the rows are dead.  (Caller guarantees nec * LDH + 48 <= sl::STAGE_EQ_CAP.)
     const double* Cs;
+    double* exbt = exb;
     if (SPILL) Cs = W_C(w);
     else {
-        double* st = QS<false>::Z(w);
+        double* st = SM_(w, sl::OFF_CI) - nec * LDH;
         ex.copy_in(st, W_C(w), kw * LDH);
         ex.sync();
         Cs = st;
+        exbt = SM_(w, sl::OFF_Z);
     }
     // quadratic term, main block: A + rho * C'C
     int i, j;
@@ -1597,15 +1653,6 @@ WBC_HDNI void generate_ex_model(const Ex ex, const Work w, int nec, int nic, dou
         H[i * LDH + j] = v;
         H[j * LDH + i] = v;
     }
-    // slack columns (shared-memory case: a zero row pads the count to even for the two-at-a-time products)
-#pragma unroll 1
-    for (int e = ex.lane(); e < nic * LDH; e += Ex::NL) {
-        const int k = e / LDH, i = e - k * LDH;
-        if (i < NMAIN) CI[k * LDH + i] = 0.0 + rho * Cs[(nec + k) * LDH + i];
-    }
-    if (!SPILL && (nic & 1))
-#pragma unroll 1
-        for (int i = ex.lane(); i < LDH; i += Ex::NL) CI[nic * LDH + i] = 0.0;
     // linear term (41650-41657, 41734-41737): per element, rows in order, two updates per row
 #pragma unroll 1
     for (int i = ex.lane(); i < n; i += Ex::NL) {
@@ -1624,7 +1671,22 @@ WBC_HDNI void generate_ex_model(const Ex ex, const Work w, int nec, int nic, dou
             v += 1.0 * (-rho * Cs[r * LDH + NMAIN]);
             v += 1.0 * (-nulc[r]);
         }
-        exb[i] = v;
+        exbt[i] = v;
+    }
+    ex.sync();
+    // slack columns: CI = rho * (working inequality rows); in the shared-memory case that is an in-place scaling, and a zero
+    // row pads the count to even for the two-at-a-time products
+#pragma unroll 1
+    for (int e = ex.lane(); e < nic * LDH; e += Ex::NL) {
+        const int k = e / LDH, i = e - k * LDH;
+        if (i < NMAIN) CI[k * LDH + i] = 0.0 + rho * Cs[(nec + k) * LDH + i];
+    }
+    if (!SPILL) {
+        if (nic & 1)
+#pragma unroll 1
+            for (int i = ex.lane(); i < LDH; i += Ex::NL) CI[nic * LDH + i] = 0.0;
+#pragma unroll 1
+        for (int i = ex.lane(); i < n; i += Ex::NL) exb[i] = exbt[i];
     }
     ex.sync();
 }
@@ -1723,8 +1785,8 @@ WBC_HDNI int setup_problem(const Ex ex, const Work w, int nrows, int* pd_out, in
     double* sc = W_SC(w);
     double* b = W_B(w);
     double* C = W_C(w);
-    double* stage = SM_(w, sl::OFF_CI);                 // CI | Z: 1710 doubles = 55 staged rows
-    constexpr int CHUNK = 55;
+    double* stage = SM_(w, sl::STAGE0);                 // everything behind H but the ints: 43 staged rows on the device
+    constexpr int CHUNK = (sl::OFF_INT - sl::STAGE0) / LDH;
     double bad = 0.0;
 #pragma unroll 1
     for (int i = ex.lane(); i < NMAIN; i += Ex::NL) {
@@ -1840,7 +1902,7 @@ WBC_HDNI int setup_problem(const Ex ex, const Work w, int nrows, int* pd_out, in
     ex.sync();
     // Cholesky of A: convexity test (42474-42523); the factor is kept for the reduced multiplier update
     double* Zs = SM_(w, sl::OFF_Z);
-    double* ladiag = W_VEC(w) + VLS;
+    double* ladiag = SM_(w, sl::OFF_XC);                // not kept
     struct SrcA {
         const double* A;
         WBC_HD double operator()(int k, int c) const { return A[k * LDH + c]; }
@@ -1849,7 +1911,7 @@ WBC_HDNI int setup_problem(const Ex ex, const Work w, int nrows, int* pd_out, in
     const bool pd = chol_cols<false>(ex, Zs, NMAIN, ladiag, W_LARINV(w), (int*)nullptr, 0.0, (bool*)nullptr, src);
     double* LA = W_LA(w);
 #pragma unroll 1
-    for (int i = ex.lane(); i < 450; i += Ex::NL) LA[i] = Zs[i];
+    for (int i = ex.lane(); i < zoff(NMAIN); i += Ex::NL) LA[i] = Zs[i];
     ex.sync();
     *pd_out = pd ? 1 : 0;
     return 0;
@@ -1881,12 +1943,12 @@ __device__ __forceinline__ int model_and_qqp_dev(const WarpEx& ex, const Work& w
 
 // ------------------------------------------------------------------------------------------------
 // Row-wise products with the constraint matrix.  C lives in global memory (row-major), so rows are first copied --
-// coalesced -- into the idle factor array in shared memory, then each lane takes a row (stride 31: conflict free).
-constexpr int STAGE_ROWS = 1152 / LDH;      // 37
+// coalesced -- into the idle arrays behind H in shared memory, then each lane takes a row (stride 31: conflict free).
+constexpr int STAGE_ROWS = sl::STAGE_CAP / LDH;      // 40 on the device
 template <class Ex>
 WBC_HD const double* stage_rows(const Ex& ex, const Work& w, int row0, int nr)
 {
-    double* st = SM_(w, sl::OFF_Z);
+    double* st = SM_(w, sl::STAGE0);
     ex.copy_in(st, W_C(w) + row0 * LDH, nr * LDH);
     ex.sync();
     return st;
@@ -1986,8 +2048,8 @@ WBC_HDN void solve_denseaul(const Ex& ex, const Work& w, const Settings& cfg, in
         bool extended;
         do {
             int term;
-            // shared-memory capacity: NICCAP working inequality rows, and nec + nicwork rows in the staging array
-            if (nicwork > NICCAP || (nec + nicwork) * LDH > 1152) { st.flags |= 32; term = model_and_qqp<true>(ex, w, nec, nicwork, rho, epsx, &st.ncholesky, &st.flops); }
+            // shared-memory capacity: NICCAP working inequality rows in CI, the equality rows (and the linear term) in front of it
+            if (nicwork > NICCAP || nec * LDH + 48 > sl::STAGE_EQ_CAP) { st.flags |= 32; term = model_and_qqp<true>(ex, w, nec, nicwork, rho, epsx, &st.ncholesky, &st.flops); }
 #if defined(__CUDA_ARCH__)
             else term = model_and_qqp_dev(ex, w, nec, nicwork, rho, epsx, &st.ncholesky, &st.flops, &st.chol_reused);
 #else

@@ -2,8 +2,8 @@
 //
 // Two kernels per cycle, no intermediate dense QP ever reaches HBM:
 //   wbc_front_kernel   thread-per-instance: update() + Fgrf + estimate() + Wcom_des -> 4.2 KB QP record
-//   wbc_solve_kernel   warp-per-instance, one warp per CTA, SOLVE_CTAS_PER_SM resident CTAs per SM (shared-memory
-//                      bound), persistent warps pulling instances from an atomic queue (iteration counts vary
+//   wbc_solve_kernel   warp-per-instance, one warp per CTA, 12 resident CTAs per SM (18.3 KB of shared memory and 168
+//                      registers each), persistent warps pulling instances from an atomic queue (iteration counts vary
 //                      4..50 Cholesky per solve): assemble (Q,c,L) from the record, DENSE-AUL/QQP solve with the
 //                      hot state in shared memory (qp_warp.cuh), torque map.
 // There is no CPU fallback anywhere in this file.
@@ -27,7 +27,9 @@ using namespace wbcqp;
 static_assert(sizeof(wbc_params) == sizeof(wbc::Params), "wbc_params and wbc::Params must have identical layout");
 
 constexpr int SOLVE_T = 32;                   // one warp per instance, one warp per CTA
-constexpr int SOLVE_CTAS_PER_SM = (227 * 1024) / (sl::BYTES + 1024);
+// resident solver CTAs per SM that the shared-memory request allows (228 KB per SM, 1 KB reserved per CTA); the launch
+// shape takes the occupancy calculator's answer, which also accounts for registers
+constexpr int SOLVE_CTAS_PER_SM = (228 * 1024) / (sl::BYTES + 1024);
 
 // ------------------------------------------------------------------------------------------------
 // kernels
@@ -79,6 +81,7 @@ __global__ void __launch_bounds__(64) wbc_front_kernel(Params P, DevInputs in, F
 
 struct SolveOut {
     double* tau; double* x; double* qp_obj; int* status; int* qp_info; double* qp_flops; long ld;
+    double* tau_prev; long ld_prev;      // [12][max_batch] last good torque of every instance index (main.cpp:242), owned by the ctx
 };
 
 __device__ __forceinline__ void write_info(const Stats& st, long i, long ld, int* status, int* info, double* flops)
@@ -118,10 +121,37 @@ __global__ void __launch_bounds__(SOLVE_T) wbc_solve_kernel(Params P, int n, con
         if (ticket >= n) break;
         const int i = order ? order[ticket] : ticket;
         const long long t0 = clock64();
-        // the record is staged in the (still idle) CI | Z arrays: one cp.async round trip instead of scattered global reads
+        // the record is staged in the (still idle) CI | EXXC arrays: one cp.async round trip instead of scattered global reads
         double* rec = SM_(w, sl::OFF_CI);
-        static_assert(QR_MODE + 1 <= NICCAP * LDH + 1152, "QP record fits the staging area");
+        static_assert(QR_MODE + 1 <= NICCAP * LDH + 104, "QP record fits the staging area");
         ex.copy_in(rec, recs + (long)i * QPREC_DOUBLES, QR_MODE + 1);
+        {
+            // Inputs the cycle refuses to process: a contact mode outside {0, 1, 2}, or anything non-finite in the record
+            // (x * 0 is NaN exactly for NaN and the infinities).  The reference would spin or publish garbage
+            // (main.cpp:584-588, lopt.cpp:114-116); here the instance gets a status word and a defined torque.
+            double chk = 0.0;
+#pragma unroll 1
+            for (int k = ex.lane(); k <= QR_MODE; k += SOLVE_T) chk += rec[k] * 0.0;
+            const bool nonfinite = __any_sync(0xffffffffu, chk != 0.0);
+            const double md = rec[QR_MODE];
+            if (nonfinite || !(md == 0.0 || md == 1.0 || md == 2.0)) {
+                for (int k = ex.lane(); k < 12; k += SOLVE_T)
+                    out.tau[(long)k * out.ld + i] = P.hold_tau_on_failure ? out.tau_prev[(long)k * out.ld_prev + i] : 0.0;
+                if (out.x)
+                    for (int k = ex.lane(); k < 30; k += SOLVE_T) out.x[(long)k * out.ld + i] = 0.0;
+                if (ex.lane() == 0) {
+                    Stats st;
+                    st.termination = nonfinite ? WBC_ST_NONFINITE : WBC_ST_BAD_MODE;
+                    st.ncholesky = 0; st.outer_its = 0; st.qqp_calls = 0; st.nicwork = 0; st.kkt_dim_max = 0; st.chol_reused = 0; st.flags = 0; st.flops = 0.0;
+                    write_info(st, i, out.ld, out.status, out.qp_info, out.qp_flops);
+                    if (out.qp_obj) out.qp_obj[i] = 0.0;
+                    cost[i] = 0u;
+                    atomicAdd(hist_next, 1);
+                }
+                ex.sync();
+                continue;
+            }
+        }
         const QpShape sh = qp_shape((int)rec[QR_MODE]);
         // Q -> H array (ld 31), c -> exb, L -> the warp's global C array (scaled in place by the solver)
         assemble_qp<LDH>(ex, P, rec, sh, W_H(w), W_EXB(w), W_C(w));
@@ -140,6 +170,13 @@ __global__ void __launch_bounds__(SOLVE_T) wbc_solve_kernel(Params P, int n, con
         }
         ex.copy_in(rec, recs + (long)i * QPREC_DOUBLES, QR_MODE + 1);     // the solver used the arrays; stage again
         torque_and_objective(ex, P, rec, sh, xs, out.tau + i, out.ld, out.qp_obj ? out.qp_obj + i : nullptr);
+        // last good torque of this instance index (main.cpp:242): refreshed on success, handed out instead of the x = 0 torque
+        // on failure when the caller asked for it
+        if (st.termination == 2) {
+            for (int k = ex.lane(); k < 12; k += SOLVE_T) out.tau_prev[(long)k * out.ld_prev + i] = out.tau[(long)k * out.ld + i];
+        } else if (P.hold_tau_on_failure) {
+            for (int k = ex.lane(); k < 12; k += SOLVE_T) out.tau[(long)k * out.ld + i] = out.tau_prev[(long)k * out.ld_prev + i];
+        }
         if (out.x)
             for (int k = ex.lane(); k < 30; k += SOLVE_T) out.x[(long)k * out.ld + i] = xs[k];
         if (ex.lane() == 0) {
@@ -191,14 +228,14 @@ __global__ void __launch_bounds__(SOLVE_T) wbc_dense_qp_kernel(Params P, int n, 
         ex.sync();
         Stats st;
         solve_denseaul(ex, w, cfg, nrows, neq, st);
-        if (st.termination == 2)
-            for (int k = ex.lane(); k < 30; k += SOLVE_T) x[(long)i * 30 + k] = W_XS(w)[k];
+        // a failed instance returns x = 0, like wbc_cycle (never a previous call's solution left in the staging block)
+        for (int k = ex.lane(); k < 30; k += SOLVE_T) x[(long)i * 30 + k] = (st.termination == 2) ? W_XS(w)[k] : 0.0;
         if (ex.lane() == 0) {   // instance-major info [n][8] on this path
             write_info(st, i, n, status, nullptr, flops);
             if (info) {
                 int* q = info + (long)i * 8;
                 q[0] = st.ncholesky; q[1] = st.outer_its; q[2] = st.qqp_calls; q[3] = st.nicwork; q[4] = st.kkt_dim_max;
-                q[5] = st.flags; q[6] = 0; q[7] = 0;
+                q[5] = st.flags; q[6] = st.chol_reused; q[7] = 0;
             }
         }
         ex.sync();
@@ -311,6 +348,7 @@ struct wbc_ctx {
     double* yd;          // [6][max_batch]
     double* yw;
     double* w_dev;       // [6][max_batch] (when the caller passes no w)
+    double* tau_prev;    // [12][max_batch] last good torque per instance index (hold_tau_on_failure)
     double* scratch;     // [nblocks][gl::TOTAL]
     int* queue;          // [cost histogram A | work-queue counter | dispatch cursors | cost histogram B]: counter and cursors sit between
                          // the two histograms so that "counter + cursors + the histogram being filled" is one contiguous memset either way
@@ -319,6 +357,7 @@ struct wbc_ctx {
     int order_n;         // batch size `cost` and the current histogram describe (0 = none)
     int hist_sel;        // which histogram the last solve filled
     int nblocks, threads;   // solver launch shape
+    int occ_per_sm;         // resident solver CTAs per SM (occupancy calculator)
     int solve_smem;         // dynamic shared memory per solver CTA (sl::BYTES, or padded by WBC_SOLVE_CTAS_PER_SM)
     // staging for WBC_HOST_PTRS
     double* d_in;        // [93+40][max_batch]
@@ -351,7 +390,7 @@ void wbc_default_params(wbc_params* p)
     p->joint_dt = 0.025; p->kp_sw = 300.0; p->kd_sw = 20.0; p->g_acc = 9.81; p->obs_gain = 10.0; p->obs_dt = 0.0025;
     p->gravity[0] = 0.0; p->gravity[1] = 0.0; p->gravity[2] = -9.8;
     p->qp_epsx = 1.0e-2; p->qp_rho = 1.0e4; p->qp_outerits = 5;
-    p->observer_enabled = 1; p->fix_swing_rhs = 0; p->qp_literal_kkt = 0;
+    p->observer_enabled = 1; p->fix_swing_rhs = 0; p->qp_literal_kkt = 0; p->hold_tau_on_failure = 0;
 }
 
 const char* wbc_last_error(void) { return g_err; }
@@ -361,7 +400,7 @@ int wbc_destroy(wbc_ctx* c)
 {
     if (!c) return WBC_OK;
     cudaSetDevice(c->device);
-    cudaFree(c->recs); cudaFree(c->yd); cudaFree(c->yw); cudaFree(c->w_dev); cudaFree(c->scratch); cudaFree(c->queue); cudaFree(c->cost); cudaFree(c->order);
+    cudaFree(c->recs); cudaFree(c->yd); cudaFree(c->yw); cudaFree(c->w_dev); cudaFree(c->tau_prev); cudaFree(c->scratch); cudaFree(c->queue); cudaFree(c->cost); cudaFree(c->order);
     cudaFree(c->traj_dur); cudaFree(c->traj_nodes); cudaFree(c->traj_s); cudaFree(c->traj_t);
     cudaFree(c->d_in); cudaFree(c->d_out); cudaFree(c->d_mode); cudaFree(c->d_iout); cudaFree(c->d_dense);
     if (c->h_pin) cudaFreeHost(c->h_pin);
@@ -394,18 +433,21 @@ int wbc_create(wbc_ctx** out, int device, int max_batch, const wbc_params* param
     memcpy(&c->params, params ? params : &def, sizeof(Params));
     const size_t nb = (size_t)max_batch;
     c->threads = SOLVE_T;
-    c->nblocks = c->sm_count * SOLVE_CTAS_PER_SM;
     c->solve_smem = sl::BYTES;
+    int per_sm = SOLVE_CTAS_PER_SM;
     // occupancy experiment knob: fewer resident solver warps per SM (the shared-memory request is padded so that
     // exactly that many CTAs fit); used by tools/ to measure how throughput scales with resident warps
     if (const char* ev = getenv("WBC_SOLVE_CTAS_PER_SM")) {
         const int k = atoi(ev);
         if (k >= 1 && k < SOLVE_CTAS_PER_SM) {
-            c->nblocks = c->sm_count * k;
-            c->solve_smem = (((227 * 1024) / k - 1024) / 16) * 16;
+            per_sm = k;
+            c->solve_smem = (((228 * 1024) / k - 1024) / 16) * 16;
+            if (c->solve_smem > 227 * 1024) c->solve_smem = 227 * 1024;
         }
     }
-    const long nteams = c->nblocks;
+    c->nblocks = c->sm_count * per_sm;
+    // one scratch block per resident solver warp a launch can use (a launch never has more CTAs than instances)
+    const long nteams = c->nblocks < max_batch ? c->nblocks : max_batch;
     cudaError_t e = cudaSuccess;
 #define TRY(call) if (e == cudaSuccess) e = (call)
     TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -414,6 +456,8 @@ int wbc_create(wbc_ctx** out, int device, int max_batch, const wbc_params* param
     TRY(cudaMalloc(&c->yd, nb * 6 * sizeof(double)));
     TRY(cudaMalloc(&c->yw, nb * 6 * sizeof(double)));
     TRY(cudaMalloc(&c->w_dev, nb * 6 * sizeof(double)));
+    TRY(cudaMalloc(&c->tau_prev, nb * 12 * sizeof(double)));
+    TRY(cudaMemset(c->tau_prev, 0, nb * 12 * sizeof(double)));
     TRY(cudaMalloc(&c->scratch, (size_t)nteams * gl::TOTAL * sizeof(double)));
     TRY(cudaMalloc(&c->queue, (1 + 3 * ORD_NB) * sizeof(int)));
     TRY(cudaMemset(c->queue, 0, (1 + 3 * ORD_NB) * sizeof(int)));
@@ -432,6 +476,15 @@ int wbc_create(wbc_ctx** out, int device, int max_batch, const wbc_params* param
     TRY(cudaFuncSetAttribute(wbc_dense_qp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->solve_smem));
     TRY(cudaFuncSetAttribute(wbc_solve_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     TRY(cudaFuncSetAttribute(wbc_dense_qp_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    if (e == cudaSuccess) {
+        // the persistent grid is exactly the resident CTAs: more would queue behind whole solves
+        int occ = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wbc_solve_kernel, SOLVE_T, (size_t)c->solve_smem);
+        if (e == cudaSuccess && occ >= 1) {
+            c->occ_per_sm = occ;
+            if (c->nblocks > c->sm_count * occ) c->nblocks = c->sm_count * occ;
+        }
+    }
 #undef TRY
     if (e != cudaSuccess) {
         fail(e == cudaErrorMemoryAllocation ? WBC_ENOMEM : WBC_ECUDA, "wbc_create: %s", cudaGetErrorString(e));
@@ -599,6 +652,7 @@ int wbc_cycle(wbc_ctx* c, int n, const wbc_inputs* in, const wbc_outputs* out, v
         w_ptr = c->d_out + 12L * n;
         w_ld = n;
     }
+    so.tau_prev = c->tau_prev; so.ld_prev = c->max_batch;
     FrontState st;
     st.yd = c->yd; st.yw = c->yw; st.ld = c->max_batch;
     DevDebug nodbg;
@@ -798,6 +852,15 @@ int wbc_last_solve_cycles(wbc_ctx* c, int n, unsigned long long* cycles)
 }
 int wbc_last_launches(wbc_ctx* c) { return c ? c->launches : 0; }
 
+int wbc_solver_shape(wbc_ctx* c, int* ctas_per_sm, int* smem_bytes, int* grid)
+{
+    if (!c) return fail(WBC_EINVAL, "null ctx");
+    if (ctas_per_sm) *ctas_per_sm = c->occ_per_sm;
+    if (smem_bytes) *smem_bytes = c->solve_smem;
+    if (grid) *grid = c->nblocks;
+    return WBC_OK;
+}
+
 int wbc_host_alloc(void** p, size_t bytes)
 {
     if (!p || bytes == 0) return fail(WBC_EINVAL, "wbc_host_alloc: bad arguments");
@@ -839,17 +902,23 @@ int wbc_debug_update(wbc_ctx* c, int n, const wbc_inputs* in, const wbc_debug* d
     size_t off = 0;
     for (int f = 0; f < 17; f++) { *dp[f] = dbuf + off * n; off += K[f]; }
     dd.ld = n;
-    // observer state must not advance: run on a scratch copy
+    // The observer state must not advance and the ctx's QP records must stay those of the last wbc_cycle (wbc_plant_step
+    // reads them): run on a scratch copy of yd/yw and into scratch records.
     double* ytmp = nullptr;
-    cudaError_t e = cudaMalloc(&ytmp, (size_t)12 * n * sizeof(double));
-    if (e != cudaSuccess) { cudaFree(dbuf); return fail(WBC_ENOMEM, "wbc_debug_update: %s", cudaGetErrorString(e)); }
-    cudaMemsetAsync(ytmp, 0, (size_t)12 * n * sizeof(double), s);
-    FrontState st;
-    st.yd = ytmp; st.yw = ytmp + 6L * n; st.ld = n;
-    const int fthreads = front_threads(c, n);
-    wbc_front_kernel<<<(n + fthreads - 1) / fthreads, fthreads, 0, s>>>(c->params, din, st, n, c->recs, c->w_dev, c->max_batch, dd, 1, DispatchOrder{nullptr, nullptr, nullptr, nullptr});
-    e = cudaStreamSynchronize(s);
-    if (e == cudaSuccess) e = cudaGetLastError();
+    double* rtmp = nullptr;
+    cudaError_t e = cudaMalloc(&ytmp, (size_t)18 * n * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&rtmp, (size_t)n * QPREC_DOUBLES * sizeof(double));
+    if (e != cudaSuccess) { cudaFree(dbuf); cudaFree(ytmp); return fail(WBC_ENOMEM, "wbc_debug_update: %s", cudaGetErrorString(e)); }
+    e = cudaMemcpy2DAsync(ytmp, (size_t)n * 8, c->yd, (size_t)c->max_batch * 8, (size_t)n * 8, 6, cudaMemcpyDeviceToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpy2DAsync(ytmp + 6L * n, (size_t)n * 8, c->yw, (size_t)c->max_batch * 8, (size_t)n * 8, 6, cudaMemcpyDeviceToDevice, s);
+    if (e == cudaSuccess) {
+        FrontState st;
+        st.yd = ytmp; st.yw = ytmp + 6L * n; st.ld = n;
+        const int fthreads = front_threads(c, n);
+        wbc_front_kernel<<<(n + fthreads - 1) / fthreads, fthreads, 0, s>>>(c->params, din, st, n, rtmp, ytmp + 12L * n, n, dd, 1, DispatchOrder{nullptr, nullptr, nullptr, nullptr});
+        e = cudaStreamSynchronize(s);
+        if (e == cudaSuccess) e = cudaGetLastError();
+    }
     off = 0;
     for (int f = 0; f < 17 && e == cudaSuccess; f++) {
         if (host[f]) e = cudaMemcpy2D(host[f], (size_t)dbg->ld * 8, dbuf + off * n, (size_t)n * 8, (size_t)n * 8, K[f], cudaMemcpyDeviceToHost);
@@ -857,6 +926,7 @@ int wbc_debug_update(wbc_ctx* c, int n, const wbc_inputs* in, const wbc_debug* d
     }
     cudaFree(dbuf);
     cudaFree(ytmp);
+    cudaFree(rtmp);
     c->launches = 1;
     if (e != cudaSuccess) return fail(WBC_ECUDA, "wbc_debug_update: %s", cudaGetErrorString(e));
     return WBC_OK;

@@ -380,6 +380,7 @@ WBC_DEVFN inline void front_cycle(const Params& P, const DevInputs& in, const Fr
     // ---- estimate() (main.cpp:692-725)
     const double comv6[6] = {comv.x, comv.y, comv.z, w0.x, w0.y, w0.z};     // CoM_vel, main.cpp:602
     double west[6], rho6[6], dd6[6];
+    bool finite_obs = true;
     for (int a = 0; a < 6; a++) {
         double rho = 0.0, fc = 0.0;
         for (int b = 0; b < 6; b++) rho += Mc[a * 6 + b] * comv6[b];        // 699, 705
@@ -390,17 +391,24 @@ WBC_DEVFN inline void front_cycle(const Params& P, const DevInputs& in, const Fr
     if (P.observer_enabled) {
         const double T = P.obs_dt, k0 = in.obs_gain ? in.obs_gain[i] : P.obs_gain;
         const double mgain = (1.0 / (1.0 + k0 * T)) * k0;                   // (I + k0 T)^-1 k0, main.cpp:716
+        double ydn[6], ywn[6];
         for (int a = 0; a < 6; a++) {
             const double yd = st.yd[(long)a * st.ld + i] + dd6[a] * T;      // 717
             const double wv = mgain * (rho6[a] - st.yw[(long)a * st.ld + i] - yd);   // 718
-            st.yd[(long)a * st.ld + i] = yd;                                // 721-724
-            st.yw[(long)a * st.ld + i] += wv * T;                           // 719
+            ydn[a] = yd;
+            ywn[a] = st.yw[(long)a * st.ld + i] + wv * T;                   // 719
             west[a] = wv;
+            finite_obs = finite_obs && (yd - yd == 0.0) && (ywn[a] - ywn[a] == 0.0);
         }
+        // the carried state (main.cpp:721-724) only advances on finite values: a NaN among the inputs must not poison the
+        // instance's observer for the rest of the run.  The estimate itself stays non-finite here, so Wcom_des and with it the
+        // QP record are, and the solver kernel flags the instance (WBC_ST_NONFINITE) instead of solving it.
+        if (finite_obs)
+            for (int a = 0; a < 6; a++) { st.yd[(long)a * st.ld + i] = ydn[a]; st.yw[(long)a * st.ld + i] = ywn[a]; }
     } else {
         for (int a = 0; a < 6; a++) west[a] = 0.0;
     }
-    for (int a = 0; a < 6; a++) w_out[(long)a * w_ld + i] = west[a];
+    for (int a = 0; a < 6; a++) w_out[(long)a * w_ld + i] = finite_obs ? west[a] : 0.0;
 
     // ---- Wcom_des (main.cpp:1012-1032)
     double Wc[6];

@@ -40,6 +40,7 @@ struct Params {
     int observer_enabled;     // north_star: 1 (the reference ships with the call commented out, main.cpp:1029)
     int fix_swing_rhs;        // 0 keeps the reference's zero swing-equality rhs (main.cpp:1238-1241)
     int qp_literal_kkt;       // 0: reduced multiplier update, literal form as fallback; 1: literal form only (opt.cpp:41803-42032)
+    int hold_tau_on_failure;  // 1: a failed instance keeps the last good tau of its index (main.cpp:242; lopt.cpp:114-116 swallows the failure)
 };
 
 struct DevInputs {

@@ -322,3 +322,88 @@ def make_trajectory(sc, nseg=3, seed=11, match_acc=False):
     t[on_j] = junction[on_j]
     t[idx % 7 == 0] = 0.0
     return {"nseg": nseg, "durations": np.ascontiguousarray(dur), "nodes": np.ascontiguousarray(nodes), "t": t}
+
+
+ROLLOUT_CYCLES_PER_PHASE = 46      # 0.115 s per gait phase at the 400 Hz control rate (quadruped_gait_generator.cc:277-310 durations, main.cpp:861)
+
+
+def _rollout_constants(n, start, seed):
+    """Per-robot constants of trot_rollout, block-keyed like make(): robot i gets the same numbers whatever the batch size
+    or the number of ranks."""
+    parts = []
+    b0, b1 = start // BLOCK, (start + max(n, 1) - 1) // BLOCK
+    for blk in range(b0, b1 + 1):
+        g = lambda s: _rng(seed, blk, s)
+        c = {"phase": g(0).integers(0, 4 * ROLLOUT_CYCLES_PER_PHASE, BLOCK),
+             "xy": g(1).uniform(-1.0, 1.0, (2, BLOCK)), "yaw": g(2).uniform(-0.3, 0.3, BLOCK),
+             "amp": g(3).uniform(0.04, 0.12, (12, BLOCK)), "freq": g(4).uniform(1.5, 2.5, BLOCK),
+             "ph": g(5).uniform(0.0, 2 * np.pi, (12, BLOCK)), "sway": g(6).uniform(0.005, 0.03, BLOCK),
+             "z": g(7).uniform(0.40, 0.44, BLOCK), "des": g(8).uniform(0.0, 2 * np.pi, (6, BLOCK)),
+             "push_leg": g(9).integers(0, 4, BLOCK), "push_fx": (5.0 + g(10).integers(0, 20, BLOCK)) * g(11).choice([-1.0, 1.0], BLOCK),
+             "push_fy": (5.0 + g(12).integers(0, 10, BLOCK)) * g(13).choice([-1.0, 1.0], BLOCK),
+             "push_t0": g(14).integers(0, 4 * ROLLOUT_CYCLES_PER_PHASE, BLOCK)}
+        c["xy"][c["xy"] == 0.0] = 0.25
+        lo = max(start, blk * BLOCK) - blk * BLOCK
+        hi = min(start + n, (blk + 1) * BLOCK) - blk * BLOCK
+        parts.append({k: v[..., lo:hi] for k, v in c.items()})
+    return {k: np.concatenate([p[k] for p in parts], axis=-1) for k in parts[0]}
+
+
+def trot_rollout(n, step, seed=5, start=0):
+    """Evolving-state workload: robots [start, start+n) of a herd that trots through the gait cycle of configs[0]
+    (stance, swing{BR,FL}, stance, swing{BL,FR}; 46 control cycles each, main.cpp:978-1400 phase switching) with
+    per-robot phase offsets, gaits and pushes.  Returns the inputs of control cycle `step` (0, 1, 2, ...) for every robot:
+    robot r is at cycle k = phase_r + step of its own gait, so at any step a quarter of the herd changes contact mode
+    within the next 11 cycles, swing and stance solves are mixed, and the QP active sets drift from cycle to cycle.
+    The observer state is NOT part of the scenario: the caller chains it (cycle k+1 uses the state cycle k produced).
+    A force_plugin-style push (fp.cpp:203-310: Fx = +-(5..24) N, Fy = +-(5..14) N on one leg) acts on each robot for 40
+    cycles of every gait cycle and shows up in the measured force of that leg."""
+    C = _rollout_constants(n, start, seed)
+    cpp = ROLLOUT_CYCLES_PER_PHASE
+    k = C["phase"] + int(step)
+    t = k * 0.0025
+    w = 2 * np.pi * C["freq"]
+    sc = {}
+    sway = C["sway"] * np.sin(2 * np.pi * 1.0 * t)
+    dsway = C["sway"] * 2 * np.pi * np.cos(2 * np.pi * 1.0 * t)
+    sc["base_pos"] = np.vstack([C["xy"][0] + sway, C["xy"][1] + 0.5 * sway, C["z"]])
+    rpy = np.vstack([0.01 * np.sin(2 * np.pi * 1.5 * t), 0.01 * np.cos(2 * np.pi * 1.2 * t), C["yaw"]])
+    sc["base_rpy"] = rpy
+    sc["base_rot"] = np.ascontiguousarray(rpy_to_rot(rpy).reshape(n, 9).T)
+    # world-frame base twist consistent with the scripted pose (yaw constant: the roll/pitch rates are the body rates to first order)
+    sc["base_vel"] = np.vstack([dsway, 0.5 * dsway, np.zeros(n), 0.01 * 2 * np.pi * 1.5 * np.cos(2 * np.pi * 1.5 * t),
+                                -0.01 * 2 * np.pi * 1.2 * np.sin(2 * np.pi * 1.2 * t), np.zeros(n)])
+    arg = w[None, :] * t[None, :] + C["ph"]
+    sc["q"] = np.clip(Q_NOMINAL[:, None] + C["amp"] * np.sin(arg), QMIN[:, None], QMAX[:, None])
+    sc["dq"] = C["amp"] * w[None, :] * np.cos(arg)
+    com, feet = forward_kinematics(sc["base_pos"], sc["base_rot"], sc["q"])
+    off = 0.015 * np.sin(2 * np.pi * 0.8 * t[None, :] + C["des"])
+    sc["com_des_pos"] = np.vstack([com.T + off[0:3], rpy + 0.5 * off[3:6]])
+    sc["com_des_vel"] = 0.015 * 2 * np.pi * 0.8 * np.cos(2 * np.pi * 0.8 * t[None, :] + C["des"]) * np.array([1, 1, 1, .5, .5, .5])[:, None]
+    sc["com_des_acc"] = -0.015 * (2 * np.pi * 0.8) ** 2 * np.sin(2 * np.pi * 0.8 * t[None, :] + C["des"]) * np.array([1, 1, 1, .5, .5, .5])[:, None]
+    phase = (k // cpp) % 4
+    mode = np.array([MODE_STANCE, MODE_SWING_BR_FL, MODE_STANCE, MODE_SWING_BL_FR], dtype=np.int32)[phase]
+    sc["mode"] = np.ascontiguousarray(mode)
+    # measured foot forces (sensor frame, stacked BR,BL,FL,FR): the stance feet share the weight
+    swing = np.zeros((4, n), dtype=bool)
+    swing[0] = swing[2] = mode == MODE_SWING_BR_FL
+    swing[1] = swing[3] = mode == MODE_SWING_BL_FR
+    nst = 4 - swing.sum(axis=0)
+    ff = np.zeros((12, n))
+    for f in range(4):
+        ff[3 * f + 2] = np.where(swing[f], 0.0, TOTAL_MASS * 9.81 / nst * (1.0 + 0.1 * np.sin(2 * np.pi * 3 * t + f)))
+        ff[3 * f + 0] = np.where(swing[f], 0.0, 2.0 * np.sin(2 * np.pi * 2 * t + f))
+        ff[3 * f + 1] = np.where(swing[f], 0.0, 2.0 * np.cos(2 * np.pi * 2 * t + f))
+    pushing = ((k - C["push_t0"]) % (4 * cpp)) < 40
+    idx = np.arange(n)
+    ff[3 * C["push_leg"] + 0, idx] += np.where(pushing, C["push_fx"], 0.0)
+    ff[3 * C["push_leg"] + 1, idx] += np.where(pushing, C["push_fy"], 0.0)
+    sc["foot_force"] = ff
+    first = np.where(mode == MODE_SWING_BL_FR, 1, 0)
+    second = np.where(mode == MODE_SWING_BL_FR, 3, 2)
+    swp = np.hstack([feet[idx, first, :], feet[idx, second, :]]).T
+    phase_t = (k % cpp) / cpp
+    arc = np.zeros((6, n)); arc[2] = arc[5] = 0.06 * np.sin(np.pi * phase_t) ** 2
+    sc["sw_des_pos"] = swp + arc
+    sc["sw_des_vel"] = np.zeros((6, n)); sc["sw_des_acc"] = np.zeros((6, n))
+    return sc
