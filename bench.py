@@ -41,6 +41,8 @@ OUT_BYTES = 8 * 18        # tau + w
 
 REPLAY = "trot_replay_single"  # BASELINE config 1: ONE robot replaying a 184-cycle synthetic trot, one control cycle per step (latency case)
 SWEEP = "push_sweep"          # BASELINE config 5: closed-loop disturbance-rejection sweep, fixed 262144-instance grid
+ROLLOUT = "trot_rollout"      # evolving-state herd: every robot steps through the trot gait, modes and active sets change from cycle to cycle
+QPREC_DOUBLES = 576           # front kernel -> solver record (wbc_types.h)
 SWEEP_TOTAL = S.SWEEP_DIRECTIONS * len(S.SWEEP_MAGNITUDES) * len(S.SWEEP_GAINS) * S.SWEEP_STATES
 
 
@@ -189,86 +191,121 @@ def single_robot_replay(args):
     return 0
 
 
-def main():
+def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="standing_4096", choices=sorted(S.CONFIGS) + [SWEEP, REPLAY])
+    ap.add_argument("--workload", default="standing_4096", choices=sorted(S.CONFIGS) + [SWEEP, REPLAY, ROLLOUT])
     ap.add_argument("--per-gpu", type=int, default=None, help="instances per GPU (default: the workload's own size, 1M config: /8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="headline workload only: skip the `also` lines (trot_65536, mixed_terrain_1m shard) and value_fifo")
     ap.add_argument("--traj-on-device", action="store_true",
                     help="e2e loop only: the plan's spline tables live in HBM and are sampled on the GPU each step (SURVEY 8f-1); "
                          "the 36 desired-trajectory doubles per instance are not sent from the host")
     ap.add_argument("--fifo", action="store_true", help="index-order work queue (WBC_FIFO_DISPATCH) instead of longest-first")
+    ap.add_argument("--sweep-cycles", type=int, default=None, help="push_sweep: closed-loop cycles of the rollout (default 400 = 1 s; --steps is ignored)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.workload == REPLAY:
-        if args.impl == "reference":
-            args.no_cpu_baseline = False
-        return single_robot_replay(args) if rank == 0 else 0
-    cfg = workload_cfg(args.workload)
+    return args
+
+
+def algorithmic_bytes(mode, terrain):
+    """1024 B per solve (97 doubles in, 31 out), +144 B for a swing solve (18 swing-foot reference doubles are
+    only read then), +320 B with per-foot terrain frames (40 doubles)."""
+    n = int(mode.shape[0])
+    return n * 1024 + int(np.count_nonzero(mode != 0)) * 144 + (n * 320 if terrain else 0)
+
+
+class Env:
+    """One rank's CUDA context for the run: device, the stream every launch and event goes to, the process group."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a B200: the CUDA path has no CPU fallback")
+        torch.cuda.set_device(self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+        self.dev = torch.device("cuda", self.local_rank)
+        # a dedicated non-default stream: the C ABI treats a NULL stream as "use the ctx's own stream", and
+        # torch.cuda.Event only sees work on the stream it is recorded on -- kernels, L2 flush and events share this one
+        self.stream = torch.cuda.Stream(device=self.dev)
+        torch.cuda.set_stream(self.stream)
+        self.sp = self.stream.cuda_stream
+        assert self.sp != 0
+        self.flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=self.dev)
+        self.cores = os.cpu_count() or 1
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+
+    def max_over_ranks(self, vals):
+        if self.world == 1:
+            return list(vals)
+        t = self.torch.tensor(list(vals), dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t.tolist()
+
+    def close(self):
+        if self.world > 1:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def timed_device_loop(env, batch, step, steps, flush=True):
+    """K device-resident steps, one CUDA-event pair per step on the launching stream; L2 flushed between steps."""
+    torch = env.torch
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    solve_ms, front_ms = [], []
+    for it in range(steps):
+        if flush:
+            env.flush.fill_(it & 0xFF)             # evict L2 between timed steps
+        ev[it][0].record(env.stream)
+        step(it)
+        ev[it][1].record(env.stream)
+        f, s_ = batch.last_timing()                # waits for this step's last event
+        front_ms.append(f); solve_ms.append(s_)
+    torch.cuda.synchronize()
+    return np.array([a.elapsed_time(b) for a, b in ev]), np.array(front_ms), np.array(solve_ms)
+
+
+def bench_batch(env, args, name, steps, warmup, per_gpu=None, cpu_baseline=False, fifo_steps=0, fifo=False, traj_on_device=False):
+    """One workload on this rank's shard: device-resident loop (`value`), end-to-end loop through wbc_cycle with host buffers
+    (`e2e`), roofline of the solve kernel, statistics gathered over the ranks.  Returns the JSON line (rank 0) or None."""
+    import torch
+    from wbc_quadruped_dob_b200 import api
+    rank, world, dev = env.rank, env.world, env.dev
+    cfg = workload_cfg(name)
     n_cfg = cfg.pop("n")
-    sweep = args.workload == SWEEP
-    per_gpu = args.per_gpu or (n_cfg // 8 if args.workload == "mixed_terrain_1m" else (n_cfg // world if sweep else n_cfg))
-    cores = os.cpu_count() or 1
+    sweep = name == SWEEP
+    per_gpu = per_gpu or (n_cfg // 8 if name == "mixed_terrain_1m" else (n_cfg // world if sweep else n_cfg))
     config = {"workload": "%s: %d DogBot instances per GPU x %d GPU(s), 18-DoF, mode mix %s, pushes=%s, terrain=%s, seed %d" % (
-        args.workload, per_gpu, world, cfg["mode_mix"], cfg["pushes"], cfg["terrain"], cfg["seed"]),
+        name, per_gpu, world, cfg["mode_mix"], cfg["pushes"], cfg["terrain"], cfg["seed"]),
         "instances_per_gpu": per_gpu, "global_batch": per_gpu * world, "parallelism": "shard%d" % world,
         "l2": "flushed between timed steps (256 MiB write)",
-        "dispatch": "fifo" if args.fifo else "longest-first, predicted from each instance's previous cycle (results are order-independent)", "solver": "DENSE-AUL/QQP restatement, reference settings (1e-2, 1e4, 5)"}
-
-    if args.impl == "reference":
-        if rank != 0:
-            return 0
-        sc = S.push_sweep(n=min(per_gpu, 4096)) if sweep else S.make(per_gpu, start=0, **cfg)
-        sample = per_gpu if (cores >= 16 or per_gpu <= 1024) else 1024
-        sample = min(sample, 4096)
-        kind, tot, times = cpu_reference_run(sc, args.steps, args.warmup, sample, cores)
-        val = sample * args.steps / tot
-        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
-                "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind,
-                                 "sample": "first %d instances of the workload per step, all %d host threads" % (sample, cores)},
-                "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-        print(json.dumps(line))
-        return 0
-
-    import torch
-    import torch.distributed as dist
-    from wbc_quadruped_dob_b200 import api
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a B200: the CUDA path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    dev = torch.device("cuda", local_rank)
-
+        "dispatch": "fifo" if fifo else "longest-first, predicted from each instance's previous cycle (results are order-independent)",
+        "solver": "DENSE-AUL/QQP restatement, reference settings (1e-2, 1e4, 5)"}
     lo, hi = sharding.shard_range(per_gpu * world, rank, world)
     n = hi - lo
     sc = S.push_sweep(n=n, start=lo) if sweep else S.make(n, start=lo, **cfg)
-    grid = sc.pop("grid", None)
-    batch = api.WbcBatch(max_batch=n, device=local_rank)
-    batch.fifo_dispatch = args.fifo
+    sc.pop("grid", None)
+    batch = api.WbcBatch(max_batch=n, device=env.local_rank)
+    batch.fifo_dispatch = fifo
     batch.set_observer_state(sc["obs_yd"], sc["obs_yw"])
     dev_in = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in sc.items() if isinstance(v, np.ndarray)}
     dev_out = {"tau": torch.zeros(12, n, dtype=torch.float64, device=dev), "w": torch.zeros(6, n, dtype=torch.float64, device=dev)}
     stat_out = dict(dev_out)
     stat_out.update(status=torch.zeros(n, dtype=torch.int32, device=dev), qp_info=torch.zeros(8, n, dtype=torch.int32, device=dev),
                     qp_flops=torch.zeros(n, dtype=torch.float64, device=dev))
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    # a dedicated non-default stream: the C ABI treats a NULL stream as "use the ctx's own stream", and
-    # torch.cuda.Event only sees work on the stream it is recorded on -- kernels, L2 flush and events share this one
-    stream = torch.cuda.Stream(device=dev)
-    torch.cuda.set_stream(stream)
-    sp = stream.cuda_stream
-    assert sp != 0
-
+    sp = env.sp
     if sweep:
         # closed loop: the plant needs the commanded forces x[18:30] every cycle; observer gain per instance
         dev_out["x"] = torch.zeros(30, n, dtype=torch.float64, device=dev)
@@ -281,50 +318,52 @@ def main():
             batch.plant_step(dev_in["base_pos"], dev_in["base_vel"], dev_in["push"], foot_force=dev_in["foot_force"], x=outs["x"], n=n, ld=n,
                              stream=sp, sync=False)
 
-    for it in range(args.warmup):
-        step(stat_out if it == args.warmup - 1 else dev_out)
+    for it in range(warmup):
+        step(stat_out if it == warmup - 1 else dev_out)
     torch.cuda.synchronize()
+    occ, smem, grid_ctas = batch.solver_shape()
+    config["solver_launch"] = "%d persistent one-warp CTAs (up to %d resident per SM; %d B of shared memory per solve), %s" % (
+        grid_ctas, occ, smem, "stage tasks with SM roles" if os.environ.get("WBC_SOLVER", "") == "staged" else "one warp per solve")
     status = stat_out["status"].cpu().numpy()
     qp_info = stat_out["qp_info"].cpu().numpy()
     qp_flops = stat_out["qp_flops"].cpu().numpy()
     dfma_peak = batch.measure_dfma_peak()
 
-    # ---- timed region: K steps, device-resident, one CUDA-event pair per step on the launching stream
-    sampler = ClockSampler(local_rank)
+    # ---- timed region: K steps, device-resident
+    sampler = ClockSampler(env.local_rank)
     sampler.start()
-    if world > 1:
-        dist.barrier()
+    env.barrier()
     torch.cuda.synchronize()
     t_wall0 = time.perf_counter()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    solve_ms, front_ms = [], []
-    for it in range(args.steps):
-        flush.fill_(it & 0xFF)                     # evict L2 between timed steps
-        ev[it][0].record(stream)
-        step(dev_out)
-        ev[it][1].record(stream)
-        f, s_ = batch.last_timing()                # waits for this step's last event
-        front_ms.append(f); solve_ms.append(s_)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
+    step_ms, front_ms, solve_ms = timed_device_loop(env, batch, lambda it: step(dev_out), steps)
+    env.barrier()
     t_wall = time.perf_counter() - t_wall0
-    step_ms = np.array([a.elapsed_time(b) for a, b in ev])
     tot_ms = float(step_ms.sum())
-    launches = (3 if sweep else 2) * args.steps
+    launches = (3 if sweep else 2) * steps
     sweep_stats = None
     if sweep:
         # how far the observer got after warmup + steps closed-loop cycles, per gain (rank 0's shard)
         w_now = dev_out["w"].cpu().numpy()
         rel = np.abs(w_now - sc["push"]).max(axis=0) / np.abs(sc["push"]).max(axis=0)
-        sweep_stats = {"cycles": args.warmup + args.steps, "sim_time_s": (args.warmup + args.steps) * 0.0025,
+        sweep_stats = {"cycles": warmup + steps, "sim_time_s": (warmup + steps) * 0.0025,
                        "w_rel_err_by_gain": {str(g): float(rel[sc["obs_gain"] == g].max()) for g in np.unique(sc["obs_gain"])},
                        "max_abs_base_lin_vel": float(dev_in["base_vel"][:3].abs().max().item())}
 
-    # ---- e2e: host buffers through the C ABI (H2D + kernels + D2H inside the timed region)
-    e2e_steps = args.steps
-    want = ("x",) if sweep else ()
+    # ---- the same loop with index-order dispatch (how much the longest-first order is worth on this workload)
+    fifo_ms = None
+    if fifo_steps > 0 and not fifo and not sweep:
+        batch.fifo_dispatch = True
+        batch.set_observer_state(sc["obs_yd"], sc["obs_yw"])
+        for it in range(warmup):
+            step(dev_out)
+        torch.cuda.synchronize()
+        fm, _, _ = timed_device_loop(env, batch, lambda it: step(dev_out), fifo_steps)
+        fifo_ms = float(fm.sum()) / fifo_steps
+        batch.fifo_dispatch = False
 
+    # ---- e2e: host buffers through the C ABI (H2D + kernels + D2H inside the timed region)
+    e2e_steps = steps
+    want = ("x",) if sweep else ()
     # the caller's arrays live in page-locked host memory (wbc_host_alloc), as a controller process feeding the
     # batch every cycle would keep them: wbc_cycle then DMAs them directly (pageable arrays take its bounce buffer)
     sc_host = batch.pinned_inputs(sc)
@@ -334,9 +373,8 @@ def main():
     out_pin = {"tau": batch.pinned((12, n)), "w": batch.pinned((6, n))}
     if sweep:
         out_pin["x"] = batch.pinned((30, n))
-
     traj = None
-    if args.traj_on_device and not sweep:
+    if traj_on_device and not sweep:
         # a plan whose splines start at the scenario's desired pose; sampled at t = 0 it reproduces the workload's inputs
         traj = S.make_trajectory(sc, nseg=3, seed=11, match_acc=True)
         batch.set_trajectory(traj)
@@ -354,10 +392,9 @@ def main():
     # same observer trajectory as the device-resident loop: the estimate feeds back into the QP (main.cpp:1032), so the
     # work per cycle drifts as the observer integrates; both loops start from the scenario's initial observer state
     batch.set_observer_state(sc["obs_yd"], sc["obs_yw"])
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         e2e_step()
-    if world > 1:
-        dist.barrier()
+    env.barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         out_host = e2e_step()
@@ -366,16 +403,14 @@ def main():
     assert np.isfinite(out_host["tau"]).all()
 
     # ---- max over ranks, statistics gather (the only collective)
-    if world > 1:
-        t = torch.tensor([tot_ms, e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        tot_ms, e2e_s = t.tolist()
-    stats = sharding.gather_stats(sharding.local_stats(n, status, qp_info, qp_flops, ms=tot_ms / args.steps), device=dev)
+    tot_ms, e2e_s = env.max_over_ranks([tot_ms, e2e_s])
+    if fifo_ms is not None:
+        fifo_ms = env.max_over_ranks([fifo_ms])[0]
+    stats = sharding.gather_stats(sharding.local_stats(n, status, qp_info, qp_flops, ms=tot_ms / steps), device=dev)
     total_inst = per_gpu * world
-    scaling = "strong" if sweep else "weak"
-    value = total_inst * args.steps / (tot_ms * 1e-3)
+    value = total_inst * steps / (tot_ms * 1e-3)
     e2e_val = total_inst * e2e_steps / e2e_s
-
+    line = None
     if rank == 0:
         solve_avg_ms = float(np.mean(solve_ms))
         flops_launch = float(qp_flops.sum())
@@ -387,41 +422,121 @@ def main():
         except Exception:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        hbm_ach = n * (IN_BYTES + OUT_BYTES) / (float(np.mean(step_ms)) * 1e-3) / 1e9
+        alg_bytes = algorithmic_bytes(sc["mode"], sc.get("terrain") is not None)
+        hbm_ach = alg_bytes / (float(np.mean(step_ms)) * 1e-3) / 1e9
         traffic, traffic_src = None, None
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(args.workload)
+            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(name)
             if tr and per_gpu == n_cfg:
                 traffic, traffic_src = tr["bytes_per_launch"], tr["source"]
         except Exception:
             pass
-        roofline = {"bound": "fp64", "kernel": "wbc_solve_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+        roofline = {"bound": "fp64", "kernel": "wbc_solve_staged_kernel" if os.environ.get("WBC_SOLVER", "") == "staged" else "wbc_solve_kernel",
+                    "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                     "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write)", "traffic_source": traffic_src,
-                    "algorithmic_bytes_per_launch": n * (8 * 528 + OUT_BYTES),
+                    "algorithmic_bytes_per_launch": alg_bytes,
+                    "algorithmic_bytes_note": "SURVEY 8(d): 1024 B per solve, +144 B per swing solve, +320 B with terrain frames",
+                    "intermediate_bytes_per_launch": n * 8 * QPREC_DOUBLES,
+                    "intermediate_note": "front kernel -> solver QP record (%d doubles per solve), written once and read once; not algorithmic traffic" % QPREC_DOUBLES,
                     "peak_source": "own DFMA microbenchmark in this process (MEASURED_PEAKS.json has no FP64 figure)",
                     "flops_per_solve": flops_launch / n, "kernel_ms": solve_avg_ms, "front_kernel_ms": float(np.mean(front_ms)),
+                    "resident_solver_warps_per_sm": occ,
                     "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
                             "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}}
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": tot_ms / args.steps, "p50_ms": float(np.median(step_ms)), "higher_is_better": True, "scaling": scaling,
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+                "ms_per_step": tot_ms / steps, "p50_ms": float(np.median(step_ms)), "higher_is_better": True, "scaling": "strong" if sweep else "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks,
-                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": n * (IN_BYTES - (36 * 8 if args.traj_on_device and not sweep else 0) + (8 + 57 * 8 if sweep else 0)),
+                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": n * (IN_BYTES - (36 * 8 if traj_on_device and not sweep else 0) + (8 + 57 * 8 if sweep else 0)),
                         "d2h_bytes_per_step": n * (OUT_BYTES + (30 * 8 + 21 * 8 if sweep else 0))},
-                "gpu_launches": launches, "e2e_gpu_launches": (3 if (sweep or (args.traj_on_device and not sweep)) else 2) * e2e_steps, "roofline": roofline,
+                "gpu_launches": launches, "e2e_gpu_launches": (3 if (sweep or (traj_on_device and not sweep)) else 2) * e2e_steps, "roofline": roofline,
                 "stats": {"solver_failures": stats["solver_failures"], "mean_ncholesky": stats["sum_ncholesky"] / total_inst,
                           "mean_outer_its": stats["sum_outer_its"] / total_inst, "max_kkt_dim": stats["max_kkt_dim"],
                           "wall_s_timed_region": t_wall}}
+        if fifo_ms is not None:
+            line["value_fifo"] = total_inst / (fifo_ms * 1e-3)
+            line["dispatch_gain"] = line["value"] / line["value_fifo"]
+            line["value_fifo_note"] = "same workload and state, index-order work queue (WBC_FIFO_DISPATCH), %d steps; the timed loop replays one " \
+                                      "state, so each solve's previous cost predicts this one exactly -- see --workload %s for a state that moves" % (fifo_steps, ROLLOUT)
         if sweep_stats:
             line["stats"]["sweep"] = sweep_stats
-        if world == 1 and not args.no_cpu_baseline:
-            kind, tot, _ = cpu_reference_run(sc, 1, 0, min(n, 4096), cores)
-            line["cpu_baseline"] = {"value": min(n, 4096) / tot, "unit": UNIT, "cores": cores, "kind": kind,
-                                    "sample": "one pass over the first %d instances of the workload, all %d host threads" % (min(n, 4096), cores)}
-        print(json.dumps(line))
+        if world == 1 and cpu_baseline:
+            kind, tot, _ = cpu_reference_run(sc, 1, 0, min(n, 4096), env.cores)
+            line["cpu_baseline"] = {"value": min(n, 4096) / tot, "unit": UNIT, "cores": env.cores, "kind": kind,
+                                    "sample": "one pass over the first %d instances of the workload, all %d host threads" % (min(n, 4096), env.cores)}
     batch.close()
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    del dev_in, dev_out, stat_out
+    torch.cuda.empty_cache()
+    return line
+
+
+ALSO = ("trot_65536", "mixed_terrain_1m")      # the other batch configs of BASELINE.json, timed in the same run for a few steps
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.workload == REPLAY:
+        if args.impl == "reference":
+            args.no_cpu_baseline = False
+        return single_robot_replay(args) if rank == 0 else 0
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        return reference_arm(args, world)
+    env = Env(args)
+    if args.workload == ROLLOUT:
+        from bench_rollout import bench_trot_rollout
+        line = bench_trot_rollout(env, args)
+    elif args.workload == SWEEP:
+        from bench_rollout import bench_push_sweep
+        line = bench_push_sweep(env, args)
+    else:
+        line = bench_batch(env, args, args.workload, args.steps, args.warmup, per_gpu=args.per_gpu, cpu_baseline=not args.no_cpu_baseline,
+                           fifo_steps=0 if (args.no_also or args.fifo) else min(args.steps, 10), fifo=args.fifo, traj_on_device=args.traj_on_device)
+        if args.workload == "standing_4096" and not args.no_also and not args.fifo and args.per_gpu is None:
+            also = {}
+            for name in ALSO:
+                l2 = bench_batch(env, args, name, min(args.steps, 5), 3, fifo_steps=min(args.steps, 3))
+                if l2 is not None:
+                    also[name] = {k: l2[k] for k in ("value", "unit", "ms_per_step", "p50_ms", "steps", "warmup", "e2e", "stats", "value_fifo", "dispatch_gain") if k in l2}
+                    also[name]["workload"] = l2["config"]["workload"]
+                    also[name]["instances_per_gpu"] = l2["config"]["instances_per_gpu"]
+                    also[name]["roofline"] = {k: l2["roofline"][k] for k in ("achieved", "peak", "unit", "frac", "kernel_ms", "front_kernel_ms", "flops_per_solve", "algorithmic_bytes_per_launch")}
+                    also[name]["clocks"] = l2["clocks"]
+            if line is not None:
+                line["also"] = also
+                line["also_note"] = "BASELINE.json configs[2] and configs[3] (131072 instances per GPU = 1048576 on 8 GPUs) timed in the same run, same method, fewer steps"
+    if rank == 0 and line is not None:
+        print(json.dumps(line))
+    env.close()
+    return 0
+
+
+def reference_arm(args, world):
+    cfg = workload_cfg(args.workload if args.workload != ROLLOUT else "standing_4096")
+    n_cfg = cfg.pop("n")
+    sweep = args.workload == SWEEP
+    per_gpu = args.per_gpu or (n_cfg // 8 if args.workload == "mixed_terrain_1m" else (n_cfg // world if sweep else n_cfg))
+    cores = os.cpu_count() or 1
+    config = {"workload": "%s: %d DogBot instances per GPU x %d GPU(s), 18-DoF, mode mix %s, pushes=%s, terrain=%s, seed %d" % (
+        args.workload, per_gpu, world, cfg["mode_mix"], cfg["pushes"], cfg["terrain"], cfg["seed"]),
+        "instances_per_gpu": per_gpu, "global_batch": per_gpu * world, "parallelism": "shard%d" % world,
+        "l2": "flushed between timed steps (256 MiB write)",
+        "dispatch": "fifo" if args.fifo else "longest-first, predicted from each instance's previous cycle (results are order-independent)",
+        "solver": "DENSE-AUL/QQP restatement, reference settings (1e-2, 1e4, 5)"}
+    sc = S.push_sweep(n=min(per_gpu, 4096)) if sweep else S.make(per_gpu, start=0, **cfg)
+    sample = per_gpu if (cores >= 16 or per_gpu <= 1024) else 1024
+    sample = min(sample, 4096)
+    kind, tot, times = cpu_reference_run(sc, args.steps, args.warmup, sample, cores)
+    val = sample * args.steps / tot
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind,
+                             "sample": "first %d instances of the workload per step, all %d host threads" % (sample, cores)},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
     return 0
 
 

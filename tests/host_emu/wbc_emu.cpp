@@ -52,7 +52,10 @@ int emu_cycle(const Params* P, const EmuIO* io, int n)
         assemble_qp<LDH>(ex, *P, rec.data(), sh, W_H(ew.w), W_EXB(ew.w), W_C(ew.w));
         Stats s;
         double xs[30];
-        solve_denseaul(ex, ew.w, cfg, sh.nrows, sh.neq, s);
+        // WBC_EMU_STAGED=1: the three resumable stages the control cycle's solver kernel hands from warp to warp, with the
+        // state going through the solve's global block between them (must reproduce solve_denseaul bit for bit)
+        if (getenv("WBC_EMU_STAGED") && atoi(getenv("WBC_EMU_STAGED"))) solve_staged(ex, ew.w, cfg, sh.nrows, sh.neq, s);
+        else solve_denseaul(ex, ew.w, cfg, sh.nrows, sh.neq, s);
         memcpy(xs, W_XS(ew.w), sizeof(xs));
         if (s.termination != 2) memset(xs, 0, sizeof(xs));
         torque_and_objective(ex, *P, rec.data(), sh, xs, io->tau + i, io->ld, io->qp_obj ? io->qp_obj + i : nullptr);

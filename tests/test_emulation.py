@@ -93,3 +93,15 @@ def test_multiplier_update_cache_is_exact(emu):
         assert np.array_equal(a[k], b[k]), k
     assert np.array_equal(a["qp_info"][0], b["qp_info"][0])
     assert np.mean((a["qp_info"][5] & 64) != 0) > 0.9 and not ((b["qp_info"][5] & 64) != 0).any()
+
+
+def test_staged_solver_reproduces_the_monolithic_one(emu, monkeypatch):
+    """solve_stage_setup / _qloop / _update (the stages the solver kernel hands from warp to warp, state through the solve's
+    global block) against solve_denseaul on the same instances: every output bit for bit, same counters."""
+    sc = S.make(300, mode_mix=(0.34, 0.33, 0.33), pushes=True, terrain=True, seed=2468)
+    a = emu.cycle(sc)
+    monkeypatch.setenv("WBC_EMU_STAGED", "1")
+    b = emu.cycle(sc)
+    for k in ("tau", "w", "x", "qp_obj", "status"):
+        assert np.array_equal(a[k], b[k]), k
+    assert np.array_equal(a["qp_info"], b["qp_info"])

@@ -72,13 +72,20 @@ int main()
     run<512, 1>("same", out, cyc, 1);
     run<1024, 1>("same", out, cyc, 1);
     run<2048, 1>("same", out, cyc, 1);
+    run<2560, 1>("same", out, cyc, 1);
+    run<3072, 1>("same", out, cyc, 1);
+    run<3584, 1>("same", out, cyc, 1);
     run<4096, 1>("same", out, cyc, 1);
     run<6144, 1>("same", out, cyc, 1);
     run<8192, 1>("same", out, cyc, 1);
     run<12288, 1>("same", out, cyc, 1);
     run<16384, 1>("same", out, cyc, 1);
     run<256, 8>("diff", out, cyc, 8);
+    run<320, 8>("diff", out, cyc, 8);
+    run<384, 8>("diff", out, cyc, 8);
+    run<448, 8>("diff", out, cyc, 8);
     run<512, 8>("diff", out, cyc, 8);
+    run<768, 8>("diff", out, cyc, 8);
     run<1024, 8>("diff", out, cyc, 8);
     run<2048, 8>("diff", out, cyc, 8);
     return 0;

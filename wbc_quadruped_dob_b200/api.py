@@ -75,7 +75,7 @@ _lib = None
 
 EXPORTS = ["wbc_default_params", "wbc_last_error", "wbc_version", "wbc_create", "wbc_destroy", "wbc_set_params",
            "wbc_set_observer_state", "wbc_get_observer_state", "wbc_cycle", "wbc_debug_update", "wbc_qp_solve",
-           "wbc_plant_step", "wbc_last_timing", "wbc_last_solve_cycles", "wbc_last_launches", "wbc_solver_shape", "wbc_host_alloc",
+           "wbc_plant_step", "wbc_last_timing", "wbc_last_solve_cycles", "wbc_last_launches", "wbc_solver_shape", "wbc_stage_profile", "wbc_host_alloc",
            "wbc_host_free",
            "wbc_set_trajectory", "wbc_sample_trajectory",
            "wbc_measure_dfma_peak"]
@@ -115,6 +115,7 @@ def load():
     lib.wbc_last_solve_cycles.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_ulonglong)]
     lib.wbc_last_launches.argtypes = [C.c_void_p]
     lib.wbc_solver_shape.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.wbc_stage_profile.argtypes = [C.c_void_p, C.POINTER(C.c_ulonglong), C.c_int]
     lib.wbc_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
     lib.wbc_host_free.argtypes = [C.c_void_p]
     lib.wbc_set_trajectory.argtypes = [C.c_void_p, C.c_int, C.POINTER(_Trajectory), C.c_void_p, C.c_uint]
@@ -396,6 +397,14 @@ class WbcBatch:
         a, b, g = C.c_int(0), C.c_int(0), C.c_int(0)
         _check(self.lib.wbc_solver_shape(self.h, C.byref(a), C.byref(b), C.byref(g)), "wbc_solver_shape")
         return a.value, b.value, g.value
+
+    def stage_profile(self):
+        """Per-warp counters of the last staged solver launch (ctx created with WBC_STAGE_PROF=1): array [warps, 12]."""
+        _, _, g = self.solver_shape()
+        a = np.zeros((g, 12), dtype=np.uint64)
+        rows = self.lib.wbc_stage_profile(self.h, a.ctypes.data_as(C.POINTER(C.c_ulonglong)), g)
+        _check(min(rows, 0), "wbc_stage_profile")
+        return a[:rows]
 
     def measure_dfma_peak(self):
         v = C.c_double(0)

@@ -177,6 +177,7 @@ __device__ __noinline__ bool chol_build30(double diagA, double rsB, unsigned fma
     if (l < NICCAP) rs[l] = rsB;
     __syncwarp();
     const int c = l;
+    const int cr = l < NMAIN ? l : NMAIN - 1;              // lanes 30, 31 shadow row 29 (they never store)
 #pragma unroll 1
     for (int k = 0; k < NMAIN; k += 2) {
         // dot products of row c with rows k and k + 1 over the finished columns, one pair-row per step
@@ -184,7 +185,7 @@ __device__ __noinline__ bool chol_build30(double diagA, double rsB, unsigned fma
         double* zq = Z;                                      // zq + 2 r = the word of row r in pair-row q:  Z + zt_base(q) - 4 q
 #pragma unroll 1
         for (int q = 0; 2 * q < k; q++) {
-            const double2 z0 = ld2(zq + 2 * c), zk = ld2(zq + 2 * k), zk1 = ld2(zq + 2 * k + 2);
+            const double2 z0 = ld2(zq + 2 * cr), zk = ld2(zq + 2 * k), zk1 = ld2(zq + 2 * k + 2);
             p0 += z0.x * zk.x; q0 += z0.y * zk.y;
             p1 += z0.x * zk1.x; q1 += z0.y * zk1.y;
             zq += 56 - 4 * q;                                // zt_base(q + 1) - 4 (q + 1) - (zt_base(q) - 4 q)
@@ -411,7 +412,7 @@ __device__ __noinline__ int step_and_move(double dA, double dB, double exbA, dou
     double* xs = wbc_smem + sl::OFF_XC;
     const double* sp = wbc_smem + sl::OFF_SP;
     const double d1 = sp[4], d2 = sp[5], stpmax = sp[6];
-    double xcA = xs[l], xcB = (l < nic) ? xs[NMAIN + l] : 0.0;
+    double xcA = xs[l < NMAIN ? l : 0], xcB = (l < nic) ? xs[NMAIN + l] : 0.0;
     double stp, a0 = 0.0, a1 = 0.0, a2 = 0.0;
     bool needact;
     int addcnt;
@@ -588,6 +589,7 @@ __device__ __noinline__ int qqp_optimize_fast(const Work w, int nic, double rho,
             const double beta = brst ? 0.0 : ddiv(v, vv);
             const double dA = vA ? -cgA + beta * dpA : 0.0;
             const double dB = (vB && !act) ? -cgB + beta * dpB : 0.0;
+            __syncwarp();                               // the product above read (and dropped) a few entries of this vector as the tail of x
             if (vA) sdc[l] = dA;
             if (vB) sdc[NMAIN + l] = dB;
             __syncwarp();

@@ -142,13 +142,19 @@ constexpr int MC_GRINV = 1496;      // [40]
 constexpr int MC_G = 1536;          // [648]
 constexpr int MC_INT = 2184;        // ints: act[40] | dep[40] | ka, version, ndep
 constexpr int MC_TOTAL = 2240;
-constexpr long OFF_KKT = OFF_MC + MC_TOTAL;
-constexpr long TOTAL = ((OFF_KKT + 2L * NQMAX * (NQMAX + 1) + 15) / 16) * 16;
+// State of a solve that is handed from stage to stage (solve_stage_* below): the SolveState header and the point exxc.
+constexpr long OFF_HDR = OFF_MC + MC_TOTAL;                      // [32] header | [104] exxc
+constexpr int HDR_DOUBLES = 32;
+constexpr long TOTAL = ((OFF_HDR + HDR_DOUBLES + 104 + 15) / 16) * 16;
+// The literal multiplier update's stacked KKT matrix is not part of the block: 2 NQMAX (NQMAX + 1) doubles (580 KB) that
+// only the 0.25 % of solves which fall back to it ever touch -- one per resident warp (Work::kkt), not one per solve in flight.
+constexpr long KKT_DOUBLES = ((2L * NQMAX * (NQMAX + 1) + 15) / 16) * 16;
 }  // namespace gl
 
 // All storage of one instance: the CTA's shared memory (device) and one global scratch block.
 struct Work {
-    double* g;      // global scratch of this warp
+    double* g;      // global scratch block of the solve (gl::TOTAL doubles)
+    double* kkt;    // global scratch of this warp for the literal multiplier update (gl::KKT_DOUBLES doubles)
     double* sm;     // host emulation only: heap stand-in for the shared memory block
 };
 #if defined(__CUDACC__)
@@ -1153,7 +1159,7 @@ template <class Ex>
 WBC_HDNI void update_lagrange_multipliers_literal(const Ex ex, const Work w, int nec, int nic, double* flops_io)
 {
     const int ntotal = NMAIN + nic, ktotal = nec + nic, nq = ntotal + ktotal, ld = nq + 1;
-    double* M = w.g + gl::OFF_KKT;
+    double* M = w.kkt;
     double* sv0 = w.g + gl::OFF_SV0;
     double* v = w.g + gl::OFF_QRV;
     const double* A = W_A(w);
@@ -2100,6 +2106,189 @@ WBC_HDN void solve_denseaul(const Ex& ex, const Work& w, const Settings& cfg, in
     for (int i = ex.lane(); i < NMAIN; i += Ex::NL) W_XS(w)[i] = W_SC(w)[i] * exxc[i] + 0.0;
     ex.sync();
     st.termination = 2;
+}
+
+// ------------------------------------------------------------------------------------------------
+// The same solver as three resumable stages.  solve_denseaul above runs a solve from start to finish on one warp; the
+// control cycle's solver kernel (wbc_b200.cu) instead hands a solve from warp to warp at the two points where the code it
+// executes changes completely, so that every SM runs one kind of stage and its instruction cache holds it:
+//     SETUP   set-up of the scaled problem                          (solve_stage_setup;  caller assembled Q, c, L)
+//     QLOOP   one outer iteration's model / QQP / working-set loop  (solve_stage_qloop)
+//     UPDATE  multiplier update, feasibility, penalty update        (solve_stage_update; sets `done` on the last one)
+// Everything a later stage needs is already in the solve's global scratch block (C, A, the factor of A, multipliers,
+// working-set bookkeeping, the multiplier-update cache) except the point exxc and a few scalars: SolveState, kept at
+// gl::OFF_HDR.  Same routines in the same order on the same operands as solve_denseaul: results are bit-identical
+// (tests/test_emulation.py runs both on the host; tools/gpu_dump.py on the device).
+struct SolveState {
+    double rho, epsx, feaserr, flops;
+    int nrows, nec, nicwork, allowevict, have_factor, goodcounter, stagnationcounter, outeridx;
+    int version;                        // working-set version (keys the multiplier-update cache)
+    int termination, ncholesky, outer_its, qqp_calls, kkt_dim_max, chol_reused, flags;
+    int done;                           // the solve is complete: result in W_XS, termination set
+    int pad_;
+};
+static_assert(sizeof(SolveState) <= gl::HDR_DOUBLES * sizeof(double), "SolveState fits its header slot");
+
+template <class Ex>
+WBC_HDN void stage_store(const Ex& ex, const Work& w, const SolveState& s)
+{
+    double* hx = w.g + gl::OFF_HDR + gl::HDR_DOUBLES;
+    const double* exxc = W_EXXC(w);
+    const int n = NMAIN + (s.nrows - s.nec);
+#pragma unroll 1
+    for (int i = ex.lane(); i < n; i += Ex::NL) hx[i] = exxc[i];
+    if (ex.lane() == 0) {
+        SolveState t = s;
+        t.version = W_ISCR(w)[6];
+        *reinterpret_cast<SolveState*>(w.g + gl::OFF_HDR) = t;
+    }
+    ex.sync();
+}
+template <class Ex>
+WBC_HDN void stage_load(const Ex& ex, const Work& w, SolveState& s)
+{
+    s = *reinterpret_cast<const SolveState*>(w.g + gl::OFF_HDR);
+    const double* hx = w.g + gl::OFF_HDR + gl::HDR_DOUBLES;
+    double* exxc = W_EXXC(w);
+    const int n = NMAIN + (s.nrows - s.nec);
+#pragma unroll 1
+    for (int i = ex.lane(); i < n; i += Ex::NL) exxc[i] = hx[i];
+    if (ex.lane() == 0) W_ISCR(w)[6] = s.version;
+    ex.sync();
+}
+WBC_HD void stage_stats(const SolveState& s, Stats& st)
+{
+    st.termination = s.termination; st.ncholesky = s.ncholesky; st.outer_its = s.outer_its; st.qqp_calls = s.qqp_calls;
+    st.nicwork = s.nicwork; st.kkt_dim_max = s.kkt_dim_max; st.chol_reused = s.chol_reused; st.flags = s.flags; st.flops = s.flops;
+}
+
+// SETUP.  On entry the warp has staged the problem (see setup_problem).  Leaves the state of the first outer iteration.
+template <class Ex>
+WBC_HDN void solve_stage_setup(const Ex& ex, const Work& w, const Settings& cfg, int nrows, int neq, SolveState& s)
+{
+    const int nec = neq, nictotal = nrows - neq;
+    s.nrows = nrows; s.nec = nec;
+    s.termination = 0; s.ncholesky = 0; s.outer_its = 0; s.qqp_calls = 0; s.nicwork = 0;
+    s.kkt_dim_max = 0; s.chol_reused = 0; s.flags = 0; s.flops = 0.0; s.done = 0; s.pad_ = 0; s.version = 0;
+    s.goodcounter = 0; s.stagnationcounter = 0; s.outeridx = 0; s.allowevict = 1; s.have_factor = 0;
+    s.rho = cfg.rho; s.epsx = cfg.epsx; s.feaserr = 1.7976931348623157e308;
+    int pd = 0;
+    const int rc = setup_problem(ex, w, nrows, &pd, cfg.dup_start[0], cfg.dup_count[0], cfg.dup_start[1], cfg.dup_count[1]);
+    if (rc != 0) { s.termination = rc; s.done = 1; return; }
+    s.flops += 2.0 * nrows * NMAIN * NMAIN + 9000.0;
+    if (ex.lane() == 0) {
+        W_ISCR(w)[6] = 0;
+        reinterpret_cast<int*>(w.g + gl::OFF_MC + gl::MC_INT)[80] = -1;
+    }
+    ex.sync();
+    int nicwork = 0;
+    if (!pd) { nicwork = nictotal; s.allowevict = 0; s.flags |= 1; }
+    s.have_factor = pd != 0;
+    s.nicwork = nicwork;
+    double* nulc = W_NULC(w);
+    double* exxc = W_EXXC(w);
+#pragma unroll 1
+    for (int i = ex.lane(); i < nictotal; i += Ex::NL) W_NICNACT(w)[i] = (i < nicwork) ? 1 : 0;
+#pragma unroll 1
+    for (int i = ex.lane(); i < nrows; i += Ex::NL) nulc[i] = 0.0;
+#pragma unroll 1
+    for (int i = ex.lane(); i < NMAIN + nictotal; i += Ex::NL) exxc[i] = 0.0;
+    ex.sync();
+    if (s.epsx <= 0.0) s.epsx = 1.0e-9;
+}
+
+// QLOOP of outer iteration s.outeridx.
+template <class Ex>
+WBC_HDN void solve_stage_qloop(const Ex& ex, const Work& w, SolveState& s)
+{
+    const int nec = s.nec, nictotal = s.nrows - s.nec;
+    int nicwork = s.nicwork;
+    s.outer_its++;
+    bool extended;
+    do {
+        int term;
+        if (nicwork > NICCAP || nec * LDH + 48 > sl::STAGE_EQ_CAP) { s.flags |= 32; term = model_and_qqp<true>(ex, w, nec, nicwork, s.rho, s.epsx, &s.ncholesky, &s.flops); }
+#if defined(__CUDA_ARCH__)
+        else term = model_and_qqp_dev(ex, w, nec, nicwork, s.rho, s.epsx, &s.ncholesky, &s.flops, &s.chol_reused);
+#else
+        else term = model_and_qqp<false>(ex, w, nec, nicwork, s.rho, s.epsx, &s.ncholesky, &s.flops);
+#endif
+        s.qqp_calls++;
+        if (term == -4) s.flags |= 4;
+        inequality_violations(ex, w, nec, nictotal);
+        s.flops += 2.0 * nictotal * NMAIN;
+        update_working_set(ex, w, nec, nictotal, nicwork, s.allowevict);
+        nicwork = W_ISCR(w)[1];
+        extended = W_ISCR(w)[2] != 0;
+        ex.sync();
+    } while (extended);
+    s.nicwork = nicwork;
+}
+
+// UPDATE of outer iteration s.outeridx; on the last one the unscaled solution is left in W_XS and s.done is set.
+template <class Ex>
+WBC_HDN void solve_stage_update(const Ex& ex, const Work& w, const Settings& cfg, SolveState& s)
+{
+    const int nec = s.nec, nicwork = s.nicwork;
+    const int kwork = nec + nicwork;
+    double* nulc = W_NULC(w);
+    double* nulcest = W_NULCEST(w);
+    const double* exxc = W_EXXC(w);
+#pragma unroll 1
+    for (int i = ex.lane(); i < kwork; i += Ex::NL) nulcest[i] = nulc[i];
+    ex.sync();
+    {
+        const int nq = NMAIN + nicwork + kwork;
+        if (nq > s.kkt_dim_max) s.kkt_dim_max = nq;
+        bool done = false;
+        if (cfg.kkt_mode == 1 && s.have_factor)
+            done = update_lagrange_multipliers_reduced(ex, w, nec, nicwork, cfg.kkt_pivtol, &s.flags, &s.flops);
+        if (!done) {
+            s.flags |= 8;
+#pragma unroll 1
+            for (int i = ex.lane(); i < kwork; i += Ex::NL) nulcest[i] = nulc[i];
+            ex.sync();
+            update_lagrange_multipliers_literal(ex, w, nec, nicwork, &s.flops);
+        }
+    }
+    const double maxrho = 1.0e12, requestedfeasdecrease = 0.33;
+    const double feaserrprev = s.feaserr;
+    s.feaserr = sqrt(feasibility_error(ex, w, nec, kwork));
+    ex.sync();
+    s.flops += 4.0 * kwork * NMAIN;
+    if (s.feaserr < s.epsx) s.goodcounter++; else s.goodcounter = 0;
+    if (s.feaserr > feaserrprev * requestedfeasdecrease) s.stagnationcounter++; else s.stagnationcounter = 0;
+    bool last = s.goodcounter >= 2;
+    if (!last) {
+        if (s.stagnationcounter >= 2) s.rho = fmin(s.rho * 10.0, maxrho);
+        else s.rho = fmin(s.rho * 1.41, maxrho);
+        s.outeridx++;
+        last = s.outeridx >= cfg.outerits;
+    }
+    if (last) {
+#pragma unroll 1
+        for (int i = ex.lane(); i < NMAIN; i += Ex::NL) W_XS(w)[i] = W_SC(w)[i] * exxc[i] + 0.0;
+        ex.sync();
+        s.termination = 2;
+        s.done = 1;
+    }
+}
+
+// The three stages back to back on one executor (the host emulation's check that they reproduce solve_denseaul).
+template <class Ex>
+WBC_HDN void solve_staged(const Ex& ex, const Work& w, const Settings& cfg, int nrows, int neq, Stats& st)
+{
+    SolveState s;
+    solve_stage_setup(ex, w, cfg, nrows, neq, s);
+    while (!s.done) {
+        stage_store(ex, w, s);
+        stage_load(ex, w, s);
+        solve_stage_qloop(ex, w, s);
+        stage_store(ex, w, s);
+        stage_load(ex, w, s);
+        solve_stage_update(ex, w, cfg, s);
+    }
+    stage_stats(s, st);
 }
 
 }  // namespace wbcqp

@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <string.h>
+#include <stddef.h>
 #include <stdlib.h>
 
 #include <new>
@@ -50,11 +51,20 @@ struct DispatchOrder {
 };
 __device__ __forceinline__ int cost_bucket(unsigned cost) { const unsigned b = cost >> 6; return b < ORD_NB ? (int)b : ORD_NB - 1; }
 
+// (stage_reset: the staged solver's queue block and rings, reset here for the solve launch that follows; see StageCtl below)
+struct StageReset { int* ctl; int nctl; int free_tail_index; int free_avail_index; int* ring; int rsize; int nslots; };
+
 __global__ void __launch_bounds__(64) wbc_front_kernel(Params P, DevInputs in, FrontState st, int n, double* __restrict__ recs,
-                                                       double* __restrict__ w_out, long w_ld, DevDebug dbg, int has_dbg, DispatchOrder ord)
+                                                       double* __restrict__ w_out, long w_ld, DevDebug dbg, int has_dbg, DispatchOrder ord,
+                                                       StageReset sr)
 {
     __shared__ int base[ORD_NB];
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (sr.ctl) {
+        const long nth = (long)gridDim.x * blockDim.x;
+        for (long k = i; k < sr.nctl; k += nth) sr.ctl[k] = (k == sr.free_tail_index || k == sr.free_avail_index) ? sr.nslots : 0;
+        for (long k = i; k < 3L * sr.rsize; k += nth) sr.ring[k] = (k >= 2L * sr.rsize && k - 2L * sr.rsize < sr.nslots) ? (int)(k - 2L * sr.rsize) : -1;
+    }
     if (ord.cost) {
         // base[b] = number of instances in costlier buckets: lane l scans buckets 255-8l .. 248-8l
         if (threadIdx.x < 32) {
@@ -103,12 +113,13 @@ __device__ __forceinline__ int next_instance(int* queue)
 }
 
 __global__ void __launch_bounds__(SOLVE_T) wbc_solve_kernel(Params P, int n, const double* __restrict__ recs, SolveOut out,
-                                                            double* __restrict__ scratch_base, int* __restrict__ queue,
+                                                            double* __restrict__ scratch_base, double* __restrict__ kkt_base, int* __restrict__ queue,
                                                             const int* __restrict__ order, unsigned* __restrict__ cost,
                                                             int* __restrict__ hist_next)
 {
     Work w;
     w.g = scratch_base + (long)blockIdx.x * gl::TOTAL;
+    w.kkt = kkt_base + (long)blockIdx.x * gl::KKT_DOUBLES;
     w.sm = nullptr;
     const WarpEx ex;
     Settings cfg;
@@ -190,6 +201,232 @@ __global__ void __launch_bounds__(SOLVE_T) wbc_solve_kernel(Params P, int n, con
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// The solver as a persistent kernel of STAGE TASKS (qp_warp.cuh, solve_stage_*).
+//
+// What bounds wbc_solve_kernel above is instruction supply: its hot code is ~140 KB, an SM's instruction cache holds ~32 KB
+// (tools/ubench/icache.cu), the twelve warps of an SM are in twelve different places of it, and every miss is served by the
+// GPC-level cache at ~4 bytes per cycle and SM -- ncu shows that cache at 80-90 % of its peak request rate and more resident
+// warps buy nothing (profiles/README.md).  Here a solve is not bound to a warp.  It lives in a slot of global memory (the
+// scratch block it always had, plus a 1 KB header) and moves through three kinds of task,
+//     SETUP  (assemble + set-up)      ->   QLOOP (model, QQP, working set)   <->   UPDATE (multipliers, feasibility)   -> torque map
+// each executed by whichever warp pops it.  Warps prefer the task kind of their SM's ROLE (QLOOP on two thirds of the SMs,
+// SETUP/UPDATE on the rest) and take the other kind only when theirs has run dry, so an SM's warps run one third of the code
+// most of the time and the GPC caches serve far fewer misses.  Hand-over = three lock-free rings of slot indices in global
+// memory (QLOOP tasks, UPDATE tasks, free slots); a push is preceded and a pop followed by __threadfence(), which on sm_100
+// is MEMBAR.SC.GPU + CCTL.IVALL, i.e. also drops the popping SM's stale L1 lines of the slot.  Same arithmetic as the
+// monolithic kernel: results are bit-identical (tools/gpu_dump.py).
+struct StageCtl {
+    int ticket; int pad0[31];          // next new solve (dispatch ticket)
+    int done; int pad1[31];            // finished solves
+    int head[3][32];                   // [q][0] is the counter; one 128-byte line each
+    int tail[3][32];
+    int avail[3][32];                  // published entries not yet claimed by a pop
+};
+constexpr int SQ_QLOOP = 0, SQ_UPDATE = 1, SQ_FREE = 2;
+constexpr int HDR_INST = gl::HDR_DOUBLES - 1, HDR_CYCLES = gl::HDR_DOUBLES - 2;      // header tail: instance index, cycles so far
+static_assert(sizeof(SolveState) <= (gl::HDR_DOUBLES - 2) * sizeof(double), "header tail is free");
+
+struct StageQueues {
+    StageCtl* ctl;
+    int* ring;          // [3][rmask + 1], -1 = empty
+    int rmask;
+    int nslots;
+};
+
+// Fetch-add rings: no compare-and-swap loop anywhere (a CAS loop on one counter serialises at one success per L2 round trip once
+// a few hundred warps contend, ~1 M pops/s against the 4 M/s this kernel needs -- measured: warps spent a third of their cycles
+// in pop).  `avail` counts published entries minus pops in progress; a pop that takes it from > 0 owns the next head position.
+__device__ __forceinline__ void sq_push(const StageQueues& q, int which, int slot)
+{
+    // caller: every lane has fenced its writes to the slot and the warp has synchronised; lane 0 only
+    const int pos = atomicAdd(&q.ctl->tail[which][0], 1);
+    atomicExch(q.ring + which * (q.rmask + 1) + (pos & q.rmask), slot);
+    atomicAdd(&q.ctl->avail[which][0], 1);      // (a pop that sees the count before the entry spins on the entry)
+}
+__device__ __forceinline__ int sq_pop(const StageQueues& q, int which)
+{
+    // lane 0 only; -1 when the ring is empty
+    if (*(volatile int*)&q.ctl->avail[which][0] <= 0) return -1;
+    if (atomicSub(&q.ctl->avail[which][0], 1) <= 0) { atomicAdd(&q.ctl->avail[which][0], 1); return -1; }
+    const int h = atomicAdd(&q.ctl->head[which][0], 1);
+    int* e = q.ring + which * (q.rmask + 1) + (h & q.rmask);
+    int sIdx;
+    while ((sIdx = atomicExch(e, -1)) < 0) __nanosleep(20);      // an earlier position's push is still in flight
+    return sIdx;
+}
+
+__global__ void __launch_bounds__(SOLVE_T) wbc_solve_staged_kernel(Params P, int n, const double* __restrict__ recs, SolveOut out,
+                                                                   double* __restrict__ slot_base, double* __restrict__ kkt_base, StageQueues sq,
+                                                                   const int* __restrict__ order, unsigned* __restrict__ cost,
+                                                                   int* __restrict__ hist_next, int m_period, int m_group, unsigned long long* __restrict__ prof)
+{
+    Work w;
+    w.g = nullptr;
+    w.kkt = kkt_base + (long)blockIdx.x * gl::KKT_DOUBLES;
+    w.sm = nullptr;
+    const WarpEx ex;
+    Settings cfg;
+    cfg.epsx = P.qp_epsx; cfg.rho = P.qp_rho; cfg.outerits = P.qp_outerits; cfg.kkt_mode = P.qp_literal_kkt ? 0 : 1;
+    for (int k = ex.lane(); k < sl::TOTAL; k += SOLVE_T) WBC_SM(w)[k] = 0.0;
+    ex.sync();
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    // role of this SM: every m_period-th group of m_group SMs runs SETUP / UPDATE tasks first, the others QLOOP tasks
+    const bool role_m = m_period > 0 && ((smid / (unsigned)m_group) % (unsigned)m_period) == (unsigned)(m_period - 1);
+    volatile int* donep = &sq.ctl->done;
+    volatile int* ticketp = &sq.ctl->ticket;
+    int idle = 0;
+    // profile (optional): cycles and counts per task kind, cycles spent looking for a task, cycles in the two fences
+    unsigned long long pr_cyc[3] = {0, 0, 0}, pr_cnt[3] = {0, 0, 0}, pr_wait = 0, pr_fence = 0, pr_steal = 0;
+    const long long k0 = clock64();
+    long long tq = k0;
+    for (;;) {
+        // ---- take a task: (kind, slot); kind 0 = QLOOP, 1 = UPDATE, 2 = SETUP (slot fresh, ticket drawn)
+        int kind = -1, slot = -1, ticket = -1;
+        if (ex.lane() == 0) {
+            const int first = role_m ? SQ_UPDATE : SQ_QLOOP;
+            slot = sq_pop(sq, first);
+            if (slot >= 0) kind = first;
+            if (kind < 0 && role_m && *ticketp < n) {                 // start a new solve
+                slot = sq_pop(sq, SQ_FREE);
+                if (slot >= 0) {
+                    ticket = atomicAdd(&sq.ctl->ticket, 1);
+                    if (ticket < n) kind = 2;
+                    else { sq_push(sq, SQ_FREE, slot); slot = -1; }
+                }
+            }
+            if (kind < 0) {                                          // own kind has run dry: take the other one
+                const int other = role_m ? SQ_QLOOP : SQ_UPDATE;
+                slot = sq_pop(sq, other);
+                if (slot >= 0) kind = other;
+            }
+            if (kind < 0 && !role_m && *ticketp < n) {
+                slot = sq_pop(sq, SQ_FREE);
+                if (slot >= 0) {
+                    ticket = atomicAdd(&sq.ctl->ticket, 1);
+                    if (ticket < n) kind = 2;
+                    else { sq_push(sq, SQ_FREE, slot); slot = -1; }
+                }
+            }
+            if (kind < 0 && *donep >= n) kind = -2;
+        }
+        kind = __shfl_sync(0xffffffffu, kind, 0);
+        if (kind == -2) break;
+        if (kind < 0) {
+            idle = idle < 8 ? idle + 1 : 8;
+            __nanosleep(64u << idle);
+            continue;
+        }
+        idle = 0;
+        slot = __shfl_sync(0xffffffffu, slot, 0);
+        ticket = __shfl_sync(0xffffffffu, ticket, 0);
+        const long long tf0 = clock64();
+        pr_wait += (unsigned long long)(tf0 - tq);
+        __threadfence();                                             // acquire: the slot as its last stage left it (also drops stale L1 lines)
+        const long long t0 = clock64();
+        pr_fence += (unsigned long long)(t0 - tf0);
+        if ((kind == SQ_QLOOP) == role_m && kind != 2) pr_steal++;
+        w.g = slot_base + (long)slot * gl::TOTAL;
+        double* hdr = w.g + gl::OFF_HDR;
+        double* rec = SM_(w, sl::OFF_CI);
+        SolveState st;
+        int i;
+        long long cyc0 = 0;
+        int next = -1;                                               // ring the slot goes to afterwards (-1: the solve is finished)
+        bool finished = false;
+        if (kind == 2) {
+            i = order ? order[ticket] : ticket;
+            ex.copy_in(rec, recs + (long)i * QPREC_DOUBLES, QR_MODE + 1);
+            double chk = 0.0;
+#pragma unroll 1
+            for (int k = ex.lane(); k <= QR_MODE; k += SOLVE_T) chk += rec[k] * 0.0;
+            const bool nonfinite = __any_sync(0xffffffffu, chk != 0.0);
+            const double md = rec[QR_MODE];
+            if (nonfinite || !(md == 0.0 || md == 1.0 || md == 2.0)) {
+                for (int k = ex.lane(); k < 12; k += SOLVE_T)
+                    out.tau[(long)k * out.ld + i] = P.hold_tau_on_failure ? out.tau_prev[(long)k * out.ld_prev + i] : 0.0;
+                if (out.x)
+                    for (int k = ex.lane(); k < 30; k += SOLVE_T) out.x[(long)k * out.ld + i] = 0.0;
+                if (ex.lane() == 0) {
+                    Stats z;
+                    z.termination = nonfinite ? WBC_ST_NONFINITE : WBC_ST_BAD_MODE;
+                    z.ncholesky = 0; z.outer_its = 0; z.qqp_calls = 0; z.nicwork = 0; z.kkt_dim_max = 0; z.chol_reused = 0; z.flags = 0; z.flops = 0.0;
+                    write_info(z, i, out.ld, out.status, out.qp_info, out.qp_flops);
+                    if (out.qp_obj) out.qp_obj[i] = 0.0;
+                    cost[i] = 0u;
+                    atomicAdd(hist_next, 1);
+                }
+                finished = true;
+            } else {
+                const QpShape sh = qp_shape((int)md);
+                assemble_qp<LDH>(ex, P, rec, sh, W_H(w), W_EXB(w), W_C(w));
+                const int rt = sh.neq + 5 * sh.nst, rq = rt + 24 + (sh.nst == 2 ? 12 : 0);
+                cfg.dup_start[0] = rt + 12; cfg.dup_count[0] = 12;
+                cfg.dup_start[1] = rq + 12; cfg.dup_count[1] = 12;
+                solve_stage_setup(ex, w, cfg, sh.nrows, sh.neq, st);
+                next = SQ_QLOOP;
+            }
+        } else {
+            i = (int)hdr[HDR_INST];
+            cyc0 = (long long)hdr[HDR_CYCLES];
+            stage_load(ex, w, st);
+            if (kind == SQ_QLOOP) { solve_stage_qloop(ex, w, st); next = SQ_UPDATE; }
+            else { solve_stage_update(ex, w, cfg, st); next = SQ_QLOOP; }
+        }
+        if (!finished && st.done) {
+            // ---- the solve is complete: torque map and outputs (as in wbc_solve_kernel)
+            double* xs = W_XS(w);
+            if (st.termination != 2) {
+                for (int k = ex.lane(); k < 30; k += SOLVE_T) xs[k] = 0.0;
+                ex.sync();
+            }
+            ex.copy_in(rec, recs + (long)i * QPREC_DOUBLES, QR_MODE + 1);
+            const QpShape sh = qp_shape((int)rec[QR_MODE]);
+            torque_and_objective(ex, P, rec, sh, xs, out.tau + i, out.ld, out.qp_obj ? out.qp_obj + i : nullptr);
+            if (st.termination == 2) {
+                for (int k = ex.lane(); k < 12; k += SOLVE_T) out.tau_prev[(long)k * out.ld_prev + i] = out.tau[(long)k * out.ld + i];
+            } else if (P.hold_tau_on_failure) {
+                for (int k = ex.lane(); k < 12; k += SOLVE_T) out.tau[(long)k * out.ld + i] = out.tau_prev[(long)k * out.ld_prev + i];
+            }
+            if (out.x)
+                for (int k = ex.lane(); k < 30; k += SOLVE_T) out.x[(long)k * out.ld + i] = xs[k];
+            if (ex.lane() == 0) {
+                Stats z;
+                stage_stats(st, z);
+                write_info(z, i, out.ld, out.status, out.qp_info, out.qp_flops);
+                const unsigned long long dt = (unsigned long long)(cyc0 + (clock64() - t0)) >> 10;
+                const unsigned cu = dt > 0xffffffffull ? 0xffffffffu : (unsigned)dt;
+                cost[i] = cu;
+                atomicAdd(hist_next + cost_bucket(cu), 1);
+            }
+            finished = true;
+        }
+        if (!finished) {
+            stage_store(ex, w, st);
+            if (ex.lane() == 0) {
+                hdr[HDR_INST] = (double)i;
+                hdr[HDR_CYCLES] = (double)(cyc0 + (clock64() - t0));
+            }
+        }
+        const long long t1 = clock64();
+        pr_cyc[kind] += (unsigned long long)(t1 - t0); pr_cnt[kind]++;
+        __threadfence();                                             // release: the slot (or the outputs) before the hand-over
+        ex.sync();
+        if (ex.lane() == 0) {
+            if (finished) { sq_push(sq, SQ_FREE, slot); atomicAdd(&sq.ctl->done, 1); }
+            else sq_push(sq, next, slot);
+        }
+        tq = clock64();
+        pr_fence += (unsigned long long)(tq - t1);
+    }
+    if (prof && ex.lane() == 0) {
+        unsigned long long* p = prof + (long)blockIdx.x * 12;
+        p[0] = pr_cyc[0]; p[1] = pr_cyc[1]; p[2] = pr_cyc[2]; p[3] = pr_cnt[0]; p[4] = pr_cnt[1]; p[5] = pr_cnt[2];
+        p[6] = pr_wait; p[7] = pr_fence; p[8] = pr_steal; p[9] = (unsigned long long)(clock64() - k0); p[10] = role_m ? 1ull : 0ull; p[11] = smid;
+    }
+}
+
 // Thread per instance: evaluate the plan's four splines at the instance's time (wbc_traj.cuh).
 __global__ void __launch_bounds__(128) wbc_traj_kernel(int n, int nseg, const double* __restrict__ dur, const double* __restrict__ nodes, long ld,
                                                        const double* __restrict__ t, double t_all, wbc::TrajOut out)
@@ -207,10 +444,11 @@ __global__ void __launch_bounds__(128) wbc_traj_kernel(int n, int nseg, const do
 __global__ void __launch_bounds__(SOLVE_T) wbc_dense_qp_kernel(Params P, int n, const double* __restrict__ Q, const double* __restrict__ c,
                                                                const double* __restrict__ L, int nrows, int neq, double* __restrict__ x,
                                                                int* status, int* info, double* flops, double* __restrict__ scratch_base,
-                                                               int* __restrict__ queue)
+                                                               double* __restrict__ kkt_base, int* __restrict__ queue)
 {
     Work w;
     w.g = scratch_base + (long)blockIdx.x * gl::TOTAL;
+    w.kkt = kkt_base + (long)blockIdx.x * gl::KKT_DOUBLES;
     w.sm = nullptr;
     const WarpEx ex;
     Settings cfg;
@@ -349,7 +587,15 @@ struct wbc_ctx {
     double* yw;
     double* w_dev;       // [6][max_batch] (when the caller passes no w)
     double* tau_prev;    // [12][max_batch] last good torque per instance index (hold_tau_on_failure)
-    double* scratch;     // [nblocks][gl::TOTAL]
+    double* scratch;     // [nslots][gl::TOTAL] one block per solve in flight (the monolithic kernels use the first nblocks)
+    double* kkt;         // [nblocks][gl::KKT_DOUBLES] literal multiplier update's matrix, one per resident warp
+    int nslots;          // solves in flight in the staged solver (2 per resident warp)
+    StageCtl* sq_ctl;    // staged solver: counters
+    int* sq_ring;        // staged solver: rings [3][sq_rsize]
+    int sq_rsize;
+    int staged;          // 0: wbc_solve_kernel (default), 1: wbc_solve_staged_kernel (WBC_SOLVER=staged)
+    int m_period, m_group;   // SM roles of the staged solver
+    unsigned long long* prof;   // [nblocks][12] per-warp profile of the last staged launch (WBC_STAGE_PROF=1)
     int* queue;          // [cost histogram A | work-queue counter | dispatch cursors | cost histogram B]: counter and cursors sit between
                          // the two histograms so that "counter + cursors + the histogram being filled" is one contiguous memset either way
     unsigned* cost;      // [max_batch] duration of each instance's last solve (1024-cycle units)
@@ -358,6 +604,8 @@ struct wbc_ctx {
     int hist_sel;        // which histogram the last solve filled
     int nblocks, threads;   // solver launch shape
     int occ_per_sm;         // resident solver CTAs per SM (occupancy calculator)
+    int occ_forced;         // WBC_SOLVE_CTAS_PER_SM was given: no per-launch adaptation
+    int last_grid;          // solver grid of the last wbc_cycle
     int solve_smem;         // dynamic shared memory per solver CTA (sl::BYTES, or padded by WBC_SOLVE_CTAS_PER_SM)
     // staging for WBC_HOST_PTRS
     double* d_in;        // [93+40][max_batch]
@@ -400,7 +648,7 @@ int wbc_destroy(wbc_ctx* c)
 {
     if (!c) return WBC_OK;
     cudaSetDevice(c->device);
-    cudaFree(c->recs); cudaFree(c->yd); cudaFree(c->yw); cudaFree(c->w_dev); cudaFree(c->tau_prev); cudaFree(c->scratch); cudaFree(c->queue); cudaFree(c->cost); cudaFree(c->order);
+    cudaFree(c->recs); cudaFree(c->yd); cudaFree(c->yw); cudaFree(c->w_dev); cudaFree(c->tau_prev); cudaFree(c->scratch); cudaFree(c->kkt); cudaFree(c->sq_ctl); cudaFree(c->sq_ring); cudaFree(c->prof); cudaFree(c->queue); cudaFree(c->cost); cudaFree(c->order);
     cudaFree(c->traj_dur); cudaFree(c->traj_nodes); cudaFree(c->traj_s); cudaFree(c->traj_t);
     cudaFree(c->d_in); cudaFree(c->d_out); cudaFree(c->d_mode); cudaFree(c->d_iout); cudaFree(c->d_dense);
     if (c->h_pin) cudaFreeHost(c->h_pin);
@@ -439,6 +687,7 @@ int wbc_create(wbc_ctx** out, int device, int max_batch, const wbc_params* param
     // exactly that many CTAs fit); used by tools/ to measure how throughput scales with resident warps
     if (const char* ev = getenv("WBC_SOLVE_CTAS_PER_SM")) {
         const int k = atoi(ev);
+        c->occ_forced = 1;
         if (k >= 1 && k < SOLVE_CTAS_PER_SM) {
             per_sm = k;
             c->solve_smem = (((228 * 1024) / k - 1024) / 16) * 16;
@@ -458,7 +707,25 @@ int wbc_create(wbc_ctx** out, int device, int max_batch, const wbc_params* param
     TRY(cudaMalloc(&c->w_dev, nb * 6 * sizeof(double)));
     TRY(cudaMalloc(&c->tau_prev, nb * 12 * sizeof(double)));
     TRY(cudaMemset(c->tau_prev, 0, nb * 12 * sizeof(double)));
-    TRY(cudaMalloc(&c->scratch, (size_t)nteams * gl::TOTAL * sizeof(double)));
+    // Which solver kernel: one warp per solve (default) or stage tasks with SM roles (WBC_SOLVER=staged).  Measured on B200
+    // (profiles/README.md, round 2): equal at 65 536 instances (43.8 vs 44.1 ms), the staged kernel loses at 4 096 (3.8 vs 3.2 ms:
+    // a solve is seven hand-overs and the batch is only 2.3 solves per warp) -- it stays selectable, with its evidence.
+    c->staged = 0; c->m_period = 3; c->m_group = 1;
+    if (const char* ev = getenv("WBC_SOLVER")) c->staged = strcmp(ev, "staged") == 0;
+    if (const char* ev = getenv("WBC_STAGE_M_PERIOD")) c->m_period = atoi(ev);
+    if (const char* ev = getenv("WBC_STAGE_M_GROUP")) c->m_group = atoi(ev) > 0 ? atoi(ev) : 1;
+    double slots_per_warp = 1.5;
+    if (const char* ev = getenv("WBC_STAGE_SLOTS_PER_WARP")) slots_per_warp = atof(ev) >= 1.0 ? atof(ev) : 1.0;
+    const long want_slots = (long)((double)nteams * slots_per_warp + 0.5);
+    c->nslots = (int)(want_slots < (long)max_batch ? want_slots : (nteams > max_batch ? nteams : max_batch));
+    if (c->nslots < nteams) c->nslots = (int)nteams;
+    c->sq_rsize = 1;
+    while (c->sq_rsize < c->nslots) c->sq_rsize <<= 1;
+    TRY(cudaMalloc(&c->scratch, (size_t)c->nslots * gl::TOTAL * sizeof(double)));
+    TRY(cudaMalloc(&c->kkt, (size_t)nteams * gl::KKT_DOUBLES * sizeof(double)));
+    TRY(cudaMalloc(&c->sq_ctl, sizeof(StageCtl)));
+    TRY(cudaMalloc(&c->sq_ring, (size_t)3 * c->sq_rsize * sizeof(int)));
+    if (getenv("WBC_STAGE_PROF")) { TRY(cudaMalloc(&c->prof, (size_t)nteams * 12 * sizeof(unsigned long long))); TRY(cudaMemset(c->prof, 0, (size_t)nteams * 12 * sizeof(unsigned long long))); }
     TRY(cudaMalloc(&c->queue, (1 + 3 * ORD_NB) * sizeof(int)));
     TRY(cudaMemset(c->queue, 0, (1 + 3 * ORD_NB) * sizeof(int)));
     TRY(cudaMalloc(&c->cost, nb * sizeof(unsigned)));
@@ -471,15 +738,19 @@ int wbc_create(wbc_ctx** out, int device, int max_batch, const wbc_params* param
     TRY(cudaMallocHost(&c->h_pin_i, nb * kOutInts * sizeof(int)));
     TRY(cudaMemset(c->yd, 0, nb * 6 * sizeof(double)));
     TRY(cudaMemset(c->yw, 0, nb * 6 * sizeof(double)));
-    TRY(cudaMemset(c->scratch, 0, (size_t)nteams * gl::TOTAL * sizeof(double)));
-    TRY(cudaFuncSetAttribute(wbc_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->solve_smem));
+    TRY(cudaMemset(c->scratch, 0, (size_t)c->nslots * gl::TOTAL * sizeof(double)));
+    TRY(cudaMemset(c->kkt, 0, (size_t)nteams * gl::KKT_DOUBLES * sizeof(double)));
+    TRY(cudaFuncSetAttribute(wbc_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));      // padded requests: see wbc_cycle
+    TRY(cudaFuncSetAttribute(wbc_solve_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->solve_smem));
+    TRY(cudaFuncSetAttribute(wbc_solve_staged_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     TRY(cudaFuncSetAttribute(wbc_dense_qp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->solve_smem));
     TRY(cudaFuncSetAttribute(wbc_solve_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     TRY(cudaFuncSetAttribute(wbc_dense_qp_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     if (e == cudaSuccess) {
         // the persistent grid is exactly the resident CTAs: more would queue behind whole solves
         int occ = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wbc_solve_kernel, SOLVE_T, (size_t)c->solve_smem);
+        e = c->staged ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wbc_solve_staged_kernel, SOLVE_T, (size_t)c->solve_smem)
+                      : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wbc_solve_kernel, SOLVE_T, (size_t)c->solve_smem);
         if (e == cudaSuccess && occ >= 1) {
             c->occ_per_sm = occ;
             if (c->nblocks > c->sm_count * occ) c->nblocks = c->sm_count * occ;
@@ -669,11 +940,42 @@ int wbc_cycle(wbc_ctx* c, int n, const wbc_inputs* in, const wbc_outputs* out, v
     CU(cudaMemsetAsync((c->hist_sel ^ 1) == 0 ? c->queue : counter, 0, (1 + 2 * ORD_NB) * sizeof(int), s));
     CU(cudaEventRecord(c->ev0, s));
     const int fthreads = front_threads(c, n);
-    wbc_front_kernel<<<(n + fthreads - 1) / fthreads, fthreads, 0, s>>>(c->params, din, st, n, c->recs, w_ptr, w_ld, nodbg, 0, ord);
+    StageReset sr;
+    memset(&sr, 0, sizeof(sr));
+    if (c->staged) {
+        sr.ctl = reinterpret_cast<int*>(c->sq_ctl); sr.nctl = (int)(sizeof(StageCtl) / sizeof(int));
+        sr.free_tail_index = (int)(offsetof(StageCtl, tail) / sizeof(int)) + SQ_FREE * 32;
+        sr.free_avail_index = (int)(offsetof(StageCtl, avail) / sizeof(int)) + SQ_FREE * 32;
+        sr.ring = c->sq_ring; sr.rsize = c->sq_rsize; sr.nslots = c->nslots;
+    }
+    wbc_front_kernel<<<(n + fthreads - 1) / fthreads, fthreads, 0, s>>>(c->params, din, st, n, c->recs, w_ptr, w_ld, nodbg, 0, ord, sr);
     CU(cudaEventRecord(c->ev1, s));
-    const int nblocks = n < c->nblocks ? n : c->nblocks;
-    wbc_solve_kernel<<<nblocks, c->threads, c->solve_smem, s>>>(c->params, n, c->recs, so, c->scratch, counter, ordered ? c->order : nullptr,
-                                                           c->cost, hist_next);
+    // Resident solver warps for this batch.  Large batches take every warp that fits (12 per SM); a batch of a few thousand is
+    // only two or three solves per warp, where the step ends with its longest solve and every solve runs slower the more
+    // warps share the SM's instruction supply: measured at 4 096 instances, 8 warps per SM beat 12 by 3 % (profiles/README.md).
+    int nblocks = c->nblocks;
+    int smem = c->solve_smem;
+    if (!c->staged && c->occ_per_sm > 8 && !c->occ_forced) {
+        int per_sm = (int)((double)n / (3.4 * c->sm_count));
+        per_sm = per_sm < 8 ? 8 : (per_sm > c->occ_per_sm ? c->occ_per_sm : per_sm);
+        if (per_sm < c->occ_per_sm) {
+            // the shared-memory request is padded so that exactly per_sm CTAs fit an SM: the block scheduler then spreads
+            // the grid evenly instead of filling the first SMs with twelve
+            nblocks = per_sm * c->sm_count;
+            smem = (((228 * 1024) / per_sm - 1024) / 16) * 16;
+        }
+    }
+    if (n < nblocks) nblocks = n;
+    c->last_grid = nblocks;
+    if (c->staged) {
+        StageQueues sq;
+        sq.ctl = c->sq_ctl; sq.ring = c->sq_ring; sq.rmask = c->sq_rsize - 1; sq.nslots = c->nslots;
+        wbc_solve_staged_kernel<<<nblocks, c->threads, c->solve_smem, s>>>(c->params, n, c->recs, so, c->scratch, c->kkt, sq, ordered ? c->order : nullptr,
+                                                                      c->cost, hist_next, c->m_period, c->m_group, c->prof);
+    } else {
+        wbc_solve_kernel<<<nblocks, c->threads, smem, s>>>(c->params, n, c->recs, so, c->scratch, c->kkt, counter, ordered ? c->order : nullptr,
+                                                               c->cost, hist_next);
+    }
     CU(cudaEventRecord(c->ev2, s));
     CU(cudaGetLastError());
     c->launches = 2;
@@ -852,12 +1154,23 @@ int wbc_last_solve_cycles(wbc_ctx* c, int n, unsigned long long* cycles)
 }
 int wbc_last_launches(wbc_ctx* c) { return c ? c->launches : 0; }
 
+int wbc_stage_profile(wbc_ctx* c, unsigned long long* out, int max_rows)
+{
+    if (!c || !out) return fail(WBC_EINVAL, "wbc_stage_profile: null argument");
+    if (!c->prof) return fail(WBC_EINVAL, "wbc_stage_profile: the ctx was created without WBC_STAGE_PROF=1");
+    CU(cudaSetDevice(c->device));
+    CU(cudaDeviceSynchronize());
+    const int rows = max_rows < c->nblocks ? max_rows : c->nblocks;
+    CU(cudaMemcpy(out, c->prof, (size_t)rows * 12 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return rows;
+}
+
 int wbc_solver_shape(wbc_ctx* c, int* ctas_per_sm, int* smem_bytes, int* grid)
 {
     if (!c) return fail(WBC_EINVAL, "null ctx");
     if (ctas_per_sm) *ctas_per_sm = c->occ_per_sm;
     if (smem_bytes) *smem_bytes = c->solve_smem;
-    if (grid) *grid = c->nblocks;
+    if (grid) *grid = c->last_grid > 0 ? c->last_grid : c->nblocks;
     return WBC_OK;
 }
 
@@ -915,7 +1228,7 @@ int wbc_debug_update(wbc_ctx* c, int n, const wbc_inputs* in, const wbc_debug* d
         FrontState st;
         st.yd = ytmp; st.yw = ytmp + 6L * n; st.ld = n;
         const int fthreads = front_threads(c, n);
-        wbc_front_kernel<<<(n + fthreads - 1) / fthreads, fthreads, 0, s>>>(c->params, din, st, n, rtmp, ytmp + 12L * n, n, dd, 1, DispatchOrder{nullptr, nullptr, nullptr, nullptr});
+        wbc_front_kernel<<<(n + fthreads - 1) / fthreads, fthreads, 0, s>>>(c->params, din, st, n, rtmp, ytmp + 12L * n, n, dd, 1, DispatchOrder{nullptr, nullptr, nullptr, nullptr}, StageReset{nullptr, 0, 0, 0, nullptr, 0, 0});
         e = cudaStreamSynchronize(s);
         if (e == cudaSuccess) e = cudaGetLastError();
     }
@@ -972,7 +1285,7 @@ int wbc_qp_solve(wbc_ctx* c, int n, const double* Q, const double* cvec, const d
     const int nblocks = n < c->nblocks ? n : c->nblocks;
     CU(cudaEventRecord(c->ev0, s));
     CU(cudaEventRecord(c->ev1, s));
-    wbc_dense_qp_kernel<<<nblocks, c->threads, c->solve_smem, s>>>(c->params, n, dQ, dc, dL, nrows, neq, dx, dstatus, dinfo, dflops, c->scratch, c->queue + ORD_NB);
+    wbc_dense_qp_kernel<<<nblocks, c->threads, c->solve_smem, s>>>(c->params, n, dQ, dc, dL, nrows, neq, dx, dstatus, dinfo, dflops, c->scratch, c->kkt, c->queue + ORD_NB);
     CU(cudaEventRecord(c->ev2, s));
     CU(cudaGetLastError());
     c->launches = 1;
