@@ -185,6 +185,28 @@ int wbc_qp_solve(wbc_ctx* ctx, int n, const double* Q, const double* c, const do
 int wbc_plant_step(wbc_ctx* ctx, int n, double* base_pos, double* base_vel, double* foot_force, const double* x, const double* push,
                    long ld, void* cuda_stream, unsigned flags);
 
+/* Forward-dynamics plant: one control period (params.obs_dt) of every robot as an articulated body under the
+ * joint torques `tau` [12][ld] (held over the period, like main.cpp's 400 Hz loop over Gazebo's 1 ms steps), a world wrench `push`
+ * [6][ld] at the CoM and rigid bilateral point contacts at the stance feet of its contact mode:
+ *     M nu_dot + h = S'tau + push_gen + Js' f,      Js nu_dot = -Jdqd_s - gamma Js nu,
+ * `substeps` semi-implicit Euler substeps.  Stands in for Gazebo + the ModelPush plugin (force_plugin.cpp:124-491), which
+ * cannot run here; the reference for this stage is a physics engine, so its parity is unpinned (checked against the oracle's
+ * dense formulation and physics identities).  The state arrays are advanced IN PLACE; foot_force receives the contact forces in
+ * the sensor frames (swing feet: 0), i.e. the next cycle's measured forces.  diag [2][ld] (may be NULL): contact-constraint
+ * residual, smallest normal force (unilaterality is not enforced).  Host or device pointers per flags. */
+typedef struct wbc_plant_state {
+    double* base_pos;    /* [3]  */
+    double* base_rot;    /* [9]  world_R_base, row-major */
+    double* base_rpy;    /* [3]  */
+    double* base_vel;    /* [6]  */
+    double* q;           /* [12] */
+    double* dq;          /* [12] */
+    double* foot_force;  /* [12] out */
+    const int* mode;     /* [1]  in  */
+} wbc_plant_state;
+int wbc_plant_dynamics_step(wbc_ctx* ctx, int n, const wbc_plant_state* st, const double* tau, const double* push, long ld, int substeps,
+                            double gamma, double* diag, void* cuda_stream, unsigned flags);
+
 /* Device-side timing of the last wbc_cycle on this ctx (CUDA events on the launching stream), ms. */
 int wbc_last_timing(wbc_ctx* ctx, float* front_ms, float* solve_ms);
 /* Per-instance solve duration of the last wbc_cycle on this ctx, in SM clock cycles (clock64 around the instance's

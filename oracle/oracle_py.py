@@ -256,6 +256,30 @@ def plant_step(sc, push, x=None, params=None, gravity=(0.0, 0.0, -9.8)):
     return np.ascontiguousarray(pos.T), np.ascontiguousarray(vel.T), (np.ascontiguousarray(ff.T) if xs is not None else None)
 
 
+def fdyn_step(sc, tau, push, params=None, nsub=5, gamma=100.0, gravity=(0.0, 0.0, -9.8)):
+    """Forward dynamics with hard contacts (wbc_oracle_fdyn_step) on every instance: tau [12][n], push [6][n] (world wrench at
+    the CoM).  Returns (next-state dict with base_pos, base_rot, base_rpy, base_vel, q, dq, foot_force in SoA layout, diag [n][2])."""
+    params = params or default_params()
+    lib = oracle_lib()
+    pd = C.POINTER(C.c_double)
+    lib.wbc_oracle_fdyn_step.argtypes = [C.POINTER(Params), C.POINTER(In), pd, pd, C.c_int, C.c_double, C.POINTER(In), pd, pd]
+    lib.wbc_oracle_fdyn_step.restype = None
+    n = sc["mode"].shape[0]
+    arr = to_structs(sc, gravity)
+    tt = np.ascontiguousarray(np.asarray(tau, dtype=np.float64).T)
+    pt = np.ascontiguousarray(np.asarray(push, dtype=np.float64).T)
+    nxt = {"base_pos": np.zeros((3, n)), "base_rot": np.zeros((9, n)), "base_rpy": np.zeros((3, n)), "base_vel": np.zeros((6, n)),
+           "q": np.zeros((12, n)), "dq": np.zeros((12, n)), "foot_force": np.zeros((12, n))}
+    diag = np.zeros((n, 2))
+    ff = np.zeros(12)
+    o = In()
+    for i in range(n):
+        lib.wbc_oracle_fdyn_step(C.byref(params), C.byref(arr[i]), _dp(tt[i]), _dp(pt[i]), int(nsub), float(gamma), C.byref(o), _dp(ff), _dp(diag[i]))
+        nxt["base_pos"][:, i] = o.base_pos; nxt["base_rot"][:, i] = o.base_R; nxt["base_rpy"][:, i] = o.rpy
+        nxt["base_vel"][:, i] = o.base_vel; nxt["q"][:, i] = o.q; nxt["dq"][:, i] = o.dq; nxt["foot_force"][:, i] = ff
+    return nxt, diag
+
+
 def spline_point(durations, nodes, t):
     """towr::Spline::GetPoint (oracle restatement): durations [nseg], nodes [nseg+1, 6] -> (id, p, v, a)."""
     lib = oracle_lib()

@@ -677,6 +677,115 @@ void wbc_oracle_plant_step(const wbc_oracle_params* p, const wbc_oracle_in* in, 
     free(d);
 }
 
+/* ------------------------------------------------------------------ forward dynamics with hard contacts
+ * Stands in for Gazebo + ModelPush (force_plugin/src/force_plugin.cpp:124-491), which cannot run here; PARITY UNPINNED (the
+ * reference for this stage is a physics engine).  One control period (p->obs_dt) of the articulated robot under the commanded
+ * joint torques (held over the period, as the 400 Hz loop of main.cpp:861 holds them over Gazebo's 1 ms steps), a world wrench
+ * `push` at the CoM (what ModelPush applies to a link, reduced to the CoM) and rigid, bilateral point contacts at the stance
+ * feet of in->mode:
+ *       [ M  -Js' ] [ nu_dot ]   [ S'tau - h + push_gen          ]
+ *       [ Js   0  ] [   f    ] = [ -Jdqd_s - gamma Js nu          ]       (dense, literal, Gauss-Jordan)
+ * nu = [v_base; omega; dq] (MIXED), M / h / Js / Jdqd from wbc_oracle_update, gamma = velocity-level constraint stabilisation.
+ * `nsub` semi-implicit Euler substeps: nu += dt nu_dot, then q += dt dq, p += dt v, R <- exp([omega dt]) R with the NEW
+ * velocities.  Outputs the next state, the contact forces of the last substep in the sensor (foot link) frame -- what the
+ * contact sensors report to the next cycle (main.cpp:794-834) -- and the largest |Js nu_dot + Jdqd_s + gamma Js nu| (should be
+ * rounding) plus the smallest normal force (unilaterality is NOT enforced: a negative value means the foot would have lifted). */
+static void rot_to_rpy(const double* R, double* rpy)
+{   /* R = Rz(yaw) Ry(pitch) Rx(roll) */
+    rpy[0] = atan2(R[7], R[8]);
+    rpy[1] = atan2(-R[6], sqrt(R[7] * R[7] + R[8] * R[8]));
+    rpy[2] = atan2(R[3], R[0]);
+}
+void wbc_oracle_fdyn_step(const wbc_oracle_params* p, const wbc_oracle_in* in0, const double* tau, const double* push, int nsub,
+                          double gamma, wbc_oracle_in* out, double* foot_force_out, double* diag /* [2] */)
+{
+    wbc_oracle_dyn* d = (wbc_oracle_dyn*)malloc(sizeof(wbc_oracle_dyn));
+    wbc_oracle_in cur = *in0;
+    const double dt = p->obs_dt / (double)nsub;
+    int stance[4], ns = 0;
+    for (int f = 0; f < 4; f++) {
+        const int swing = (in0->mode == 1 && (f == 0 || f == 2)) || (in0->mode == 2 && (f == 1 || f == 3));
+        stance[f] = !swing;
+        ns += stance[f];
+    }
+    const int nc = 3 * ns, nk = 18 + nc;
+    double* K = (double*)malloc(sizeof(double) * nk * nk);
+    double* rhs = (double*)malloc(sizeof(double) * nk);
+    double worst = 0.0, fzmin = 1e300;
+    for (int c = 0; c < 12; c++) foot_force_out[c] = 0.0;
+    for (int it = 0; it < nsub; it++) {
+        wbc_oracle_update(&cur, d);
+        double nu[18];
+        for (int c = 0; c < 6; c++) nu[c] = cur.base_vel[c];
+        for (int c = 0; c < 12; c++) nu[6 + c] = cur.dq[c];
+        double xbc[3], tq[3];
+        for (int c = 0; c < 3; c++) xbc[c] = d->com[c] - cur.base_pos[c];
+        cross3(xbc, push, tq);                                  /* wrench at the CoM -> about the base origin */
+        memset(K, 0, sizeof(double) * nk * nk);
+        for (int a = 0; a < 18; a++) {
+            for (int b = 0; b < 18; b++) K[a * nk + b] = d->M[a * 18 + b];
+            rhs[a] = -d->h[a];
+        }
+        for (int c = 0; c < 3; c++) { rhs[c] += push[c]; rhs[3 + c] += push[3 + c] + tq[c]; }
+        for (int c = 0; c < 12; c++) rhs[6 + c] += tau[c];
+        int r = 0;
+        double cres[12];
+        for (int f = 0; f < 4; f++) {
+            if (!stance[f]) continue;
+            for (int a = 0; a < 3; a++, r++) {
+                double jn = 0.0;
+                for (int b = 0; b < 18; b++) {
+                    const double j = d->Jac_lin[(3 * f + a) * 18 + b];
+                    K[(18 + r) * nk + b] = j;
+                    K[b * nk + 18 + r] = -j;
+                    jn += j * nu[b];
+                }
+                rhs[18 + r] = -d->Jdqd_lin[3 * f + a] - gamma * jn;
+                cres[r] = rhs[18 + r];
+            }
+        }
+        gj_solve(K, rhs, nk, 1);                                /* rhs <- [nu_dot; f] */
+        /* residual of the contact constraint with the computed acceleration */
+        r = 0;
+        for (int f = 0; f < 4; f++) {
+            if (!stance[f]) continue;
+            for (int a = 0; a < 3; a++, r++) {
+                double ja = 0.0;
+                for (int b = 0; b < 18; b++) ja += d->Jac_lin[(3 * f + a) * 18 + b] * rhs[b];
+                worst = fmax(worst, fabs(ja - cres[r]));
+            }
+        }
+        /* contact forces in the sensor frame */
+        r = 0;
+        for (int f = 0; f < 4; f++) {
+            if (!stance[f]) { for (int a = 0; a < 3; a++) foot_force_out[3 * f + a] = 0.0; continue; }
+            double Rt[9];
+            mat_T(&d->foot_R[f * 9], Rt, 3, 3);
+            mat_mul(Rt, &rhs[18 + r], &foot_force_out[3 * f], 3, 3, 1);
+            fzmin = fmin(fzmin, rhs[18 + r + 2]);
+            r += 3;
+        }
+        /* semi-implicit Euler */
+        for (int c = 0; c < 18; c++) nu[c] += dt * rhs[c];
+        for (int c = 0; c < 6; c++) cur.base_vel[c] = nu[c];
+        for (int c = 0; c < 12; c++) { cur.dq[c] = nu[6 + c]; cur.q[c] += dt * nu[6 + c]; }
+        for (int c = 0; c < 3; c++) cur.base_pos[c] += dt * nu[c];
+        {
+            const double wn = sqrt(nu[3] * nu[3] + nu[4] * nu[4] + nu[5] * nu[5]);
+            if (wn > 0.0) {
+                double ax[3] = {nu[3] / wn, nu[4] / wn, nu[5] / wn}, Rw[9], Rn[9];
+                rot_axis_angle(ax, wn * dt, Rw);
+                mat_mul(Rw, cur.base_R, Rn, 3, 3, 3);
+                memcpy(cur.base_R, Rn, sizeof(Rn));
+            }
+            rot_to_rpy(cur.base_R, cur.rpy);
+        }
+    }
+    *out = cur;
+    if (diag) { diag[0] = worst; diag[1] = (ns > 0) ? fzmin : 0.0; }
+    free(K); free(rhs); free(d);
+}
+
 /* ------------------------------------------------------------------ threaded batch (CPU baseline) */
 typedef struct {
     const wbc_oracle_params* p; const wbc_oracle_in* in; wbc_oracle_out* out; wbc_qp_fn solve; int lo, hi;

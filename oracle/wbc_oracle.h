@@ -106,6 +106,12 @@ int  wbc_oracle_cycle(const wbc_oracle_params* p, const wbc_oracle_in* in, wbc_q
  * and, in closed loop, the next sensor-frame foot forces (12). */
 void wbc_oracle_plant_step(const wbc_oracle_params* p, const wbc_oracle_in* in, const double* push, const double* x,
                            double* base_pos_out, double* base_vel_out, double* foot_force_out);
+/* Forward dynamics with hard point contacts at the stance feet (stands in for Gazebo + ModelPush, parity
+ * unpinned): one control period under joint torques tau (12), a world wrench push (6) at the CoM, nsub semi-implicit Euler
+ * substeps, velocity-level constraint stabilisation gamma.  out = next state (pose, twist, q, dq; the other fields are copied),
+ * foot_force_out (12) = contact forces in the sensor frames, diag[0] = contact-constraint residual, diag[1] = smallest normal force. */
+void wbc_oracle_fdyn_step(const wbc_oracle_params* p, const wbc_oracle_in* in, const double* tau, const double* push, int nsub,
+                          double gamma, wbc_oracle_in* out, double* foot_force_out, double* diag);
 /* towr::Spline::GetPoint(t) for one spline of nseg cubic-Hermite polynomials in 3 dimensions (spline.cc:48-93,
  * polynomial.cc:50-104): durations[nseg]; nodes[(nseg+1)][6] = position(3), velocity(3) per node.
  * Outputs p, v, a (3 each).  Returns the polynomial id, or -1 where the reference would assert (t < 0, t past the end). */

@@ -90,6 +90,16 @@ void emu_sample_trajectory(int n, int nseg, const double* dur, const double* nod
     }
 }
 
+// The device's forward-dynamics plant step (wbc_front.cuh, fdyn_step_instance) for n instances; all arrays SoA [k][ld], state in place.
+void emu_fdyn_step(const Params* P, int n, long ld, double* base_pos, double* base_rot, double* base_rpy, double* base_vel, double* q, double* dq,
+                   double* foot_force, const int* mode, const double* tau, const double* push, double* diag, int nsub, double gamma)
+{
+    wbc::FdynIO io;
+    io.base_pos = base_pos; io.base_rot = base_rot; io.base_rpy = base_rpy; io.base_vel = base_vel; io.q = q; io.dq = dq; io.foot_force = foot_force;
+    io.mode = mode; io.tau = tau; io.push = push; io.diag = diag; io.ld = ld;
+    for (long i = 0; i < n; i++) wbc::fdyn_step_instance(*P, io, i, nsub, gamma);
+}
+
 int emu_sizeof_params() { return (int)sizeof(Params); }
 int emu_qprec_doubles() { return QPREC_DOUBLES; }
 }

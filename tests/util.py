@@ -102,6 +102,22 @@ class Emu:
         self.lib.emu_cycle(C.byref(P), C.byref(io), n)
         return out
 
+    def fdyn_step(self, sc, tau, push, nsub=5, gamma=100.0, params=None):
+        """The device code's forward-dynamics plant step on the host; returns (next-state dict, diag [2, n])."""
+        P = params or emu_default_params()
+        n = int(sc["mode"].shape[0])
+        st = {k: np.array(sc[k], dtype=np.float64, order="C") for k in ("base_pos", "base_rot", "base_rpy", "base_vel", "q", "dq")}
+        st["foot_force"] = np.zeros((12, n))
+        mode = np.ascontiguousarray(sc["mode"], dtype=np.int32)
+        tau = np.ascontiguousarray(tau, dtype=np.float64); push = np.ascontiguousarray(push, dtype=np.float64)
+        diag = np.zeros((2, n))
+        self.lib.emu_fdyn_step.argtypes = [C.POINTER(EmuParams), C.c_int, C.c_long] + [_dp] * 7 + [_ip, _dp, _dp, _dp, C.c_int, C.c_double]
+        self.lib.emu_fdyn_step.restype = None
+        d = lambda a: a.ctypes.data_as(_dp)
+        self.lib.emu_fdyn_step(C.byref(P), n, n, d(st["base_pos"]), d(st["base_rot"]), d(st["base_rpy"]), d(st["base_vel"]), d(st["q"]), d(st["dq"]),
+                               d(st["foot_force"]), mode.ctypes.data_as(_ip), d(tau), d(push), d(diag), int(nsub), float(gamma))
+        return st, diag
+
     def sample_trajectory(self, traj, t):
         dur = np.ascontiguousarray(traj["durations"], dtype=np.float64)
         nodes = np.ascontiguousarray(traj["nodes"], dtype=np.float64)

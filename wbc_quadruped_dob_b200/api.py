@@ -56,6 +56,10 @@ class _Debug(C.Structure):
     _fields_ = [(n, C.c_void_p) for n, _ in DEBUG_FIELDS] + [("ld", C.c_long)]
 
 
+class _PlantState(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("base_pos", "base_rot", "base_rpy", "base_vel", "q", "dq", "foot_force", "mode")]
+
+
 class _Trajectory(C.Structure):
     _fields_ = [("nseg", C.c_int), ("durations", C.c_void_p), ("nodes", C.c_void_p), ("ld", C.c_long)]
 
@@ -75,7 +79,7 @@ _lib = None
 
 EXPORTS = ["wbc_default_params", "wbc_last_error", "wbc_version", "wbc_create", "wbc_destroy", "wbc_set_params",
            "wbc_set_observer_state", "wbc_get_observer_state", "wbc_cycle", "wbc_debug_update", "wbc_qp_solve",
-           "wbc_plant_step", "wbc_last_timing", "wbc_last_solve_cycles", "wbc_last_launches", "wbc_solver_shape", "wbc_stage_profile", "wbc_host_alloc",
+           "wbc_plant_step", "wbc_plant_dynamics_step", "wbc_last_timing", "wbc_last_solve_cycles", "wbc_last_launches", "wbc_solver_shape", "wbc_stage_profile", "wbc_host_alloc",
            "wbc_host_free",
            "wbc_set_trajectory", "wbc_sample_trajectory",
            "wbc_measure_dfma_peak"]
@@ -111,6 +115,8 @@ def load():
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint]
     lib.wbc_plant_step.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_void_p,
                                    C.c_uint]
+    lib.wbc_plant_dynamics_step.argtypes = [C.c_void_p, C.c_int, C.POINTER(_PlantState), C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_double,
+                                            C.c_void_p, C.c_void_p, C.c_uint]
     lib.wbc_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     lib.wbc_last_solve_cycles.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_ulonglong)]
     lib.wbc_last_launches.argtypes = [C.c_void_p]
@@ -377,6 +383,19 @@ class WbcBatch:
             flags = DEVICE_PTRS | (0 if sync else NO_SYNC)
         _check(self.lib.wbc_plant_step(self.h, int(n), _ptr(base_pos), _ptr(base_vel), _ptr(foot_force), _ptr(x), _ptr(push), int(ld),
                                        stream, flags), "wbc_plant_step")
+
+    def plant_dynamics_step(self, state, tau, push, n=None, ld=None, substeps=5, gamma=100.0, diag=None, stream=None, sync=True):
+        """Forward-dynamics plant (wbc_plant_dynamics_step): `state` is a dict with base_pos, base_rot, base_rpy, base_vel, q, dq,
+        foot_force, mode (numpy arrays: host path, advanced in place; torch CUDA tensors: device path)."""
+        host = isinstance(state["q"], np.ndarray)
+        n = int(state["mode"].shape[0]) if n is None else int(n)
+        ld = n if ld is None else int(ld)
+        ps = _PlantState()
+        for k in ("base_pos", "base_rot", "base_rpy", "base_vel", "q", "dq", "foot_force", "mode"):
+            setattr(ps, k, _ptr(state[k]))
+        flags = (HOST_PTRS if host else DEVICE_PTRS) | (0 if (sync or host) else NO_SYNC)
+        _check(self.lib.wbc_plant_dynamics_step(self.h, n, C.byref(ps), _ptr(tau), _ptr(push), ld, int(substeps), float(gamma), _ptr(diag), stream, flags),
+               "wbc_plant_dynamics_step")
 
     def last_timing(self):
         a, b = C.c_float(0), C.c_float(0)

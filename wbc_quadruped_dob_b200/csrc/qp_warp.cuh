@@ -145,7 +145,10 @@ constexpr int MC_TOTAL = 2240;
 // State of a solve that is handed from stage to stage (solve_stage_* below): the SolveState header and the point exxc.
 constexpr long OFF_HDR = OFF_MC + MC_TOTAL;                      // [32] header | [104] exxc
 constexpr int HDR_DOUBLES = 32;
-constexpr long TOTAL = ((OFF_HDR + HDR_DOUBLES + 104 + 15) / 16) * 16;
+// The extended model of a QQP call handed to the warp that runs it (stage tasks): H [30][31]; its CI rows go to the spill
+// CI array and its linear term to the spill EXB array (the spill mode never hands its QQP over).
+constexpr long OFF_HQ = OFF_HDR + HDR_DOUBLES + 104;
+constexpr long TOTAL = ((OFF_HQ + NMAIN * LDH + 15) / 16) * 16;
 // The literal multiplier update's stacked KKT matrix is not part of the block: 2 NQMAX (NQMAX + 1) doubles (580 KB) that
 // only the 0.25 % of solves which fall back to it ever touch -- one per resident warp (Work::kkt), not one per solve in flight.
 constexpr long KKT_DOUBLES = ((2L * NQMAX * (NQMAX + 1) + 15) / 16) * 16;
@@ -2273,6 +2276,73 @@ WBC_HDN void solve_stage_update(const Ex& ex, const Work& w, const Settings& cfg
         s.done = 1;
     }
 }
+
+// ---- Finer stages for the solver kernel's SM roles: the QQP iteration alone (its hot code is ~25 KB and fits an SM's
+// instruction cache) against everything else.
+//   stage_post_and_model  after a QQP call: violations, working set, and -- when the working set has settled -- the multiplier
+//                         update; then the extended model of the NEXT QQP call, written to the solve's global block.
+//                         Returns 1 when a QQP task must follow, 0 when the solve is complete (s.done).
+//                         Spilled working sets (rare) run their generic QQP right here.
+//   stage_qqp_load/store  (device) the QQP task: model in, qqp_optimize_fast, point out.
+template <class Ex>
+WBC_HDN int stage_post_and_model(const Ex& ex, const Work& w, const Settings& cfg, SolveState& s, bool after_qqp)
+{
+    const int nec = s.nec, nictotal = s.nrows - s.nec;
+    for (;;) {
+        if (after_qqp) {
+            s.qqp_calls++;
+            inequality_violations(ex, w, nec, nictotal);
+            s.flops += 2.0 * nictotal * NMAIN;
+            update_working_set(ex, w, nec, nictotal, s.nicwork, s.allowevict);
+            s.nicwork = W_ISCR(w)[1];
+            const bool extended = W_ISCR(w)[2] != 0;
+            ex.sync();
+            if (!extended) {
+                solve_stage_update(ex, w, cfg, s);
+                if (s.done) return 0;
+                s.outer_its++;
+            }
+        }
+        if (s.nicwork > NICCAP || nec * LDH + 48 > sl::STAGE_EQ_CAP) {
+            s.flags |= 32;
+            const int term = model_and_qqp<true>(ex, w, nec, s.nicwork, s.rho, s.epsx, &s.ncholesky, &s.flops);
+            if (term == -4) s.flags |= 4;
+            after_qqp = true;
+            continue;
+        }
+        generate_ex_model<false>(ex, w, nec, s.nicwork, s.rho);
+        s.flops += (double)NMAIN * NMAIN * (nec + s.nicwork) + 4.0 * NMAIN * (nec + s.nicwork);
+        // hand the model over: H, the (even-padded) CI rows, the linear term
+        const int nic2 = (s.nicwork + 1) & ~1;
+        double* gh = w.g + gl::OFF_HQ;
+        double* gc = w.g + gl::OFF_CI;
+        double* gb = w.g + gl::OFF_EXBG;
+        const double* H = W_H(w);
+        const double* CI = SM_(w, sl::OFF_CI);
+        const double* exb = W_EXB(w);
+#pragma unroll 1
+        for (int k = ex.lane(); k < NMAIN * LDH; k += Ex::NL) gh[k] = H[k];
+#pragma unroll 1
+        for (int k = ex.lane(); k < nic2 * LDH; k += Ex::NL) gc[k] = CI[k];
+#pragma unroll 1
+        for (int k = ex.lane(); k < NMAIN + s.nicwork; k += Ex::NL) gb[k] = exb[k];
+        ex.sync();
+        return 1;
+    }
+}
+#if defined(__CUDACC__)
+// The QQP task: stage the model (one cp.async round trip), iterate, leave the point in EXXC for stage_store.
+__device__ __forceinline__ void stage_qqp(const WarpEx& ex, const Work& w, SolveState& s)
+{
+    const int nic2 = (s.nicwork + 1) & ~1;
+    ex.copy_start(W_H(w), w.g + gl::OFF_HQ, NMAIN * LDH);
+    if (nic2 > 0) ex.copy_start(SM_(w, sl::OFF_CI), w.g + gl::OFF_CI, nic2 * LDH);
+    ex.copy_start(W_EXB(w), w.g + gl::OFF_EXBG, NMAIN + s.nicwork);
+    ex.copy_wait();
+    const int term = fast::qqp_optimize_fast(w, s.nicwork, s.rho, 0.01 * s.epsx, 50, &s.ncholesky, &s.flops, &s.chol_reused);
+    if (term == -4) s.flags |= 4;
+}
+#endif
 
 // The three stages back to back on one executor (the host emulation's check that they reproduce solve_denseaul).
 template <class Ex>

@@ -272,8 +272,17 @@ __global__ void __launch_bounds__(SOLVE_T) wbc_solve_staged_kernel(Params P, int
     ex.sync();
     unsigned smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    // role of this SM: every m_period-th group of m_group SMs runs SETUP / UPDATE tasks first, the others QLOOP tasks
-    const bool role_m = m_period > 0 && ((smid / (unsigned)m_group) % (unsigned)m_period) == (unsigned)(m_period - 1);
+    // Role of this SM.  m_period packs (nS << 16 | nP << 8 | den): of every `den` groups of m_group SMs (an SM pair = a TPC shares
+    // its instruction supply, so roles go by pairs), nS start new solves first (SETUP tasks: assemble + set-up), nP take POST tasks
+    // first (violations, working set, multiplier update, next model), the others QQP tasks.  Group indices are spread with a
+    // stride so that the roles interleave across the chip.
+    const unsigned r_ns = ((unsigned)m_period >> 16) & 255u, r_np = ((unsigned)m_period >> 8) & 255u, r_den = (unsigned)m_period & 255u;
+    int role = 0;                                                    // 0: QQP, 1: POST, 2: SETUP
+    if (r_den > 0) {
+        const unsigned gi = ((smid / (unsigned)m_group) * 7u) % r_den;
+        role = gi < r_ns ? 2 : (gi < r_ns + r_np ? 1 : 0);
+    }
+    const bool role_m = role != 0;
     volatile int* donep = &sq.ctl->done;
     volatile int* ticketp = &sq.ctl->ticket;
     int idle = 0;
@@ -285,28 +294,25 @@ __global__ void __launch_bounds__(SOLVE_T) wbc_solve_staged_kernel(Params P, int
         // ---- take a task: (kind, slot); kind 0 = QLOOP, 1 = UPDATE, 2 = SETUP (slot fresh, ticket drawn)
         int kind = -1, slot = -1, ticket = -1;
         if (ex.lane() == 0) {
-            const int first = role_m ? SQ_UPDATE : SQ_QLOOP;
-            slot = sq_pop(sq, first);
-            if (slot >= 0) kind = first;
-            if (kind < 0 && role_m && *ticketp < n) {                 // start a new solve
-                slot = sq_pop(sq, SQ_FREE);
-                if (slot >= 0) {
-                    ticket = atomicAdd(&sq.ctl->ticket, 1);
-                    if (ticket < n) kind = 2;
-                    else { sq_push(sq, SQ_FREE, slot); slot = -1; }
-                }
-            }
-            if (kind < 0) {                                          // own kind has run dry: take the other one
-                const int other = role_m ? SQ_QLOOP : SQ_UPDATE;
-                slot = sq_pop(sq, other);
-                if (slot >= 0) kind = other;
-            }
-            if (kind < 0 && !role_m && *ticketp < n) {
-                slot = sq_pop(sq, SQ_FREE);
-                if (slot >= 0) {
-                    ticket = atomicAdd(&sq.ctl->ticket, 1);
-                    if (ticket < n) kind = 2;
-                    else { sq_push(sq, SQ_FREE, slot); slot = -1; }
+            // preference order of the three sources of work by role; a source that has run dry is skipped
+            //   QQP SMs:   QQP ring, POST ring, new solve        POST SMs:  POST ring, new solve, QQP ring
+            //   SETUP SMs: new solve, POST ring, QQP ring
+            const int order3[3][3] = {{SQ_QLOOP, SQ_UPDATE, 2}, {SQ_UPDATE, 2, SQ_QLOOP}, {2, SQ_UPDATE, SQ_QLOOP}};
+#pragma unroll 1
+            for (int t = 0; t < 3 && kind < 0; t++) {
+                const int src = order3[role][t];
+                if (src == 2) {
+                    if (*ticketp < n) {                              // start a new solve: a free slot and a dispatch ticket
+                        slot = sq_pop(sq, SQ_FREE);
+                        if (slot >= 0) {
+                            ticket = atomicAdd(&sq.ctl->ticket, 1);
+                            if (ticket < n) kind = 2;
+                            else { sq_push(sq, SQ_FREE, slot); slot = -1; }
+                        }
+                    }
+                } else {
+                    slot = sq_pop(sq, src);
+                    if (slot >= 0) kind = src;
                 }
             }
             if (kind < 0 && *donep >= n) kind = -2;
@@ -326,7 +332,7 @@ __global__ void __launch_bounds__(SOLVE_T) wbc_solve_staged_kernel(Params P, int
         __threadfence();                                             // acquire: the slot as its last stage left it (also drops stale L1 lines)
         const long long t0 = clock64();
         pr_fence += (unsigned long long)(t0 - tf0);
-        if ((kind == SQ_QLOOP) == role_m && kind != 2) pr_steal++;
+        if (kind != role) pr_steal++;
         w.g = slot_base + (long)slot * gl::TOTAL;
         double* hdr = w.g + gl::OFF_HDR;
         double* rec = SM_(w, sl::OFF_CI);
@@ -365,14 +371,17 @@ __global__ void __launch_bounds__(SOLVE_T) wbc_solve_staged_kernel(Params P, int
                 cfg.dup_start[0] = rt + 12; cfg.dup_count[0] = 12;
                 cfg.dup_start[1] = rq + 12; cfg.dup_count[1] = 12;
                 solve_stage_setup(ex, w, cfg, sh.nrows, sh.neq, st);
-                next = SQ_QLOOP;
+                if (!st.done) {
+                    st.outer_its++;
+                    if (stage_post_and_model(ex, w, cfg, st, false)) next = SQ_QLOOP;
+                }
             }
         } else {
             i = (int)hdr[HDR_INST];
             cyc0 = (long long)hdr[HDR_CYCLES];
             stage_load(ex, w, st);
-            if (kind == SQ_QLOOP) { solve_stage_qloop(ex, w, st); next = SQ_UPDATE; }
-            else { solve_stage_update(ex, w, cfg, st); next = SQ_QLOOP; }
+            if (kind == SQ_QLOOP) { stage_qqp(ex, w, st); next = SQ_UPDATE; }
+            else if (stage_post_and_model(ex, w, cfg, st, true)) next = SQ_QLOOP;
         }
         if (!finished && st.done) {
             // ---- the solve is complete: torque map and outputs (as in wbc_solve_kernel)
@@ -423,7 +432,7 @@ __global__ void __launch_bounds__(SOLVE_T) wbc_solve_staged_kernel(Params P, int
     if (prof && ex.lane() == 0) {
         unsigned long long* p = prof + (long)blockIdx.x * 12;
         p[0] = pr_cyc[0]; p[1] = pr_cyc[1]; p[2] = pr_cyc[2]; p[3] = pr_cnt[0]; p[4] = pr_cnt[1]; p[5] = pr_cnt[2];
-        p[6] = pr_wait; p[7] = pr_fence; p[8] = pr_steal; p[9] = (unsigned long long)(clock64() - k0); p[10] = role_m ? 1ull : 0ull; p[11] = smid;
+        p[6] = pr_wait; p[7] = pr_fence; p[8] = pr_steal; p[9] = (unsigned long long)(clock64() - k0); p[10] = (unsigned long long)role; p[11] = smid;
     }
 }
 
@@ -460,12 +469,18 @@ __global__ void __launch_bounds__(SOLVE_T) wbc_dense_qp_kernel(Params P, int n, 
         const int i = next_instance(queue);
         if (i >= n) break;
         double* H = W_H(w);
-        for (int k = ex.lane(); k < 900; k += SOLVE_T) H[(k / 30) * LDH + (k % 30)] = Q[(long)i * 900 + k];
-        for (int k = ex.lane(); k < 30; k += SOLVE_T) W_EXB(w)[k] = c[(long)i * 30 + k];
-        for (int k = ex.lane(); k < nrows * 31; k += SOLVE_T) W_C(w)[k] = L[(long)i * nrows * 31 + k];
+        double chk = 0.0;                      // x * 0 is NaN exactly for NaN and the infinities
+        for (int k = ex.lane(); k < 900; k += SOLVE_T) { const double v = Q[(long)i * 900 + k]; H[(k / 30) * LDH + (k % 30)] = v; chk += v * 0.0; }
+        for (int k = ex.lane(); k < 30; k += SOLVE_T) { const double v = c[(long)i * 30 + k]; W_EXB(w)[k] = v; chk += v * 0.0; }
+        for (int k = ex.lane(); k < nrows * 31; k += SOLVE_T) { const double v = L[(long)i * nrows * 31 + k]; W_C(w)[k] = v; chk += v * 0.0; }
         ex.sync();
         Stats st;
-        solve_denseaul(ex, w, cfg, nrows, neq, st);
+        if (__any_sync(0xffffffffu, chk != 0.0)) {
+            // a non-finite coefficient: nothing is solved (ALGLIB would throw or return garbage; the reference swallows both, lopt.cpp:114-116)
+            st.termination = WBC_ST_NONFINITE; st.ncholesky = 0; st.outer_its = 0; st.qqp_calls = 0; st.nicwork = 0; st.kkt_dim_max = 0;
+            st.chol_reused = 0; st.flags = 0; st.flops = 0.0;
+        } else
+            solve_denseaul(ex, w, cfg, nrows, neq, st);
         // a failed instance returns x = 0, like wbc_cycle (never a previous call's solution left in the staging block)
         for (int k = ex.lane(); k < 30; k += SOLVE_T) x[(long)i * 30 + k] = (st.termination == 2) ? W_XS(w)[k] : 0.0;
         if (ex.lane() == 0) {   // instance-major info [n][8] on this path
@@ -537,6 +552,14 @@ __global__ void __launch_bounds__(128) wbc_plant_kernel(Params P, int n, const d
     if (base_pos) {
         base_pos[0 * ld + i] += P.obs_dt * vx; base_pos[1 * ld + i] += P.obs_dt * vy; base_pos[2 * ld + i] += P.obs_dt * vz;
     }
+}
+
+// Forward-dynamics plant, thread per instance (wbc_front.cuh, fdyn_step_instance).
+__global__ void __launch_bounds__(64) wbc_fdyn_kernel(Params P, wbc::FdynIO io, int n, int nsub, double gamma)
+{
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    wbc::fdyn_step_instance(P, io, i, nsub, gamma);
 }
 
 // FP64 DFMA peak: 8 independent chains per thread, fully unrolled.
@@ -710,9 +733,12 @@ int wbc_create(wbc_ctx** out, int device, int max_batch, const wbc_params* param
     // Which solver kernel: one warp per solve (default) or stage tasks with SM roles (WBC_SOLVER=staged).  Measured on B200
     // (profiles/README.md, round 2): equal at 65 536 instances (43.8 vs 44.1 ms), the staged kernel loses at 4 096 (3.8 vs 3.2 ms:
     // a solve is seven hand-overs and the batch is only 2.3 solves per warp) -- it stays selectable, with its evidence.
-    c->staged = 0; c->m_period = 3; c->m_group = 1;
+    c->staged = 0; c->m_period = (0 << 16) | (2 << 8) | 5; c->m_group = 2;       // of every 5 SM pairs: 2 POST/SETUP, 3 QQP
     if (const char* ev = getenv("WBC_SOLVER")) c->staged = strcmp(ev, "staged") == 0;
-    if (const char* ev = getenv("WBC_STAGE_M_PERIOD")) c->m_period = atoi(ev);
+    if (const char* ev = getenv("WBC_STAGE_ROLES")) {        // "nS,nP/den"
+        int a = 0, b = 2, d = 5;
+        if (sscanf(ev, "%d,%d/%d", &a, &b, &d) == 3 && d > 0 && d < 256 && a >= 0 && b >= 0 && a + b <= d) c->m_period = (a << 16) | (b << 8) | d;
+    }
     if (const char* ev = getenv("WBC_STAGE_M_GROUP")) c->m_group = atoi(ev) > 0 ? atoi(ev) : 1;
     double slots_per_warp = 1.5;
     if (const char* ev = getenv("WBC_STAGE_SLOTS_PER_WARP")) slots_per_warp = atof(ev) >= 1.0 ? atof(ev) : 1.0;
@@ -1118,6 +1144,55 @@ int wbc_plant_step(wbc_ctx* c, int n, double* base_pos, double* base_vel, double
         if (base_pos) for (int k = 0; k < 3; k++) memcpy(base_pos + (size_t)k * ld, c->h_pin + (size_t)k * n, (size_t)n * 8);
         for (int k = 0; k < 6; k++) memcpy(base_vel + (size_t)k * ld, c->h_pin + (size_t)(3 + k) * n, (size_t)n * 8);
         if (foot_force) for (int k = 0; k < 12; k++) memcpy(foot_force + (size_t)k * ld, c->h_pin + (size_t)(9 + k) * n, (size_t)n * 8);
+    } else if (!(flags & WBC_NO_SYNC)) {
+        CU(cudaStreamSynchronize(s));
+    }
+    return WBC_OK;
+}
+
+int wbc_plant_dynamics_step(wbc_ctx* c, int n, const wbc_plant_state* st, const double* tau, const double* push, long ld, int substeps,
+                            double gamma, double* diag, void* cuda_stream, unsigned flags)
+{
+    if (!c || !st || !tau || !push) return fail(WBC_EINVAL, "wbc_plant_dynamics_step: null argument");
+    if (!st->base_pos || !st->base_rot || !st->base_rpy || !st->base_vel || !st->q || !st->dq || !st->foot_force || !st->mode)
+        return fail(WBC_EINVAL, "wbc_plant_dynamics_step: a state array is NULL");
+    if (n < 0 || n > c->max_batch || ld < n) return fail(WBC_EINVAL, "wbc_plant_dynamics_step: n outside [0, max_batch] or ld < n");
+    if (substeps < 1 || substeps > 1000) return fail(WBC_EINVAL, "wbc_plant_dynamics_step: substeps outside [1, 1000]");
+    if (n == 0) { c->launches = 0; return WBC_OK; }
+    CU(cudaSetDevice(c->device));
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : c->stream;
+    const bool dev_ptrs = (flags & WBC_DEVICE_PTRS) != 0;
+    wbc::FdynIO io;
+    static const int K[7] = {3, 9, 3, 6, 12, 12, 12};
+    double* host[7] = {st->base_pos, st->base_rot, st->base_rpy, st->base_vel, st->q, st->dq, st->foot_force};
+    const size_t N = (size_t)n;
+    if (dev_ptrs) {
+        io.base_pos = st->base_pos; io.base_rot = st->base_rot; io.base_rpy = st->base_rpy; io.base_vel = st->base_vel; io.q = st->q; io.dq = st->dq;
+        io.foot_force = st->foot_force; io.mode = st->mode; io.tau = tau; io.push = push; io.diag = diag; io.ld = ld;
+    } else {
+        // packed staging in the ctx's input buffer: state 57 rows | tau 12 | push 6 | diag 2
+        double* h = c->h_pin;
+        size_t off = 0;
+        for (int f = 0; f < 7; f++)
+            for (int k = 0; k < K[f]; k++, off++) memcpy(h + off * N, host[f] + (size_t)k * ld, N * 8);
+        for (int k = 0; k < 12; k++, off++) memcpy(h + off * N, tau + (size_t)k * ld, N * 8);
+        for (int k = 0; k < 6; k++, off++) memcpy(h + off * N, push + (size_t)k * ld, N * 8);
+        CU(cudaMemcpyAsync(c->d_in, h, off * N * 8, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(c->d_mode, st->mode, N * sizeof(int), cudaMemcpyHostToDevice, s));
+        double* d = c->d_in;
+        io.base_pos = d; io.base_rot = d + 3 * N; io.base_rpy = d + 12 * N; io.base_vel = d + 15 * N; io.q = d + 21 * N; io.dq = d + 33 * N;
+        io.foot_force = d + 45 * N; io.tau = d + 57 * N; io.push = d + 69 * N; io.diag = d + 75 * N; io.mode = c->d_mode; io.ld = n;
+    }
+    wbc_fdyn_kernel<<<(n + 63) / 64, 64, 0, s>>>(c->params, io, n, substeps, gamma);
+    CU(cudaGetLastError());
+    c->launches = 1;
+    if (!dev_ptrs) {
+        CU(cudaMemcpyAsync(c->h_pin, c->d_in, (size_t)77 * N * 8, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        size_t off = 0;
+        for (int f = 0; f < 7; f++)
+            for (int k = 0; k < K[f]; k++, off++) memcpy(host[f] + (size_t)k * ld, c->h_pin + off * N, N * 8);
+        if (diag) for (int k = 0; k < 2; k++) memcpy(diag + (size_t)k * ld, c->h_pin + (size_t)(75 + k) * N, N * 8);
     } else if (!(flags & WBC_NO_SYNC)) {
         CU(cudaStreamSynchronize(s));
     }

@@ -127,23 +127,34 @@ struct FrontState {        // observer state carried across cycles (main.cpp:721
     long ld;
 };
 
-// One instance.  `i` indexes the SoA arrays; `rec` points at this instance's QP record.
-WBC_DEVFN inline void front_cycle(const Params& P, const DevInputs& in, const FrontState& st, long i, double* rec,
-                                double* w_out, long w_ld, const DevDebug* dbg)
+// Floating-base dynamics of one instance in the MIXED representation (the first half of update(), main.cpp:591-630): mass-matrix
+// blocks, bias and gravity forces, foot kinematics.  Shared by the control cycle (front_cycle) and the forward-dynamics plant.
+struct FrontDyn {
+    V3 p0, v0, w0;
+    M3 R0;
+    double Mb[36], Mbj[72], Mjj[144];    // mass-matrix blocks (base-base, base-joint, joint-joint)
+    double hb[6], hj[12], gb[6], gj[12];
+    V3 mr, mvrel;                        // sum m_i r_i (r relative to the base origin); sum m_i (v_ci - v0)
+    V3 footp[4], footv[4], foota[4];     // canonical leg order; relative position, velocity, bias acceleration
+    M3 footR[4];
+    double Jleg[4][9];                   // d(foot velocity)/d(dq of its leg), [axis][k]
+};
+
+WBC_DEVFN inline void front_dynamics(const Params& P, const DevInputs& in, long i, FrontDyn& D)
 {
     using namespace dogbot;
     const long ld = in.ld;
 #define LD1(ptr, k) (ptr)[(long)(k) * ld + i]
-    const V3 p0 = v3(LD1(in.base_pos, 0), LD1(in.base_pos, 1), LD1(in.base_pos, 2));
-    M3 R0;
+    D.p0 = v3(LD1(in.base_pos, 0), LD1(in.base_pos, 1), LD1(in.base_pos, 2));
+    M3& R0 = D.R0;
     for (int k = 0; k < 9; k++) R0.m[k] = LD1(in.base_rot, k);
-    const V3 v0 = v3(LD1(in.base_vel, 0), LD1(in.base_vel, 1), LD1(in.base_vel, 2));
-    const V3 w0 = v3(LD1(in.base_vel, 3), LD1(in.base_vel, 4), LD1(in.base_vel, 5));
+    D.v0 = v3(LD1(in.base_vel, 0), LD1(in.base_vel, 1), LD1(in.base_vel, 2));
+    D.w0 = v3(LD1(in.base_vel, 3), LD1(in.base_vel, 4), LD1(in.base_vel, 5));
+    const V3 v0 = D.v0, w0 = D.w0;
     const V3 grav = v3(P.gravity[0], P.gravity[1], P.gravity[2]);
-    const int mode = in.mode[i];
 
-    double Mb[36], Mbj[72], Mjj[144];    // mass-matrix blocks (base-base, base-joint, joint-joint)
-    double hb[6], hj[12], gb[6], gj[12];
+    double (&Mb)[36] = D.Mb; double (&Mbj)[72] = D.Mbj; double (&Mjj)[144] = D.Mjj;
+    double (&hb)[6] = D.hb; double (&hj)[12] = D.hj; double (&gb)[6] = D.gb; double (&gj)[12] = D.gj;
     for (int k = 0; k < 144; k++) Mjj[k] = 0.0;
 
     // ---- base body (body + bodytext lumped, CoM at the base origin)
@@ -160,9 +171,9 @@ WBC_DEVFN inline void front_cycle(const Params& P, const DevInputs& in, const Fr
         gftot = ftot;
         gntot = v3(0, 0, 0);
     }
-    V3 footp[4], footv[4], foota[4];   // canonical leg order; relative position, velocity, bias acceleration
-    M3 footR[4];
-    double Jleg[4][9];                 // d(foot velocity)/d(dq of its leg), [axis][k]
+    V3 (&footp)[4] = D.footp; V3 (&footv)[4] = D.footv; V3 (&foota)[4] = D.foota;
+    M3 (&footR)[4] = D.footR;
+    double (&Jleg)[4][9] = D.Jleg;
 
     for (int leg = 0; leg < 4; leg++) {
         V3 pj[3], z[3], c[3], f[3], n[3], fg[3];
@@ -267,6 +278,29 @@ WBC_DEVFN inline void front_cycle(const Params& P, const DevInputs& in, const Fr
     hb[0] = ftot.x; hb[1] = ftot.y; hb[2] = ftot.z; hb[3] = ntot.x; hb[4] = ntot.y; hb[5] = ntot.z;
     gb[0] = gftot.x; gb[1] = gftot.y; gb[2] = gftot.z; gb[3] = gntot.x; gb[4] = gntot.y; gb[5] = gntot.z;
 
+    D.mr = mr; D.mvrel = mvrel;
+#undef LD1
+}
+
+// One instance.  `i` indexes the SoA arrays; `rec` points at this instance's QP record.
+WBC_DEVFN inline void front_cycle(const Params& P, const DevInputs& in, const FrontState& st, long i, double* rec,
+                                double* w_out, long w_ld, const DevDebug* dbg)
+{
+    using namespace dogbot;
+    const long ld = in.ld;
+#define LD1(ptr, k) (ptr)[(long)(k) * ld + i]
+    FrontDyn D;
+    front_dynamics(P, in, i, D);
+    const V3 p0 = D.p0, v0 = D.v0, w0 = D.w0;
+    const M3& R0 = D.R0;
+    const int mode = in.mode[i];
+    double (&Mb)[36] = D.Mb; double (&Mbj)[72] = D.Mbj; double (&Mjj)[144] = D.Mjj;
+    double (&hb)[6] = D.hb; double (&hj)[12] = D.hj; double (&gb)[6] = D.gb; double (&gj)[12] = D.gj;
+    const V3 mr = D.mr, mvrel = D.mvrel;
+    V3 (&footp)[4] = D.footp; V3 (&footv)[4] = D.footv; V3 (&foota)[4] = D.foota;
+    M3 (&footR)[4] = D.footR;
+    double (&Jleg)[4][9] = D.Jleg;
+    const double mtot = kTotalMass;
     // CoM (getCenterOfMassPosition / Velocity, main.cpp:597-602)
     const V3 xbc = (1.0 / mtot) * mr;                 // com - base            main.cpp:518
     const V3 xbcd = (1.0 / mtot) * mvrel;             // com_vel - v_base      main.cpp:538
@@ -513,6 +547,204 @@ WBC_DEVFN inline void front_cycle(const Params& P, const DevInputs& in, const Fr
 #undef ST1
     }
 #undef LD1
+}
+
+// ---- Forward dynamics with hard contacts: the closed-loop plant that stands in for Gazebo + ModelPush
+// (force_plugin.cpp:124-491).  One control period of instance i under joint torques tau, a world wrench `push` at the CoM and
+// rigid bilateral point contacts at the stance feet of its mode; the state arrays of `in` are advanced IN PLACE
+// (base_pos, base_rot, base_rpy, base_vel, q, dq) and foot_force receives the contact forces in the sensor frames.
+//     M nu_dot + h = S'tau + push_gen + Js' f,     Js nu_dot = -Jdqd_s - gamma Js nu
+// solved through the Schur complement of the contact forces: M = L L' (18 x 18 Cholesky), Y = L^-1 Js', A = Y'Y,
+// f = A^-1 (c - Js M^-1 b), nu_dot = M^-1 (b + Js' f) -- a different route from the oracle's dense 30 x 30 elimination
+// (oracle/wbc_oracle.c, wbc_oracle_fdyn_step).  nsub semi-implicit Euler substeps.  diag (optional, [2][ld]): largest
+// contact-constraint residual, smallest normal force.
+struct FdynIO {
+    double *base_pos, *base_rot, *base_rpy, *base_vel, *q, *dq, *foot_force;   // state, SoA [k][ld], read and written
+    const int* mode;
+    const double *tau, *push;           // [12][ld], [6][ld]
+    double* diag;                       // [2][ld] or nullptr
+    long ld;
+};
+
+WBC_DEVFN inline void fdyn_step_instance(const Params& P, const FdynIO& io, long i, int nsub, double gamma)
+{
+    using namespace dogbot;
+    const long ld = io.ld;
+    DevInputs in;
+    in.base_pos = io.base_pos; in.base_rot = io.base_rot; in.base_rpy = io.base_rpy; in.base_vel = io.base_vel; in.q = io.q; in.dq = io.dq;
+    in.com_des_pos = in.com_des_vel = in.com_des_acc = in.sw_des_pos = in.sw_des_vel = in.sw_des_acc = nullptr;
+    in.foot_force = io.foot_force; in.terrain = nullptr; in.mode = io.mode; in.obs_gain = nullptr; in.ld = ld;
+    const int mode = io.mode[i];
+    int stance[4], ns = 0;
+    for (int sf = 0; sf < 4; sf++) {
+        const bool swing = (mode == MODE_SWING_BR_FL && (sf == 0 || sf == 2)) || (mode == MODE_SWING_BL_FR && (sf == 1 || sf == 3));
+        stance[sf] = swing ? 0 : 1;
+        ns += stance[sf];
+    }
+    const int nc = 3 * ns;
+    const double dt = P.obs_dt / (double)nsub;
+    double tau[12], push[6];
+    for (int k = 0; k < 12; k++) tau[k] = io.tau[(long)k * ld + i];
+    for (int k = 0; k < 6; k++) push[k] = io.push[(long)k * ld + i];
+    double worst = 0.0, fzmin = 1.0e300;
+    for (int it = 0; it < nsub; it++) {
+        FrontDyn D;
+        front_dynamics(P, in, i, D);
+        // M (18 x 18, lower triangle) and its Cholesky factor
+        double L[18 * 18];
+        for (int a = 0; a < 18; a++)
+            for (int b = 0; b <= a; b++) {
+                double v;
+                if (a < 6) v = D.Mb[a * 6 + b];
+                else if (b < 6) v = D.Mbj[b * 12 + (a - 6)];
+                else v = D.Mjj[(a - 6) * 12 + (b - 6)];
+                L[a * 18 + b] = v;
+            }
+        for (int j = 0; j < 18; j++) {
+            double d = L[j * 18 + j];
+            for (int k = 0; k < j; k++) d -= L[j * 18 + k] * L[j * 18 + k];
+            d = sqrt(d);
+            L[j * 18 + j] = d;
+            const double r = 1.0 / d;
+            for (int a = j + 1; a < 18; a++) {
+                double sacc = L[a * 18 + j];
+                for (int k = 0; k < j; k++) sacc -= L[a * 18 + k] * L[j * 18 + k];
+                L[a * 18 + j] = sacc * r;
+            }
+        }
+        // generalised velocity, right-hand side b = S'tau - h + push_gen
+        double nu[18], b[18];
+        nu[0] = D.v0.x; nu[1] = D.v0.y; nu[2] = D.v0.z; nu[3] = D.w0.x; nu[4] = D.w0.y; nu[5] = D.w0.z;
+        for (int k = 0; k < 12; k++) nu[6 + k] = io.dq[(long)k * ld + i];
+        const V3 xbc = (1.0 / kTotalMass) * D.mr;
+        const V3 tq = cross(xbc, v3(push[0], push[1], push[2]));
+        for (int k = 0; k < 6; k++) b[k] = -D.hb[k] + push[k];
+        b[3] += tq.x; b[4] += tq.y; b[5] += tq.z;
+        for (int k = 0; k < 12; k++) b[6 + k] = -D.hj[k] + tau[k];
+        // stance rows of the linear foot Jacobian (base columns [I, -S(rf)], the leg's three joint columns) and their targets
+        double Js[12 * 18], c[12];
+        int r = 0;
+        for (int sf = 0; sf < 4; sf++) {
+            if (!stance[sf]) continue;
+            const int leg = kFootLeg[sf];
+            const V3 rf = D.footp[leg];
+            const double nSf[9] = {0, rf.z, -rf.y, -rf.z, 0, rf.x, rf.y, -rf.x, 0};
+            for (int a = 0; a < 3; a++, r++) {
+                double* row = Js + r * 18;
+                for (int k = 0; k < 18; k++) row[k] = 0.0;
+                row[a] = 1.0;
+                for (int k = 0; k < 3; k++) row[3 + k] = nSf[a * 3 + k];
+                for (int k = 0; k < 3; k++) row[6 + dof_index(leg, k)] = D.Jleg[leg][a * 3 + k];
+                double jn = 0.0;
+                for (int k = 0; k < 18; k++) jn += row[k] * nu[k];
+                c[r] = -comp(D.foota[leg], a) - gamma * jn;
+            }
+        }
+        // a0 = M^-1 b
+        double a0[18];
+        for (int a = 0; a < 18; a++) {
+            double sacc = b[a];
+            for (int k = 0; k < a; k++) sacc -= L[a * 18 + k] * a0[k];
+            a0[a] = sacc / L[a * 18 + a];
+        }
+        for (int a = 17; a >= 0; a--) {
+            double sacc = a0[a];
+            for (int k = a + 1; k < 18; k++) sacc -= L[k * 18 + a] * a0[k];
+            a0[a] = sacc / L[a * 18 + a];
+        }
+        // Y = L^-1 Js' (column r of Y in row r of Ym), A = Y'Y, rhs = c - Js a0
+        double Ym[12 * 18], A[12 * 12], f[12];
+        for (int rr = 0; rr < nc; rr++) {
+            double* y = Ym + rr * 18;
+            for (int a = 0; a < 18; a++) {
+                double sacc = Js[rr * 18 + a];
+                for (int k = 0; k < a; k++) sacc -= L[a * 18 + k] * y[k];
+                y[a] = sacc / L[a * 18 + a];
+            }
+        }
+        for (int p_ = 0; p_ < nc; p_++) {
+            for (int q_ = 0; q_ <= p_; q_++) {
+                double sacc = 0.0;
+                for (int k = 0; k < 18; k++) sacc += Ym[p_ * 18 + k] * Ym[q_ * 18 + k];
+                A[p_ * 12 + q_] = sacc;
+            }
+            double sacc = c[p_];
+            for (int k = 0; k < 18; k++) sacc -= Js[p_ * 18 + k] * a0[k];
+            f[p_] = sacc;
+        }
+        for (int j = 0; j < nc; j++) {                    // Cholesky of A, in place (lower)
+            double d = A[j * 12 + j];
+            for (int k = 0; k < j; k++) d -= A[j * 12 + k] * A[j * 12 + k];
+            d = sqrt(d);
+            A[j * 12 + j] = d;
+            for (int a = j + 1; a < nc; a++) {
+                double sacc = A[a * 12 + j];
+                for (int k = 0; k < j; k++) sacc -= A[a * 12 + k] * A[j * 12 + k];
+                A[a * 12 + j] = sacc / d;
+            }
+        }
+        for (int a = 0; a < nc; a++) {
+            double sacc = f[a];
+            for (int k = 0; k < a; k++) sacc -= A[a * 12 + k] * f[k];
+            f[a] = sacc / A[a * 12 + a];
+        }
+        for (int a = nc - 1; a >= 0; a--) {
+            double sacc = f[a];
+            for (int k = a + 1; k < nc; k++) sacc -= A[k * 12 + a] * f[k];
+            f[a] = sacc / A[a * 12 + a];
+        }
+        // nu_dot = a0 + M^-1 Js' f
+        double nd[18];
+        for (int a = 0; a < 18; a++) {
+            double sacc = 0.0;
+            for (int rr = 0; rr < nc; rr++) sacc += Js[rr * 18 + a] * f[rr];
+            nd[a] = sacc;
+        }
+        for (int a = 0; a < 18; a++) {
+            double sacc = nd[a];
+            for (int k = 0; k < a; k++) sacc -= L[a * 18 + k] * nd[k];
+            nd[a] = sacc / L[a * 18 + a];
+        }
+        for (int a = 17; a >= 0; a--) {
+            double sacc = nd[a];
+            for (int k = a + 1; k < 18; k++) sacc -= L[k * 18 + a] * nd[k];
+            nd[a] = sacc / L[a * 18 + a];
+        }
+        for (int a = 0; a < 18; a++) nd[a] += a0[a];
+        for (int rr = 0; rr < nc; rr++) {
+            double ja = 0.0;
+            for (int k = 0; k < 18; k++) ja += Js[rr * 18 + k] * nd[k];
+            worst = fmax(worst, fabs(ja - c[rr]));
+        }
+        // contact forces in the sensor frames (what the contact sensors report, main.cpp:794-834)
+        r = 0;
+        for (int sf = 0; sf < 4; sf++) {
+            double fs[3] = {0.0, 0.0, 0.0};
+            if (stance[sf]) {
+                const M3& Rf = D.footR[kFootLeg[sf]];
+                for (int k = 0; k < 3; k++) fs[k] = Rf.m[k] * f[r] + Rf.m[3 + k] * f[r + 1] + Rf.m[6 + k] * f[r + 2];
+                fzmin = fmin(fzmin, f[r + 2]);
+                r += 3;
+            }
+            for (int k = 0; k < 3; k++) io.foot_force[(long)(3 * sf + k) * ld + i] = fs[k];
+        }
+        // semi-implicit Euler: velocities first, then the configuration with the new velocities
+        for (int a = 0; a < 18; a++) nu[a] += dt * nd[a];
+        for (int k = 0; k < 6; k++) io.base_vel[(long)k * ld + i] = nu[k];
+        for (int k = 0; k < 12; k++) {
+            io.dq[(long)k * ld + i] = nu[6 + k];
+            io.q[(long)k * ld + i] += dt * nu[6 + k];
+        }
+        for (int k = 0; k < 3; k++) io.base_pos[(long)k * ld + i] += dt * nu[k];
+        M3 Rn = D.R0;
+        const double wn = sqrt(nu[3] * nu[3] + nu[4] * nu[4] + nu[5] * nu[5]);
+        if (wn > 0.0) Rn = mul(axis_rotation(v3(nu[3] / wn, nu[4] / wn, nu[5] / wn), wn * dt), D.R0);
+        for (int k = 0; k < 9; k++) io.base_rot[(long)k * ld + i] = Rn.m[k];
+        io.base_rpy[0 * ld + i] = atan2(Rn.m[7], Rn.m[8]);
+        io.base_rpy[1 * ld + i] = atan2(-Rn.m[6], sqrt(Rn.m[7] * Rn.m[7] + Rn.m[8] * Rn.m[8]));
+        io.base_rpy[2 * ld + i] = atan2(Rn.m[3], Rn.m[0]);
+    }
+    if (io.diag) { io.diag[0 * ld + i] = worst; io.diag[1 * ld + i] = (ns > 0) ? fzmin : 0.0; }
 }
 
 }  // namespace wbc
