@@ -556,7 +556,7 @@ WBC_DEVFN inline void front_cycle(const Params& P, const DevInputs& in, const Fr
 //     M nu_dot + h = S'tau + push_gen + Js' f,     Js nu_dot = -Jdqd_s - gamma Js nu
 // solved through the Schur complement of the contact forces: M = L L' (18 x 18 Cholesky), Y = L^-1 Js', A = Y'Y,
 // f = A^-1 (c - Js M^-1 b), nu_dot = M^-1 (b + Js' f) -- a different route from the oracle's dense 30 x 30 elimination
-// (oracle/wbc_oracle.c, wbc_oracle_fdyn_step).  nsub semi-implicit Euler substeps.  diag (optional, [2][ld]): largest
+// (the test oracle restates the same step with one 30 x 30 Gauss-Jordan).  nsub semi-implicit Euler substeps.  diag (optional, [2][ld]): largest
 // contact-constraint residual, smallest normal force.
 struct FdynIO {
     double *base_pos, *base_rot, *base_rpy, *base_vel, *q, *dq, *foot_force;   // state, SoA [k][ld], read and written
