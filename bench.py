@@ -323,7 +323,7 @@ def bench_batch(env, args, name, steps, warmup, per_gpu=None, cpu_baseline=False
     torch.cuda.synchronize()
     occ, smem, grid_ctas = batch.solver_shape()
     config["solver_launch"] = "%d persistent one-warp CTAs (up to %d resident per SM; %d B of shared memory per solve), %s" % (
-        grid_ctas, occ, smem, "stage tasks with SM roles" if os.environ.get("WBC_SOLVER", "") == "staged" else "one warp per solve")
+        grid_ctas, occ, smem, "stage tasks with SM roles" if batch.last_solver_kernel == "wbc_solve_staged_kernel" else "one warp per solve")
     status = stat_out["status"].cpu().numpy()
     qp_info = stat_out["qp_info"].cpu().numpy()
     qp_flops = stat_out["qp_flops"].cpu().numpy()
@@ -431,7 +431,7 @@ def bench_batch(env, args, name, steps, warmup, per_gpu=None, cpu_baseline=False
                 traffic, traffic_src = tr["bytes_per_launch"], tr["source"]
         except Exception:
             pass
-        roofline = {"bound": "fp64", "kernel": "wbc_solve_staged_kernel" if os.environ.get("WBC_SOLVER", "") == "staged" else "wbc_solve_kernel",
+        roofline = {"bound": "fp64", "kernel": batch.last_solver_kernel,
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                     "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write)", "traffic_source": traffic_src,
                     "algorithmic_bytes_per_launch": alg_bytes,

@@ -43,7 +43,6 @@ def bench_trot_rollout(env, args):
     host_sc = [S.trot_rollout(n, t, start=start) for t in range(total_steps)]
     dev_sc = [{k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in sc.items()} for sc in host_sc]
     batch = api.WbcBatch(max_batch=n, device=env.local_rank)
-    occ, smem, grid_ctas = batch.solver_shape()
     dev_out = {"tau": torch.zeros(12, n, dtype=torch.float64, device=dev), "w": torch.zeros(6, n, dtype=torch.float64, device=dev)}
     stat_out = dict(dev_out)
     stat_out.update(status=torch.zeros(n, dtype=torch.int32, device=dev), qp_info=torch.zeros(8, n, dtype=torch.int32, device=dev),
@@ -101,6 +100,7 @@ def bench_trot_rollout(env, args):
     tot_ms, fifo_tot, e2e_s = env.max_over_ranks([float(step_ms.sum()), float(fifo_ms.sum()), e2e_s])
     stats = sharding.gather_stats(sharding.local_stats(n, status, qp_info, qp_flops, ms=tot_ms / steps), device=dev)
     line = None
+    occ, smem, grid_ctas = batch.solver_shape()
     if rank == 0:
         total = n * world
         solve_avg = float(np.mean(solve_ms))
@@ -122,7 +122,7 @@ def bench_trot_rollout(env, args):
                                         "robots_changing_mode_per_cycle": float(np.mean(flips))},
                 "e2e": {"value": total * steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": n * B.IN_BYTES, "d2h_bytes_per_step": n * B.OUT_BYTES},
                 "gpu_launches": 2 * steps, "e2e_gpu_launches": 2 * steps,
-                "roofline": {"bound": "fp64", "kernel": "wbc_solve_staged_kernel" if os.environ.get("WBC_SOLVER", "") == "staged" else "wbc_solve_kernel",
+                "roofline": {"bound": "fp64", "kernel": batch.last_solver_kernel,
                              "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
                              "algorithmic_bytes_per_launch": B.algorithmic_bytes(host_sc[-1]["mode"], False),
                              "flops_per_solve": float(qp_flops.mean()), "kernel_ms": solve_avg, "front_kernel_ms": float(np.mean(front_ms)),
@@ -155,7 +155,6 @@ def bench_push_sweep(env, args):
     sc = S.push_sweep(n=n, start=lo)
     sc.pop("grid", None)
     batch = api.WbcBatch(max_batch=n, device=env.local_rank)
-    occ, smem, grid_ctas = batch.solver_shape()
     batch.set_observer_state(sc["obs_yd"], sc["obs_yw"])
     din = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in sc.items() if isinstance(v, np.ndarray)}
     dout = {"tau": torch.zeros(12, n, dtype=torch.float64, device=dev), "w": torch.zeros(6, n, dtype=torch.float64, device=dev),
@@ -218,6 +217,7 @@ def bench_push_sweep(env, args):
     stats = sharding.gather_stats(sharding.local_stats(n, status, qp_info, qp_flops, ms=tot_ms / cycles), device=dev)
     solve_ms = batch.last_timing()[1]          # before the peak measurement, which reuses the ctx's events
     dfma_peak = batch.measure_dfma_peak()
+    occ, smem, grid_ctas = batch.solver_shape()
     line = None
     if rank == 0:
         cnt = sums[0:G]
@@ -239,7 +239,7 @@ def bench_push_sweep(env, args):
                 "e2e": {"value": total * cycles / wall, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                         "note": "a closed-loop rollout has no per-cycle host traffic: the plant runs on the device; wall clock of the whole rollout including the per-cycle metric reductions"},
                 "gpu_launches": 3 * cycles,
-                "roofline": {"bound": "fp64", "kernel": "wbc_solve_staged_kernel" if os.environ.get("WBC_SOLVER", "") == "staged" else "wbc_solve_kernel",
+                "roofline": {"bound": "fp64", "kernel": batch.last_solver_kernel,
                              "achieved": achieved, "peak": dfma_peak / 1e12, "unit": "TFLOP/s", "frac": achieved / (dfma_peak / 1e12), "traffic": None,
                              "kernel_ms": float(solve_ms), "flops_per_solve": float(qp_flops.mean())},
                 "stats": {"solver_failures": stats["solver_failures"], "mean_ncholesky": stats["sum_ncholesky"] / total, "wall_s_timed_region": wall,

@@ -217,9 +217,10 @@ int wbc_last_solve_cycles(wbc_ctx* ctx, int n, unsigned long long* cycles);
 int wbc_last_launches(wbc_ctx* ctx);
 /* Launch shape of the persistent solver kernel: resident CTAs (= warps) per SM as the occupancy calculator reports them
  * for this device, dynamic shared memory per CTA in bytes, and the grid of the last wbc_cycle (before any: SMs x resident
- * CTAs; small batches are launched with fewer CTAs per SM).  Any pointer may be NULL.
+ * CTAs; small batches are launched with fewer CTAs per SM), and which solver kernel the last wbc_cycle ran (0: one warp per
+ * solve, 1: stage tasks with SM roles -- chosen by batch size).  Any pointer may be NULL.
  * Measurement only (bench.py reports it beside the roofline); the reference has no counterpart. */
-int wbc_solver_shape(wbc_ctx* ctx, int* ctas_per_sm, int* smem_bytes, int* grid);
+int wbc_solver_shape(wbc_ctx* ctx, int* ctas_per_sm, int* smem_bytes, int* grid, int* stage_tasks);
 /* Per-warp profile of the last solver launch when the ctx was created with WBC_STAGE_PROF=1 in the environment: rows of 12
  * counters (cycles in QLOOP / UPDATE / SETUP tasks, their counts, cycles looking for a task, cycles in fences and queue
  * operations, tasks taken from the other role's queue, cycles in the kernel, role, SM id).  Returns the rows written (<= max_rows)

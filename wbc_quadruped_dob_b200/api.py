@@ -120,7 +120,7 @@ def load():
     lib.wbc_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     lib.wbc_last_solve_cycles.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_ulonglong)]
     lib.wbc_last_launches.argtypes = [C.c_void_p]
-    lib.wbc_solver_shape.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.wbc_solver_shape.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.wbc_stage_profile.argtypes = [C.c_void_p, C.POINTER(C.c_ulonglong), C.c_int]
     lib.wbc_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
     lib.wbc_host_free.argtypes = [C.c_void_p]
@@ -412,9 +412,10 @@ class WbcBatch:
         return int(self.lib.wbc_last_launches(self.h))
 
     def solver_shape(self):
-        """(resident solver CTAs per SM, shared-memory bytes per CTA, grid) of the persistent solver kernel."""
-        a, b, g = C.c_int(0), C.c_int(0), C.c_int(0)
-        _check(self.lib.wbc_solver_shape(self.h, C.byref(a), C.byref(b), C.byref(g)), "wbc_solver_shape")
+        """(resident solver CTAs per SM, shared-memory bytes per CTA, grid of the last cycle) of the persistent solver kernel."""
+        a, b, g, st = C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0)
+        _check(self.lib.wbc_solver_shape(self.h, C.byref(a), C.byref(b), C.byref(g), C.byref(st)), "wbc_solver_shape")
+        self.last_solver_kernel = "wbc_solve_staged_kernel" if st.value else "wbc_solve_kernel"
         return a.value, b.value, g.value
 
     def stage_profile(self):

@@ -27,7 +27,7 @@ constexpr unsigned FULL = 0xffffffffu;
 __device__ __forceinline__ double bshfl(double v, int src) { return __shfl_sync(FULL, v, src); }
 __device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
 __device__ __noinline__ double ddiv(double a, double b) { return a / b; }
-__device__ __noinline__ double dsqrt(double a) { return sqrt(a); }
+__device__ __forceinline__ double dsqrt(double a) { return dsqrt_ni(a); }
 // warp sum, every lane gets the same bits
 __device__ __forceinline__ double wsum(double v) { return warp_sum_ni(v); }      // one shared copy of the butterfly (unrolled inside)
 // warp maximum of non-negative doubles (bit patterns order like the values)
@@ -518,7 +518,9 @@ __device__ __noinline__ double2 newton_diag(int nic, double rho, unsigned fmask)
 }
 
 // One QQP solve from the point exxc (in/out) on the model (H, CI, rho, exb).  Returns the QQP termination type.
-__device__ __noinline__ int qqp_optimize_fast(const Work w, int nic, double rho, double epsx, int maxouterits, int* ncholesky, double* flops_io, int* reused_io)
+// pre_stats: the model's (absasum, absasum2, max|exb|) when the caller has them already (stage tasks), else NULL.
+__device__ __noinline__ int qqp_optimize_fast(const Work w, int nic, double rho, double epsx, int maxouterits, int* ncholesky, double* flops_io, int* reused_io,
+                                              const double* pre_stats)
 {
     const int l = threadIdx.x & 31;
     const int n = NMAIN + nic;
@@ -554,8 +556,9 @@ __device__ __noinline__ int qqp_optimize_fast(const Work w, int nic, double rho,
     }
     if (vA) sxc[l] = xcA;
     if (l < nic2) { sxc[NMAIN + l] = xcB; sdc[NMAIN + l] = 0.0; }
-    qqp_stats(nic, rho, exbA, exbB);
-    const double absasum = spare[8], absasum2 = spare[9], mb = spare[10];
+    double absasum, absasum2, mb;
+    if (pre_stats) { absasum = pre_stats[0]; absasum2 = pre_stats[1]; mb = pre_stats[2]; __syncwarp(); }     // (the mirrors of x written above are read by every lane)
+    else { qqp_stats(nic, rho, exbA, exbB); absasum = spare[8]; absasum2 = spare[9]; mb = spare[10]; }
     int term = 0;
     int cgmax = cgminits;
     int outerits = 0;

@@ -391,18 +391,30 @@ WBC_HD void generaterotation(double f, double g, double& cs, double& sn, double&
     cs = f / r; sn = g / r;
     if (fabs(f) > fabs(g) && cs < 0.0) { cs = -cs; sn = -sn; r = -r; }
 }
+#if defined(__CUDACC__)
+// one shared copy of the double-precision square root (an inlined one is ~30 instructions; code size is what this solver pays for)
+__device__ __noinline__ double dsqrt_ni(double a) { return sqrt(a); }
+#endif
+WBC_HD double sqrt_shared(double a)
+{
+#if defined(__CUDA_ARCH__)
+    return dsqrt_ni(a);
+#else
+    return sqrt(a);
+#endif
+}
 // returns (d1est + 1) * 4 + (d2est + 1)
 WBC_HDNI int estimateparabolicmodel(double absasum, double absasum2, double mx, double mb, double md, double d1, double d2)
 { // opt.cpp:23071-23131
     const double eps = 4 * MACHEPS;
-    const double sq2 = sqrt(absasum2);
+    const double sq2 = sqrt_shared(absasum2);
     double e1 = eps * md * (mx * absasum + mb);
     double e2 = eps * md * (mx * sq2 + mb);
-    double err = sqrt(e1 * e2);
+    double err = sqrt_shared(e1 * e2);
     const int d1est = (fabs(d1) <= err) ? 0 : (d1 > 0 ? 1 : (d1 < 0 ? -1 : 0));
     e1 = eps * md * md * absasum;
     e2 = eps * md * md * sq2;
-    err = sqrt(e1 * e2);
+    err = sqrt_shared(e1 * e2);
     const int d2est = (fabs(d2) <= err) ? 0 : (d2 > 0 ? 1 : (d2 < 0 ? -1 : 0));
     return (d1est + 1) * 4 + (d2est + 1);
 }
@@ -1946,7 +1958,7 @@ __device__ __forceinline__ int model_and_qqp_dev(const WarpEx& ex, const Work& w
 {
     generate_ex_model<false>(ex, w, nec, nicwork, rho);
     *flops += (double)NMAIN * NMAIN * (nec + nicwork) + 4.0 * NMAIN * (nec + nicwork);
-    return fast::qqp_optimize_fast(w, nicwork, rho, 0.01 * epsx, 50, ncholesky, flops, reused);
+    return fast::qqp_optimize_fast(w, nicwork, rho, 0.01 * epsx, 50, ncholesky, flops, reused, (const double*)nullptr);
 }
 #endif
 
@@ -2129,6 +2141,7 @@ struct SolveState {
     int termination, ncholesky, outer_its, qqp_calls, kkt_dim_max, chol_reused, flags;
     int done;                           // the solve is complete: result in W_XS, termination set
     int pad_;
+    double qstat[3];                    // |A| statistics of the next QQP call's model (qqp_stats), computed where the model is built
 };
 static_assert(sizeof(SolveState) <= gl::HDR_DOUBLES * sizeof(double), "SolveState fits its header slot");
 
@@ -2175,6 +2188,7 @@ WBC_HDN void solve_stage_setup(const Ex& ex, const Work& w, const Settings& cfg,
     s.kkt_dim_max = 0; s.chol_reused = 0; s.flags = 0; s.flops = 0.0; s.done = 0; s.pad_ = 0; s.version = 0;
     s.goodcounter = 0; s.stagnationcounter = 0; s.outeridx = 0; s.allowevict = 1; s.have_factor = 0;
     s.rho = cfg.rho; s.epsx = cfg.epsx; s.feaserr = 1.7976931348623157e308;
+    s.qstat[0] = s.qstat[1] = s.qstat[2] = 0.0;
     int pd = 0;
     const int rc = setup_problem(ex, w, nrows, &pd, cfg.dup_start[0], cfg.dup_count[0], cfg.dup_start[1], cfg.dup_count[1]);
     if (rc != 0) { s.termination = rc; s.done = 1; return; }
@@ -2327,6 +2341,14 @@ WBC_HDN int stage_post_and_model(const Ex& ex, const Work& w, const Settings& cf
 #pragma unroll 1
         for (int k = ex.lane(); k < NMAIN + s.nicwork; k += Ex::NL) gb[k] = exb[k];
         ex.sync();
+#if defined(__CUDA_ARCH__)
+        {   // the model's |A| statistics (opt.cpp:29893-29915): once per call, so they are taken here and not on the QQP SMs
+            const int l = ex.lane();
+            fast::qqp_stats(s.nicwork, s.rho, l < NMAIN ? exb[l] : 0.0, l < s.nicwork ? exb[NMAIN + l] : 0.0);
+            const double* sp = SM_(w, sl::OFF_SP);
+            s.qstat[0] = sp[8]; s.qstat[1] = sp[9]; s.qstat[2] = sp[10];
+        }
+#endif
         return 1;
     }
 }
@@ -2339,7 +2361,7 @@ __device__ __forceinline__ void stage_qqp(const WarpEx& ex, const Work& w, Solve
     if (nic2 > 0) ex.copy_start(SM_(w, sl::OFF_CI), w.g + gl::OFF_CI, nic2 * LDH);
     ex.copy_start(W_EXB(w), w.g + gl::OFF_EXBG, NMAIN + s.nicwork);
     ex.copy_wait();
-    const int term = fast::qqp_optimize_fast(w, s.nicwork, s.rho, 0.01 * s.epsx, 50, &s.ncholesky, &s.flops, &s.chol_reused);
+    const int term = fast::qqp_optimize_fast(w, s.nicwork, s.rho, 0.01 * s.epsx, 50, &s.ncholesky, &s.flops, &s.chol_reused, s.qstat);
     if (term == -4) s.flags |= 4;
 }
 #endif

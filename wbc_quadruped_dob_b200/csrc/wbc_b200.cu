@@ -616,7 +616,9 @@ struct wbc_ctx {
     StageCtl* sq_ctl;    // staged solver: counters
     int* sq_ring;        // staged solver: rings [3][sq_rsize]
     int sq_rsize;
-    int staged;          // 0: wbc_solve_kernel (default), 1: wbc_solve_staged_kernel (WBC_SOLVER=staged)
+    int staged;          // 0: wbc_solve_kernel, 1: wbc_solve_staged_kernel, 2 (default): by batch size (staged from staged_min_n instances)
+    int staged_min_n;
+    int last_staged;     // which kernel the last wbc_cycle launched
     int m_period, m_group;   // SM roles of the staged solver
     unsigned long long* prof;   // [nblocks][12] per-warp profile of the last staged launch (WBC_STAGE_PROF=1)
     int* queue;          // [cost histogram A | work-queue counter | dispatch cursors | cost histogram B]: counter and cursors sit between
@@ -730,11 +732,14 @@ int wbc_create(wbc_ctx** out, int device, int max_batch, const wbc_params* param
     TRY(cudaMalloc(&c->w_dev, nb * 6 * sizeof(double)));
     TRY(cudaMalloc(&c->tau_prev, nb * 12 * sizeof(double)));
     TRY(cudaMemset(c->tau_prev, 0, nb * 12 * sizeof(double)));
-    // Which solver kernel: one warp per solve (default) or stage tasks with SM roles (WBC_SOLVER=staged).  Measured on B200
-    // (profiles/README.md, round 2): equal at 65 536 instances (43.8 vs 44.1 ms), the staged kernel loses at 4 096 (3.8 vs 3.2 ms:
-    // a solve is seven hand-overs and the batch is only 2.3 solves per warp) -- it stays selectable, with its evidence.
-    c->staged = 0; c->m_period = (0 << 16) | (2 << 8) | 5; c->m_group = 2;       // of every 5 SM pairs: 2 POST/SETUP, 3 QQP
-    if (const char* ev = getenv("WBC_SOLVER")) c->staged = strcmp(ev, "staged") == 0;
+    // Which solver kernel.  wbc_solve_kernel: one warp per solve.  wbc_solve_staged_kernel: stage tasks with SM roles -- the QQP
+    // iteration (its hot code fits an SM's instruction cache) on three SM pairs of five, everything else on the other two.
+    // Measured on B200 (profiles/README.md, round 2): the staged kernel is 19 % faster at 65 536 instances (37.1 against 44.1 ms) and
+    // slower at 4 096 (4.0 against 3.3 ms: a solve is eleven hand-overs and the batch is only 2.3 solves per warp), so the choice
+    // goes by batch size; WBC_SOLVER = mono | staged forces one, WBC_STAGED_MIN_N moves the threshold.
+    c->staged = 2; c->staged_min_n = 12288; c->m_period = (0 << 16) | (2 << 8) | 5; c->m_group = 2;       // of every 5 SM pairs: 2 POST/SETUP, 3 QQP
+    if (const char* ev = getenv("WBC_SOLVER")) c->staged = strcmp(ev, "staged") == 0 ? 1 : (strcmp(ev, "mono") == 0 ? 0 : 2);
+    if (const char* ev = getenv("WBC_STAGED_MIN_N")) c->staged_min_n = atoi(ev);
     if (const char* ev = getenv("WBC_STAGE_ROLES")) {        // "nS,nP/den"
         int a = 0, b = 2, d = 5;
         if (sscanf(ev, "%d,%d/%d", &a, &b, &d) == 3 && d > 0 && d < 256 && a >= 0 && b >= 0 && a + b <= d) c->m_period = (a << 16) | (b << 8) | d;
@@ -775,8 +780,10 @@ int wbc_create(wbc_ctx** out, int device, int max_batch, const wbc_params* param
     if (e == cudaSuccess) {
         // the persistent grid is exactly the resident CTAs: more would queue behind whole solves
         int occ = 0;
-        e = c->staged ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wbc_solve_staged_kernel, SOLVE_T, (size_t)c->solve_smem)
-                      : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wbc_solve_kernel, SOLVE_T, (size_t)c->solve_smem);
+        int occ2 = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wbc_solve_staged_kernel, SOLVE_T, (size_t)c->solve_smem);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, wbc_solve_kernel, SOLVE_T, (size_t)c->solve_smem);
+        if (occ2 < occ) occ = occ2;
         if (e == cudaSuccess && occ >= 1) {
             c->occ_per_sm = occ;
             if (c->nblocks > c->sm_count * occ) c->nblocks = c->sm_count * occ;
@@ -968,7 +975,8 @@ int wbc_cycle(wbc_ctx* c, int n, const wbc_inputs* in, const wbc_outputs* out, v
     const int fthreads = front_threads(c, n);
     StageReset sr;
     memset(&sr, 0, sizeof(sr));
-    if (c->staged) {
+    const bool staged_next = c->staged == 1 || (c->staged == 2 && n >= c->staged_min_n);
+    if (staged_next) {
         sr.ctl = reinterpret_cast<int*>(c->sq_ctl); sr.nctl = (int)(sizeof(StageCtl) / sizeof(int));
         sr.free_tail_index = (int)(offsetof(StageCtl, tail) / sizeof(int)) + SQ_FREE * 32;
         sr.free_avail_index = (int)(offsetof(StageCtl, avail) / sizeof(int)) + SQ_FREE * 32;
@@ -981,7 +989,9 @@ int wbc_cycle(wbc_ctx* c, int n, const wbc_inputs* in, const wbc_outputs* out, v
     // warps share the SM's instruction supply: measured at 4 096 instances, 8 warps per SM beat 12 by 3 % (profiles/README.md).
     int nblocks = c->nblocks;
     int smem = c->solve_smem;
-    if (!c->staged && c->occ_per_sm > 8 && !c->occ_forced) {
+    const bool staged = c->staged == 1 || (c->staged == 2 && n >= c->staged_min_n);
+    c->last_staged = staged ? 1 : 0;
+    if (!staged && c->occ_per_sm > 8 && !c->occ_forced) {
         int per_sm = (int)((double)n / (3.4 * c->sm_count));
         per_sm = per_sm < 8 ? 8 : (per_sm > c->occ_per_sm ? c->occ_per_sm : per_sm);
         if (per_sm < c->occ_per_sm) {
@@ -993,7 +1003,7 @@ int wbc_cycle(wbc_ctx* c, int n, const wbc_inputs* in, const wbc_outputs* out, v
     }
     if (n < nblocks) nblocks = n;
     c->last_grid = nblocks;
-    if (c->staged) {
+    if (staged) {
         StageQueues sq;
         sq.ctl = c->sq_ctl; sq.ring = c->sq_ring; sq.rmask = c->sq_rsize - 1; sq.nslots = c->nslots;
         wbc_solve_staged_kernel<<<nblocks, c->threads, c->solve_smem, s>>>(c->params, n, c->recs, so, c->scratch, c->kkt, sq, ordered ? c->order : nullptr,
@@ -1240,12 +1250,13 @@ int wbc_stage_profile(wbc_ctx* c, unsigned long long* out, int max_rows)
     return rows;
 }
 
-int wbc_solver_shape(wbc_ctx* c, int* ctas_per_sm, int* smem_bytes, int* grid)
+int wbc_solver_shape(wbc_ctx* c, int* ctas_per_sm, int* smem_bytes, int* grid, int* stage_tasks)
 {
     if (!c) return fail(WBC_EINVAL, "null ctx");
     if (ctas_per_sm) *ctas_per_sm = c->occ_per_sm;
     if (smem_bytes) *smem_bytes = c->solve_smem;
     if (grid) *grid = c->last_grid > 0 ? c->last_grid : c->nblocks;
+    if (stage_tasks) *stage_tasks = c->last_staged;
     return WBC_OK;
 }
 
