@@ -76,6 +76,8 @@ typedef struct wbc_params {
     double obs_dt;            /* 0.0025            main.cpp:715       */
     double gravity[3];        /* (0,0,-9.8)        main.cpp:855       */
     double qp_epsx, qp_rho;   /* 1e-2, 1e4         lopt.cpp:101, 138  */
+    double obs_gain2;         /* 1                 second entry of the coefficient vector {10, 1} (main.cpp:707-708,
+                                                   estimator_sem.cpp:47-48); only read when obs_order == 2 */
     int qp_outerits;          /* 5                 lopt.cpp:101, 138  */
     int observer_enabled;     /* 1: call estimate() at main.cpp:1029/1220/1569/1767 (reference ships 0) */
     int fix_swing_rhs;        /* 0: keep the reference's zero swing-equality rhs (main.cpp:1238-1241) */
@@ -83,6 +85,14 @@ typedef struct wbc_params {
     int hold_tau_on_failure;  /* 0 (default): a failed instance gets tau from x = 0 (tau = 0 when its inputs are invalid);
                                  1: it gets the last good tau this ctx produced for that instance index -- the reference
                                  keeps publishing its `tau` member when the QP throws (lopt.cpp:114-116, main.cpp:242, 1126) */
+    int obs_order;            /* 1 (default): the first-order observer DOGCTRL::estimate() runs (main.cpp:692-725).
+                                 2: second-order recursion through the `ygamma` state both the controller and the
+                                 dead ESTIMATOR_SEM carry but never advance (main.cpp:243, 724; estimator_sem.cpp:17-20):
+                                     gamma1 = k1 (rho - yw - yd),  ygamma' = gamma1 - w,  w = k2 ygamma,
+                                 k1 = obs_gain (or the per-instance gain), k2 = obs_gain2, i.e. w = k1 k2 / (s^2 + k2 s + k1 k2) w_true. */
+    int obs_form;             /* 0 (default): backward-Euler gain of main.cpp:716-718, w = (I + k T)^-1 k (rho - yw_prev - yd);
+                                 1: the explicit gain of ESTIMATOR_SEM::estimate, w = k (rho - yw_prev - yd) (estimator_sem.cpp:55-57,
+                                 which also uses T = 0.001: set obs_dt). */
 } wbc_params;
 
 /* One control cycle's inputs for n instances (what update() receives plus the members it reads). */
@@ -118,6 +128,9 @@ typedef struct wbc_outputs {
     int* qp_info;       /* [8]  ncholesky, outer its, QQP calls, working set, max KKT dim, flags, factorisations reused (of ncholesky), 0; may be NULL */
     double* qp_flops;   /* [1]  instrumented algorithmic flop count of the solve, may be NULL */
     long ld;
+    double* w3;         /* [12] the estimate mapped onto the feet, w3 = pinv(J)' w with J = JacCOM_lin[:, 0:6], stacked foot order
+                               (ESTIMATOR_SEM::getw3, estimator_sem.cpp:64-70): the least-norm foot forces whose CoM wrench is w.
+                               May be NULL (then nothing is computed). */
 } wbc_outputs;
 
 /* Intermediates of update() for stage-by-stage validation (all may be NULL individually). */
@@ -154,6 +167,9 @@ int wbc_set_params(wbc_ctx* ctx, const wbc_params* params);
 /* Observer state yd, yw (main.cpp:243, 721-724): SoA [6][ld], host pointers.  The ctx zero-initialises it. */
 int wbc_set_observer_state(wbc_ctx* ctx, int n, const double* yd, const double* yw, long ld);
 int wbc_get_observer_state(wbc_ctx* ctx, int n, double* yd, double* yw, long ld);
+/* The second-order observer's extra integrator state ygamma (main.cpp:243; estimator_sem.cpp:20), same layout; zero-initialised. */
+int wbc_set_observer_state2(wbc_ctx* ctx, int n, const double* ygamma, long ld);
+int wbc_get_observer_state2(wbc_ctx* ctx, int n, double* ygamma, long ld);
 
 /* One control cycle for n instances: update() -> Fgrf -> estimate() -> QP assembly -> solve -> tau.
  * `cuda_stream` is a cudaStream_t (NULL = the ctx's own stream). */

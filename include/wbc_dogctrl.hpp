@@ -125,7 +125,7 @@ public:
     explicit Batch(int n, int device = 0, const wbc_params* params = nullptr)
         : n_(n), ctx_(n > 0 ? n : 1, device, params), base_pos(3 * n), base_rot(9 * n), base_rpy(3 * n), base_vel(6 * n), q(12 * n), dq(12 * n),
           com_des_pos(6 * n), com_des_vel(6 * n), com_des_acc(6 * n), sw_des_pos(6 * n), sw_des_vel(6 * n), sw_des_acc(6 * n),
-          foot_force(12 * n), terrain(), mode(n, WBC_MODE_STANCE), tau(12 * n), w(6 * n), x(30 * n), qp_obj(n), status(n)
+          foot_force(12 * n), terrain(), mode(n, WBC_MODE_STANCE), tau(12 * n), w(6 * n), x(30 * n), qp_obj(n), status(n), w3(12 * n)
     {
     }
     int size() const { return n_; }
@@ -135,6 +135,10 @@ public:
     void enable_terrain() { terrain.assign((size_t)40 * n_, 0.0); }
     void set_observer_state(const double* yd, const double* yw) { check(wbc_set_observer_state(ctx_.get(), n_, yd, yw, n_), "wbc_set_observer_state"); }
     void get_observer_state(double* yd, double* yw) { check(wbc_get_observer_state(ctx_.get(), n_, yd, yw, n_), "wbc_get_observer_state"); }
+    // ygamma, the second-order observer's extra integrator (wbc_params::obs_order == 2; main.cpp:243, estimator_sem.cpp:20)
+    void set_observer_state2(const double* yg) { check(wbc_set_observer_state2(ctx_.get(), n_, yg, n_), "wbc_set_observer_state2"); }
+    void get_observer_state2(double* yg) { check(wbc_get_observer_state2(ctx_.get(), n_, yg, n_), "wbc_get_observer_state2"); }
+    bool want_w3 = false;   // also compute ESTIMATOR_SEM::getw3 (estimator_sem.cpp:64-70) into w3
     // Planner hand-over (once per plan): the node tables of the four towr splines of every instance, see wbc_trajectory.
     // durations [4*nseg][n], nodes [4*(nseg+1)*6][n].  Replaces keeping `SplineHolder solution` on the host (main.cpp:900-960).
     void set_trajectory(int nseg, const double* durations, const double* nodes)
@@ -158,7 +162,7 @@ public:
         in.mode = mode.data(); in.ld = n_; in.obs_gain = nullptr;
         wbc_outputs out;
         out.tau = tau.data(); out.w = w.data(); out.x = x.data(); out.qp_obj = qp_obj.data(); out.status = status.data();
-        out.qp_info = nullptr; out.qp_flops = nullptr; out.ld = n_;
+        out.qp_info = nullptr; out.qp_flops = nullptr; out.ld = n_; out.w3 = want_w3 ? w3.data() : nullptr;
         check(wbc_cycle(ctx_.get(), n_, &in, &out, nullptr, WBC_HOST_PTRS | (sampled_trajectory ? WBC_SAMPLED_TRAJ : 0u)), "wbc_cycle");
     }
 
@@ -172,6 +176,7 @@ public:
     std::vector<int> mode;
     std::vector<double> tau, w, x, qp_obj;
     std::vector<int> status;
+    std::vector<double> w3;   // [12][n] when want_w3
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -240,7 +245,9 @@ public:
     }
 
     const double* tau() const { return b_.tau.data(); }     // [12]  main.cpp:1126, 1396
-    const double* w() const { return b_.w.data(); }         // [6]   main.cpp:718
+    const double* w() const { return b_.w.data(); }         // [6]   main.cpp:718; ESTIMATOR_SEM::getwext (estimator_sem.cpp:98-104)
+    // ESTIMATOR_SEM::getw3 (estimator_sem.cpp:64-70): the estimate as foot forces, stacked BR, BL, FL, FR; set batch().want_w3 first
+    const double* getw3() const { return b_.w3.data(); }    // [12]
     const double* x() const { return b_.x.data(); }         // [30]  QP solution
     double qp_objective() const { return b_.qp_obj[0]; }
     int status() const { return b_.status[0]; }

@@ -23,7 +23,8 @@ MODE_STANCE, MODE_SWING_BR_FL, MODE_SWING_BL_FR = 0, 1, 2
 class Params(C.Structure):
     _fields_ = [(n, C.c_double) for n in
                 ("kcom", "dcom", "q1_weight", "slack_weight", "mu", "tau_max", "joint_dt", "kp_sw", "kd_sw",
-                 "g_acc", "obs_gain", "obs_dt")] + [("observer_enabled", C.c_int), ("fix_swing_rhs", C.c_int)]
+                 "g_acc", "obs_gain", "obs_dt")] + [("observer_enabled", C.c_int), ("fix_swing_rhs", C.c_int),
+                                                    ("obs_gain2", C.c_double), ("obs_order", C.c_int), ("obs_form", C.c_int)]
 
 
 class In(C.Structure):
@@ -34,12 +35,13 @@ class In(C.Structure):
                 ("mode", C.c_int),
                 ("sw_des_pos", C.c_double * 6), ("sw_des_vel", C.c_double * 6), ("sw_des_acc", C.c_double * 6),
                 ("foot_force", C.c_double * 12), ("terrain", C.c_double * 40), ("has_terrain", C.c_int),
-                ("yd_prev", C.c_double * 6), ("yw_prev", C.c_double * 6)]
+                ("yd_prev", C.c_double * 6), ("yw_prev", C.c_double * 6), ("yg_prev", C.c_double * 6)]
 
 
 class Out(C.Structure):
     _fields_ = [("tau", C.c_double * 12), ("w", C.c_double * 6), ("yd", C.c_double * 6), ("yw", C.c_double * 6),
-                ("x", C.c_double * 30), ("qp_obj", C.c_double), ("status", C.c_int), ("ncholesky", C.c_int)]
+                ("x", C.c_double * 30), ("qp_obj", C.c_double), ("status", C.c_int), ("ncholesky", C.c_int),
+                ("yg", C.c_double * 6)]
 
 
 class Dyn(C.Structure):
@@ -156,6 +158,7 @@ def to_structs(sc, gravity=(0.0, 0.0, -9.8)):
         src = sc[_SOA_NAME.get(name, name)]          # [k][n]
         view[name][:] = np.ascontiguousarray(src.T)
     view["mode"][:] = sc["mode"]
+    view["yg_prev"][:] = np.ascontiguousarray(sc["obs_yg"].T) if sc.get("obs_yg") is not None else 0.0
     view["gravity"][:] = np.asarray(gravity, dtype=np.float64)[None, :]
     if sc.get("terrain") is not None:
         view["terrain"][:] = np.ascontiguousarray(sc["terrain"].T)
@@ -176,7 +179,7 @@ def run_cycle_batch(sc, params=None, nthreads=1, solver="ref", gravity=(0.0, 0.0
     fn = C.cast(ref_lib().ref_qp_solve, C.c_void_p)
     secs = oracle_lib().wbc_oracle_batch(C.byref(params), arr, n, nthreads, fn, out)
     v = np.frombuffer(out, dtype=np.dtype(Out))
-    res = {k: np.array(v[k]) for k in ("tau", "w", "yd", "yw", "x", "qp_obj", "status", "ncholesky")}
+    res = {k: np.array(v[k]) for k in ("tau", "w", "yd", "yw", "yg", "x", "qp_obj", "status", "ncholesky")}
     return res, secs
 
 
@@ -310,3 +313,10 @@ def sample_trajectory(traj, t):
             out[pre + "vel"][r0:r0 + 3, i] = v
             out[pre + "acc"][r0:r0 + 3, i] = a
     return out
+
+
+def foot_wrench_map(Jcom_lin, w):
+    """ESTIMATOR_SEM::getw3 (estimator_sem.cpp:64-70): w3 = pinv(J)' w with J = JacCOM_lin[:, 0:6] (12 x 6).  The reference takes the
+    pseudo-inverse from Eigen's complete orthogonal decomposition; numpy's SVD-based pinv is the same Moore-Penrose matrix."""
+    J = np.asarray(Jcom_lin, dtype=np.float64).reshape(12, 18)[:, :6]
+    return np.linalg.pinv(J).T @ np.asarray(w, dtype=np.float64)

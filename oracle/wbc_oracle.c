@@ -96,6 +96,7 @@ void wbc_oracle_default_params(wbc_oracle_params* p)
     p->kcom = 2500.0; p->dcom = 50.0; p->q1_weight = 50.0; p->slack_weight = 100000000.0;
     p->mu = 0.6; p->tau_max = 60.0; p->joint_dt = 0.025; p->kp_sw = 300.0; p->kd_sw = 20.0;
     p->g_acc = 9.81; p->obs_gain = 10.0; p->obs_dt = 0.0025;
+    p->obs_gain2 = 1.0; p->obs_order = 1; p->obs_form = 0;
     p->observer_enabled = 1; p->fix_swing_rhs = 0;
 }
 
@@ -361,6 +362,9 @@ void wbc_oracle_fgrf(const wbc_oracle_in* in, const wbc_oracle_dyn* d, double* F
 /* ------------------------------------------------------------------ estimate(), main.cpp:692-725 */
 static void wbc_oracle_estimate_full(const wbc_oracle_params* p, const double* Mc, const double* qd, const double* fc,
                                      const double* yd_prev, const double* yw_prev, double* w, double* yd, double* yw);
+static void wbc_oracle_estimate_sem(const wbc_oracle_params* p, const double* Mc, const double* qd, const double* fc,
+                                    const double* yd_prev, const double* yw_prev, const double* yg_prev, double* w, double* yd,
+                                    double* yw, double* yg);
 
 void wbc_oracle_estimate(const wbc_oracle_params* p, const wbc_oracle_in* in, const wbc_oracle_dyn* d,
                          const double* Fgrf, double* w, double* yd, double* yw)
@@ -375,6 +379,55 @@ void wbc_oracle_estimate(const wbc_oracle_params* p, const wbc_oracle_in* in, co
         fc[c] = s;
     }
     wbc_oracle_estimate_full(p, Mc, qd, fc, in->yd_prev, in->yw_prev, w, yd, yw);
+}
+
+/* Same inputs, the forms of SURVEY.md 8f-3 (obs_order == 2 or obs_form == 1). */
+void wbc_oracle_estimate_ext(const wbc_oracle_params* p, const wbc_oracle_in* in, const wbc_oracle_dyn* d,
+                             const double* Fgrf, double* w, double* yd, double* yw, double* yg)
+{
+    double Mc[36], qd[6], fc[6];
+    for (int a = 0; a < 6; a++)
+        for (int b = 0; b < 6; b++) Mc[a * 6 + b] = d->Mcom[a * 18 + b];
+    for (int c = 0; c < 3; c++) { qd[c] = d->com_vel[c]; qd[3 + c] = in->base_vel[3 + c]; }
+    for (int c = 0; c < 6; c++) {
+        double s = 0.0;
+        for (int r = 0; r < 12; r++) s += d->Jcom_lin[r * 18 + c] * Fgrf[r];
+        fc[c] = s;
+    }
+    wbc_oracle_estimate_sem(p, Mc, qd, fc, in->yd_prev, in->yw_prev, in->yg_prev, w, yd, yw, yg);
+}
+
+/* ESTIMATOR_SEM::estimate (estimator_sem.cpp:24-61) and its second-order continuation.
+ *   order 1, form 1: the literal lines 53-59: yd = yd_prev + d T; w = k0 (rho - yw_prev - yd); yw = yw_prev + w T
+ *                    (its `Ctq` term comes from QUADRUPED::getCtq, declared at main.cpp:155 and defined nowhere: taken as zero,
+ *                    which is exact for the centroidal momentum rho = Mcom CoM_vel; its T = 0.001 is p->obs_dt);
+ *   order 2:         the r = 2 member of the family the coefficient vector {10, 1} and the ygamma state belong to,
+ *                        gamma1 = k1 (rho - int(w + d)),  w = k2 int(gamma1 - w),   w / w_true = k1 k2 / (s^2 + k2 s + k1 k2),
+ *                    form 0 discretised as main.cpp:716-719 does the first order (backward Euler, the new w on both sides),
+ *                    form 1 as estimator_sem.cpp:55-59 does (forward Euler). */
+static void wbc_oracle_estimate_sem(const wbc_oracle_params* p, const double* Mc, const double* qd, const double* fc,
+                                    const double* yd_prev, const double* yw_prev, const double* yg_prev, double* w, double* yd,
+                                    double* yw, double* yg)
+{
+    const double mass = DB_TOTAL_MASS, T = p->obs_dt, k1 = p->obs_gain, k2 = p->obs_gain2;
+    for (int a = 0; a < 6; a++) {
+        double rho = 0.0;
+        for (int b = 0; b < 6; b++) rho += Mc[a * 6 + b] * qd[b];
+        const double dd = -mass * ((a == 2) ? p->g_acc : 0.0) + fc[a];
+        yd[a] = yd_prev[a] + dd * T;
+        const double e = rho - yw_prev[a] - yd[a];
+        if (p->obs_order != 2) {
+            w[a] = (p->obs_form == 1) ? k1 * e : (1.0 / (1.0 + k1 * T)) * k1 * e;
+            yg[a] = yg_prev[a];
+        } else if (p->obs_form == 1) {
+            yg[a] = yg_prev[a] + T * (k1 * e - k2 * yg_prev[a]);
+            w[a] = k2 * yg[a];
+        } else {
+            w[a] = k2 * (yg_prev[a] + T * k1 * e) / (1.0 + k2 * T + k1 * k2 * T * T);
+            yg[a] = yg_prev[a] + T * (k1 * (e - w[a] * T) - w[a]);
+        }
+        yw[a] = yw_prev[a] + w[a] * T;
+    }
 }
 
 /* The recurrence itself: Mc 6x6 row-major, qd = CoM_vel (6), fc = J' Fgrf (6). */
@@ -606,9 +659,13 @@ int wbc_oracle_cycle(const wbc_oracle_params* p, const wbc_oracle_in* in, wbc_qp
     wbc_oracle_fgrf(in, d, qp->Fgrf);
     if (p->observer_enabled) {
         /* estimate() placed where the reference's commented-out call sits (main.cpp:1029, 1220, 1569, 1767) */
-        wbc_oracle_estimate(p, in, d, qp->Fgrf, out->w, out->yd, out->yw);
+        if (p->obs_order == 2 || p->obs_form == 1) wbc_oracle_estimate_ext(p, in, d, qp->Fgrf, out->w, out->yd, out->yw, out->yg);
+        else {
+            wbc_oracle_estimate(p, in, d, qp->Fgrf, out->w, out->yd, out->yw);
+            for (int c = 0; c < 6; c++) out->yg[c] = in->yg_prev[c];
+        }
     } else {
-        for (int c = 0; c < 6; c++) { out->w[c] = 0.0; out->yd[c] = in->yd_prev[c]; out->yw[c] = in->yw_prev[c]; }
+        for (int c = 0; c < 6; c++) { out->w[c] = 0.0; out->yd[c] = in->yd_prev[c]; out->yw[c] = in->yw_prev[c]; out->yg[c] = in->yg_prev[c]; }
     }
     wbc_oracle_assemble(p, in, d, out->w, qp);
     int nchol = 0, term = 0;

@@ -39,6 +39,11 @@ typedef struct {
     double obs_dt;            /* 0.0025            main.cpp:715       */
     int observer_enabled;     /* reference ships 0 (calls commented out, main.cpp:1029); north_star: 1 */
     int fix_swing_rhs;        /* 0 = keep the reference quirk (swing equality rhs = 0, main.cpp:1238-1241) */
+    /* SURVEY.md 8f-3 (the dead ESTIMATOR_SEM, estimator_sem.cpp:24-61; second gain main.cpp:707-708) -- PARITY UNPINNED: the
+     * reference never runs these forms, there is nothing to compare against except this restatement and the closed-form response */
+    double obs_gain2;         /* 1: second entry of the coefficient vector {10, 1}                   */
+    int obs_order;            /* 1 = estimate() as main.cpp runs it; 2 = second-order recursion via ygamma */
+    int obs_form;             /* 0 = (I + kT)^-1 k (main.cpp:716-718); 1 = k (estimator_sem.cpp:55-57)  */
 } wbc_oracle_params;
 
 void wbc_oracle_default_params(wbc_oracle_params* p);
@@ -59,6 +64,7 @@ typedef struct {
     double terrain[40];     /* per stacked foot: n(3) t1(3) t2(3) mu(1); used when has_terrain != 0   */
     int has_terrain;
     double yd_prev[6], yw_prev[6];  /* observer state carried across cycles, main.cpp:721-724       */
+    double yg_prev[6];              /* ygamma_prev (main.cpp:243, 724), read by the second-order form only */
 } wbc_oracle_in;
 
 typedef struct {
@@ -69,6 +75,7 @@ typedef struct {
     double qp_obj;          /* 0.5 x'Qx + c'x at x                                                */
     int status;             /* 0 ok, <0 QP solver threw                                           */
     int ncholesky;
+    double yg[6];           /* ygamma (second-order form), else a copy of yg_prev                 */
 } wbc_oracle_out;
 
 /* Intermediates of update(), exposed so tests can compare stage by stage. */

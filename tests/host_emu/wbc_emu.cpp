@@ -28,6 +28,8 @@ struct EmuIO {
     int* status;              // [ld]
     int* info;                // [8][ld]
     double* rec;              // [ld][QPREC_DOUBLES] (optional)
+    double* yg;               // [6][ld] in/out (second-order observer; may be NULL when obs_order == 1)
+    double* w3;               // [12][ld] (optional)
 };
 
 int emu_cycle(const Params* P, const EmuIO* io, int n)
@@ -39,7 +41,7 @@ int emu_cycle(const Params* P, const EmuIO* io, int n)
     in.com_des_acc = io->com_des_acc; in.sw_des_pos = io->sw_des_pos; in.sw_des_vel = io->sw_des_vel;
     in.sw_des_acc = io->sw_des_acc; in.foot_force = io->foot_force; in.terrain = io->terrain; in.mode = io->mode; in.obs_gain = nullptr; in.ld = io->ld;
     FrontState st;
-    st.yd = io->yd; st.yw = io->yw; st.ld = io->ld;
+    st.yd = io->yd; st.yw = io->yw; st.ld = io->ld; st.yg = io->yg; st.w3 = io->w3; st.w3_ld = io->ld;
     std::vector<double> rec(QPREC_DOUBLES);
     HostEx ex;
     Settings cfg;

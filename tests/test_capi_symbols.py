@@ -27,11 +27,12 @@ def test_library_exports_every_declared_symbol():
 
 def test_params_layout_and_defaults():
     p = api.default_params()
-    assert C.sizeof(api.Params) == 160
+    assert C.sizeof(api.Params) == 176
     assert (p.kcom, p.dcom, p.q1_weight, p.slack_weight, p.mu, p.tau_max) == (2500.0, 50.0, 50.0, 1e8, 0.6, 60.0)
     assert (p.joint_dt, p.kp_sw, p.kd_sw, p.g_acc, p.obs_gain, p.obs_dt) == (0.025, 300.0, 20.0, 9.81, 10.0, 0.0025)
     assert tuple(p.gravity) == (0.0, 0.0, -9.8)
     assert (p.qp_epsx, p.qp_rho, p.qp_outerits) == (1e-2, 1e4, 5)
+    assert (p.obs_gain2, p.obs_order, p.obs_form) == (1.0, 1, 0)
     assert api.load().wbc_version().startswith(b"wbc_b200")
 
 

@@ -44,20 +44,20 @@ def _build_emu(src, so):
 class EmuParams(C.Structure):
     _fields_ = [(n, C.c_double) for n in
                 "kcom dcom q1_weight slack_weight mu tau_max joint_dt kp_sw kd_sw g_acc obs_gain obs_dt".split()] + \
-               [("gravity", C.c_double * 3), ("qp_epsx", C.c_double), ("qp_rho", C.c_double), ("qp_outerits", C.c_int),
-                ("observer_enabled", C.c_int), ("fix_swing_rhs", C.c_int), ("qp_literal_kkt", C.c_int),
-                ("hold_tau_on_failure", C.c_int)]
+               [("gravity", C.c_double * 3), ("qp_epsx", C.c_double), ("qp_rho", C.c_double), ("obs_gain2", C.c_double),
+                ("qp_outerits", C.c_int), ("observer_enabled", C.c_int), ("fix_swing_rhs", C.c_int), ("qp_literal_kkt", C.c_int),
+                ("hold_tau_on_failure", C.c_int), ("obs_order", C.c_int), ("obs_form", C.c_int)]
 
 
 class _EmuIO(C.Structure):
     _fields_ = [(n, _dp) for n in IN_NAMES + ["terrain"]] + \
                [("mode", _ip), ("ld", C.c_long), ("yd", _dp), ("yw", _dp), ("tau", _dp), ("w", _dp), ("x", _dp),
-                ("qp_obj", _dp), ("status", _ip), ("info", _ip), ("rec", _dp)]
+                ("qp_obj", _dp), ("status", _ip), ("info", _ip), ("rec", _dp), ("yg", _dp), ("w3", _dp)]
 
 
 def emu_default_params():
     return EmuParams(2500, 50, 50, 1e8, 0.6, 60, 0.025, 300, 20, 9.81, 10, 0.0025, (C.c_double * 3)(0, 0, -9.8),
-                     1e-2, 1e4, 5, 1, 0, 0, 0)
+                     1e-2, 1e4, 1.0, 5, 1, 0, 0, 0, 1, 0)
 
 
 class Emu:
@@ -94,8 +94,10 @@ class Emu:
         out = dict(yd=np.array(sc["obs_yd"], dtype=np.float64, order="C"), yw=np.array(sc["obs_yw"], dtype=np.float64, order="C"),
                    tau=np.zeros((12, n)), w=np.zeros((6, n)), x=np.zeros((30, n)), qp_obj=np.zeros(n),
                    status=np.zeros(n, dtype=np.int32), qp_info=np.zeros((8, n), dtype=np.int32),
-                   rec=np.zeros((n, self.lib.emu_qprec_doubles())))
+                   rec=np.zeros((n, self.lib.emu_qprec_doubles())),
+                   yg=np.array(sc.get("obs_yg", np.zeros((6, n))), dtype=np.float64, order="C"), w3=np.zeros((12, n)))
         io.yd, io.yw = out["yd"].ctypes.data_as(_dp), out["yw"].ctypes.data_as(_dp)
+        io.yg, io.w3 = out["yg"].ctypes.data_as(_dp), out["w3"].ctypes.data_as(_dp)
         io.tau, io.w, io.x = out["tau"].ctypes.data_as(_dp), out["w"].ctypes.data_as(_dp), out["x"].ctypes.data_as(_dp)
         io.qp_obj, io.status, io.info = out["qp_obj"].ctypes.data_as(_dp), out["status"].ctypes.data_as(_ip), out["qp_info"].ctypes.data_as(_ip)
         io.rec = out["rec"].ctypes.data_as(_dp)

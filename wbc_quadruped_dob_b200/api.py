@@ -38,9 +38,10 @@ class Params(C.Structure):
     _fields_ = [(n, C.c_double) for n in
                 ("kcom", "dcom", "q1_weight", "slack_weight", "mu", "tau_max", "joint_dt", "kp_sw", "kd_sw", "g_acc",
                  "obs_gain", "obs_dt")] + [("gravity", C.c_double * 3), ("qp_epsx", C.c_double), ("qp_rho", C.c_double),
+                                           ("obs_gain2", C.c_double),
                                            ("qp_outerits", C.c_int), ("observer_enabled", C.c_int),
                                            ("fix_swing_rhs", C.c_int), ("qp_literal_kkt", C.c_int),
-                                           ("hold_tau_on_failure", C.c_int)]
+                                           ("hold_tau_on_failure", C.c_int), ("obs_order", C.c_int), ("obs_form", C.c_int)]
 
 
 class _Inputs(C.Structure):
@@ -49,7 +50,7 @@ class _Inputs(C.Structure):
 
 class _Outputs(C.Structure):
     _fields_ = [("tau", C.c_void_p), ("w", C.c_void_p), ("x", C.c_void_p), ("qp_obj", C.c_void_p), ("status", C.c_void_p),
-                ("qp_info", C.c_void_p), ("qp_flops", C.c_void_p), ("ld", C.c_long)]
+                ("qp_info", C.c_void_p), ("qp_flops", C.c_void_p), ("ld", C.c_long), ("w3", C.c_void_p)]
 
 
 class _Debug(C.Structure):
@@ -78,7 +79,7 @@ class WbcError(RuntimeError):
 _lib = None
 
 EXPORTS = ["wbc_default_params", "wbc_last_error", "wbc_version", "wbc_create", "wbc_destroy", "wbc_set_params",
-           "wbc_set_observer_state", "wbc_get_observer_state", "wbc_cycle", "wbc_debug_update", "wbc_qp_solve",
+           "wbc_set_observer_state", "wbc_get_observer_state", "wbc_set_observer_state2", "wbc_get_observer_state2", "wbc_cycle", "wbc_debug_update", "wbc_qp_solve",
            "wbc_plant_step", "wbc_plant_dynamics_step", "wbc_last_timing", "wbc_last_solve_cycles", "wbc_last_launches", "wbc_solver_shape", "wbc_stage_profile", "wbc_host_alloc",
            "wbc_host_free",
            "wbc_set_trajectory", "wbc_sample_trajectory",
@@ -109,6 +110,8 @@ def load():
     lib.wbc_set_params.argtypes = [C.c_void_p, C.POINTER(Params)]
     lib.wbc_set_observer_state.argtypes = [C.c_void_p, C.c_int, _dp, _dp, C.c_long]
     lib.wbc_get_observer_state.argtypes = [C.c_void_p, C.c_int, _dp, _dp, C.c_long]
+    lib.wbc_set_observer_state2.argtypes = [C.c_void_p, C.c_int, _dp, C.c_long]
+    lib.wbc_get_observer_state2.argtypes = [C.c_void_p, C.c_int, _dp, C.c_long]
     lib.wbc_cycle.argtypes = [C.c_void_p, C.c_int, C.POINTER(_Inputs), C.POINTER(_Outputs), C.c_void_p, C.c_uint]
     lib.wbc_debug_update.argtypes = [C.c_void_p, C.c_int, C.POINTER(_Inputs), C.POINTER(_Debug), C.c_uint]
     lib.wbc_qp_solve.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
@@ -193,6 +196,17 @@ class WbcBatch:
         _check(self.lib.wbc_get_observer_state(self.h, n, yd.ctypes.data_as(_dp), yw.ctypes.data_as(_dp), n),
                "wbc_get_observer_state")
         return yd, yw
+
+    def set_observer_state2(self, yg):
+        """ygamma, the extra integrator of the second-order observer (params.obs_order == 2)."""
+        yg = np.ascontiguousarray(yg, dtype=np.float64)
+        n = yg.shape[1]
+        _check(self.lib.wbc_set_observer_state2(self.h, n, yg.ctypes.data_as(_dp), n), "wbc_set_observer_state2")
+
+    def get_observer_state2(self, n):
+        yg = np.zeros((6, n))
+        _check(self.lib.wbc_get_observer_state2(self.h, n, yg.ctypes.data_as(_dp), n), "wbc_get_observer_state2")
+        return yg
 
     @staticmethod
     def _inputs_struct(sc, n, keep, skip=()):
@@ -301,8 +315,9 @@ class WbcBatch:
             if "status" in want: out["status"] = np.zeros(n, dtype=np.int32)
             if "qp_info" in want: out["qp_info"] = np.zeros((8, n), dtype=np.int32)
             if "qp_flops" in want: out["qp_flops"] = np.zeros(n)
+            if "w3" in want: out["w3"] = np.zeros((12, n))
         o = _Outputs()
-        for k in ("tau", "w", "x", "qp_obj", "status", "qp_info", "qp_flops"):
+        for k in ("tau", "w", "x", "qp_obj", "status", "qp_info", "qp_flops", "w3"):
             setattr(o, k, _ptr(out.get(k)))
         o.ld = max(n, 1)
         _check(self.lib.wbc_cycle(self.h, n, C.byref(ins), C.byref(o), None, HOST_PTRS | (FIFO_DISPATCH if self.fifo_dispatch else 0) | (HOST_SLAB if sc.get("_slab") else 0) | (SAMPLED_TRAJ if sampled_traj else 0)), "wbc_cycle")
@@ -332,7 +347,7 @@ class WbcBatch:
         ins.obs_gain = _ptr(dev_in.get("obs_gain"))
         ins.ld = ld
         o = _Outputs()
-        for k in ("tau", "w", "x", "qp_obj", "status", "qp_info", "qp_flops"):
+        for k in ("tau", "w", "x", "qp_obj", "status", "qp_info", "qp_flops", "w3"):
             setattr(o, k, _ptr(dev_out.get(k)))
         o.ld = out_ld
         flags = DEVICE_PTRS | (0 if sync else NO_SYNC) | (FIFO_DISPATCH if self.fifo_dispatch else 0)

@@ -595,7 +595,7 @@ static int fail(int code, const char* fmt, const char* a = "", const char* b = "
 struct FieldDesc { int k; };
 static const int kInFieldK[15] = {3, 9, 3, 6, 12, 12, 6, 6, 6, 6, 6, 6, 12, 40, 1};
 static const int kInDoublesNoTerrain = 3 + 9 + 3 + 6 + 12 + 12 + 6 + 6 + 6 + 6 + 6 + 6 + 12;   // 93
-static const int kOutDoubles = 12 + 6 + 30 + 1 + 1;   // tau, w, x, obj, flops
+static const int kOutDoubles = 12 + 6 + 30 + 1 + 1 + 12;   // tau, w, x, obj, flops, w3
 static const int kOutInts = 1 + 8;
 
 struct wbc_ctx {
@@ -608,6 +608,7 @@ struct wbc_ctx {
     double* recs;        // [max_batch][QPREC_DOUBLES]
     double* yd;          // [6][max_batch]
     double* yw;
+    double* yg;          // [6][max_batch] ygamma of the second-order observer
     double* w_dev;       // [6][max_batch] (when the caller passes no w)
     double* tau_prev;    // [12][max_batch] last good torque per instance index (hold_tau_on_failure)
     double* scratch;     // [nslots][gl::TOTAL] one block per solve in flight (the monolithic kernels use the first nblocks)
@@ -634,7 +635,7 @@ struct wbc_ctx {
     int solve_smem;         // dynamic shared memory per solver CTA (sl::BYTES, or padded by WBC_SOLVE_CTAS_PER_SM)
     // staging for WBC_HOST_PTRS
     double* d_in;        // [93+40][max_batch]
-    double* d_out;       // [50][max_batch]
+    double* d_out;       // [62][max_batch]
     int* d_mode;         // [max_batch]
     int* d_iout;         // [9][max_batch]
     double* h_pin;       // pinned bounce buffer, max(in,out) doubles
@@ -664,6 +665,7 @@ void wbc_default_params(wbc_params* p)
     p->gravity[0] = 0.0; p->gravity[1] = 0.0; p->gravity[2] = -9.8;
     p->qp_epsx = 1.0e-2; p->qp_rho = 1.0e4; p->qp_outerits = 5;
     p->observer_enabled = 1; p->fix_swing_rhs = 0; p->qp_literal_kkt = 0; p->hold_tau_on_failure = 0;
+    p->obs_gain2 = 1.0; p->obs_order = 1; p->obs_form = 0;
 }
 
 const char* wbc_last_error(void) { return g_err; }
@@ -673,7 +675,7 @@ int wbc_destroy(wbc_ctx* c)
 {
     if (!c) return WBC_OK;
     cudaSetDevice(c->device);
-    cudaFree(c->recs); cudaFree(c->yd); cudaFree(c->yw); cudaFree(c->w_dev); cudaFree(c->tau_prev); cudaFree(c->scratch); cudaFree(c->kkt); cudaFree(c->sq_ctl); cudaFree(c->sq_ring); cudaFree(c->prof); cudaFree(c->queue); cudaFree(c->cost); cudaFree(c->order);
+    cudaFree(c->recs); cudaFree(c->yd); cudaFree(c->yw); cudaFree(c->yg); cudaFree(c->w_dev); cudaFree(c->tau_prev); cudaFree(c->scratch); cudaFree(c->kkt); cudaFree(c->sq_ctl); cudaFree(c->sq_ring); cudaFree(c->prof); cudaFree(c->queue); cudaFree(c->cost); cudaFree(c->order);
     cudaFree(c->traj_dur); cudaFree(c->traj_nodes); cudaFree(c->traj_s); cudaFree(c->traj_t);
     cudaFree(c->d_in); cudaFree(c->d_out); cudaFree(c->d_mode); cudaFree(c->d_iout); cudaFree(c->d_dense);
     if (c->h_pin) cudaFreeHost(c->h_pin);
@@ -729,6 +731,7 @@ int wbc_create(wbc_ctx** out, int device, int max_batch, const wbc_params* param
     TRY(cudaMalloc(&c->recs, nb * QPREC_DOUBLES * sizeof(double)));
     TRY(cudaMalloc(&c->yd, nb * 6 * sizeof(double)));
     TRY(cudaMalloc(&c->yw, nb * 6 * sizeof(double)));
+    TRY(cudaMalloc(&c->yg, nb * 6 * sizeof(double)));
     TRY(cudaMalloc(&c->w_dev, nb * 6 * sizeof(double)));
     TRY(cudaMalloc(&c->tau_prev, nb * 12 * sizeof(double)));
     TRY(cudaMemset(c->tau_prev, 0, nb * 12 * sizeof(double)));
@@ -769,6 +772,7 @@ int wbc_create(wbc_ctx** out, int device, int max_batch, const wbc_params* param
     TRY(cudaMallocHost(&c->h_pin_i, nb * kOutInts * sizeof(int)));
     TRY(cudaMemset(c->yd, 0, nb * 6 * sizeof(double)));
     TRY(cudaMemset(c->yw, 0, nb * 6 * sizeof(double)));
+    TRY(cudaMemset(c->yg, 0, nb * 6 * sizeof(double)));
     TRY(cudaMemset(c->scratch, 0, (size_t)c->nslots * gl::TOTAL * sizeof(double)));
     TRY(cudaMemset(c->kkt, 0, (size_t)nteams * gl::KKT_DOUBLES * sizeof(double)));
     TRY(cudaFuncSetAttribute(wbc_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));      // padded requests: see wbc_cycle
@@ -814,6 +818,26 @@ int wbc_set_observer_state(wbc_ctx* c, int n, const double* yd, const double* yw
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaMemcpy2D(c->yd, (size_t)c->max_batch * 8, yd, (size_t)ld * 8, (size_t)n * 8, 6, cudaMemcpyHostToDevice));
     CU(cudaMemcpy2D(c->yw, (size_t)c->max_batch * 8, yw, (size_t)ld * 8, (size_t)n * 8, 6, cudaMemcpyHostToDevice));
+    return WBC_OK;
+}
+
+int wbc_set_observer_state2(wbc_ctx* c, int n, const double* yg, long ld)
+{
+    if (!c || !yg || n < 0 || n > c->max_batch || ld < n) return fail(WBC_EINVAL, "wbc_set_observer_state2: bad arguments");
+    if (n == 0) return WBC_OK;
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaMemcpy2D(c->yg, (size_t)c->max_batch * 8, yg, (size_t)ld * 8, (size_t)n * 8, 6, cudaMemcpyHostToDevice));
+    return WBC_OK;
+}
+
+int wbc_get_observer_state2(wbc_ctx* c, int n, double* yg, long ld)
+{
+    if (!c || !yg || n < 0 || n > c->max_batch || ld < n) return fail(WBC_EINVAL, "wbc_get_observer_state2: bad arguments");
+    if (n == 0) return WBC_OK;
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaMemcpy2D(yg, (size_t)ld * 8, c->yg, (size_t)c->max_batch * 8, (size_t)n * 8, 6, cudaMemcpyDeviceToHost));
     return WBC_OK;
 }
 
@@ -936,6 +960,8 @@ int wbc_cycle(wbc_ctx* c, int n, const wbc_inputs* in, const wbc_outputs* out, v
     SolveOut so;
     double* w_ptr;
     long w_ld;
+    double* w3_ptr;
+    long w3_ld;
     if (dev_ptrs) {
         to_dev_inputs(in, &din);
         if (sampled) {
@@ -947,6 +973,7 @@ int wbc_cycle(wbc_ctx* c, int n, const wbc_inputs* in, const wbc_outputs* out, v
         so.qp_flops = out->qp_flops; so.ld = out->ld;
         w_ptr = out->w ? out->w : c->w_dev;
         w_ld = out->w ? out->ld : c->max_batch;
+        w3_ptr = out->w3; w3_ld = out->ld;
     } else {
         rc = stage_inputs(c, n, in, s, &din, (flags & WBC_HOST_SLAB) != 0, sampled);
         if (rc) return rc;
@@ -955,10 +982,12 @@ int wbc_cycle(wbc_ctx* c, int n, const wbc_inputs* in, const wbc_outputs* out, v
         so.status = out->status ? c->d_iout : nullptr; so.qp_info = out->qp_info ? c->d_iout + n : nullptr; so.ld = n;
         w_ptr = c->d_out + 12L * n;
         w_ld = n;
+        w3_ptr = out->w3 ? c->d_out + 50L * n : nullptr; w3_ld = n;
     }
     so.tau_prev = c->tau_prev; so.ld_prev = c->max_batch;
     FrontState st;
-    st.yd = c->yd; st.yw = c->yw; st.ld = c->max_batch;
+    st.yd = c->yd; st.yw = c->yw; st.yg = c->yg; st.ld = c->max_batch;
+    st.w3 = w3_ptr; st.w3_ld = w3_ld;
     DevDebug nodbg;
     memset(&nodbg, 0, sizeof(nodbg));
     // dispatch order: longest solve first, predicted by each instance's previous solve (same batch size only)
@@ -1021,22 +1050,23 @@ int wbc_cycle(wbc_ctx* c, int n, const wbc_inputs* in, const wbc_outputs* out, v
     if (!dev_ptrs) {
         // results: straight into the caller's arrays where they are page-locked, else one D2H of the packed block
         // (tau 12 | w 6 | x 30 | obj 1 | flops 1) into the bounce buffer and a scatter after the synchronisation
-        struct OutF { double* p; int k0, K; long ld; } of[5] = {{out->tau, 0, 12, out->ld}, {out->w, 12, 6, out->ld}, {out->x, 18, 30, out->ld},
-                                                                {out->qp_obj, 48, 1, n}, {out->qp_flops, 49, 1, n}};
-        bool direct[5];
+        constexpr int NOF = 6;
+        struct OutF { double* p; int k0, K; long ld; } of[NOF] = {{out->tau, 0, 12, out->ld}, {out->w, 12, 6, out->ld}, {out->x, 18, 30, out->ld},
+                                                                  {out->qp_obj, 48, 1, n}, {out->qp_flops, 49, 1, n}, {out->w3, 50, 12, out->ld}};
+        bool direct[NOF];
         const size_t row = (size_t)n * sizeof(double);
         int hi = 0;                                   // bounce prefix, in rows
-        for (int f = 0; f < 5; f++) {
+        for (int f = 0; f < NOF; f++) {
             direct[f] = of[f].p && is_pinned_host(of[f].p);
             if (of[f].p && !direct[f]) hi = of[f].k0 + of[f].K;
         }
-        for (int f = 0; f < 5; f++)
+        for (int f = 0; f < NOF; f++)
             if (direct[f])
                 CU(cudaMemcpy2DAsync(of[f].p, (size_t)of[f].ld * sizeof(double), c->d_out + (size_t)of[f].k0 * n, row, row, of[f].K, cudaMemcpyDeviceToHost, s));
         if (hi) CU(cudaMemcpyAsync(c->h_pin, c->d_out, (size_t)hi * row, cudaMemcpyDeviceToHost, s));
         if (out->status || out->qp_info) CU(cudaMemcpyAsync(c->h_pin_i, c->d_iout, (size_t)kOutInts * n * sizeof(int), cudaMemcpyDeviceToHost, s));
         CU(cudaStreamSynchronize(s));
-        for (int f = 0; f < 5; f++)
+        for (int f = 0; f < NOF; f++)
             if (of[f].p && !direct[f])
                 for (int k = 0; k < of[f].K; k++) memcpy(of[f].p + (size_t)k * of[f].ld, c->h_pin + (size_t)(of[f].k0 + k) * n, row);
         if (out->status) memcpy(out->status, c->h_pin_i, (size_t)n * 4);
@@ -1305,14 +1335,15 @@ int wbc_debug_update(wbc_ctx* c, int n, const wbc_inputs* in, const wbc_debug* d
     // reads them): run on a scratch copy of yd/yw and into scratch records.
     double* ytmp = nullptr;
     double* rtmp = nullptr;
-    cudaError_t e = cudaMalloc(&ytmp, (size_t)18 * n * sizeof(double));
+    cudaError_t e = cudaMalloc(&ytmp, (size_t)24 * n * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&rtmp, (size_t)n * QPREC_DOUBLES * sizeof(double));
     if (e != cudaSuccess) { cudaFree(dbuf); cudaFree(ytmp); return fail(WBC_ENOMEM, "wbc_debug_update: %s", cudaGetErrorString(e)); }
     e = cudaMemcpy2DAsync(ytmp, (size_t)n * 8, c->yd, (size_t)c->max_batch * 8, (size_t)n * 8, 6, cudaMemcpyDeviceToDevice, s);
     if (e == cudaSuccess) e = cudaMemcpy2DAsync(ytmp + 6L * n, (size_t)n * 8, c->yw, (size_t)c->max_batch * 8, (size_t)n * 8, 6, cudaMemcpyDeviceToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpy2DAsync(ytmp + 18L * n, (size_t)n * 8, c->yg, (size_t)c->max_batch * 8, (size_t)n * 8, 6, cudaMemcpyDeviceToDevice, s);
     if (e == cudaSuccess) {
         FrontState st;
-        st.yd = ytmp; st.yw = ytmp + 6L * n; st.ld = n;
+        st.yd = ytmp; st.yw = ytmp + 6L * n; st.yg = ytmp + 18L * n; st.ld = n; st.w3 = nullptr; st.w3_ld = 0;
         const int fthreads = front_threads(c, n);
         wbc_front_kernel<<<(n + fthreads - 1) / fthreads, fthreads, 0, s>>>(c->params, din, st, n, rtmp, ytmp + 12L * n, n, dd, 1, DispatchOrder{nullptr, nullptr, nullptr, nullptr}, StageReset{nullptr, 0, 0, 0, nullptr, 0, 0});
         e = cudaStreamSynchronize(s);

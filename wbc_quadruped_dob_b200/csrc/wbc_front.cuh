@@ -125,6 +125,9 @@ struct FrontState {        // observer state carried across cycles (main.cpp:721
     double* yd;            // [6][ld]
     double* yw;            // [6][ld]
     long ld;
+    double* yg;            // [6][ld] ygamma: integrator of the second-order recursion (Params::obs_order == 2), else unused
+    double* w3;            // [12][w3_ld] or nullptr: the estimate mapped onto the feet (estimator_sem.cpp:64-70)
+    long w3_ld;
 };
 
 // Floating-base dynamics of one instance in the MIXED representation (the first half of update(), main.cpp:591-630): mass-matrix
@@ -425,22 +428,63 @@ WBC_DEVFN inline void front_cycle(const Params& P, const DevInputs& in, const Fr
     if (P.observer_enabled) {
         const double T = P.obs_dt, k0 = in.obs_gain ? in.obs_gain[i] : P.obs_gain;
         const double mgain = (1.0 / (1.0 + k0 * T)) * k0;                   // (I + k0 T)^-1 k0, main.cpp:716
-        double ydn[6], ywn[6];
+        const bool second = P.obs_order == 2, expl = P.obs_form == 1;
+        const double k2 = P.obs_gain2;
+        double ydn[6], ywn[6], ygn[6];
         for (int a = 0; a < 6; a++) {
             const double yd = st.yd[(long)a * st.ld + i] + dd6[a] * T;      // 717
-            const double wv = mgain * (rho6[a] - st.yw[(long)a * st.ld + i] - yd);   // 718
+            double wv;
+            if (!second) {
+                if (!expl) wv = mgain * (rho6[a] - st.yw[(long)a * st.ld + i] - yd);   // 718
+                else wv = k0 * (rho6[a] - st.yw[(long)a * st.ld + i] - yd);            // estimator_sem.cpp:57
+                ygn[a] = 0.0;
+            } else {
+                // second order: gamma1 = k0 (rho - yw - yd), ygamma' = gamma1 - w, w = k2 ygamma, discretised like
+                // the first-order forms: backward Euler with the unknown w on both sides (form 0), or forward Euler (form 1)
+                const double e = rho6[a] - st.yw[(long)a * st.ld + i] - yd;
+                const double ygp = st.yg[(long)a * st.ld + i];
+                if (!expl) {
+                    wv = k2 * (ygp + T * k0 * e) / (1.0 + k2 * T + k0 * k2 * T * T);
+                    ygn[a] = ygp + T * (k0 * (e - wv * T) - wv);
+                } else {
+                    ygn[a] = ygp + T * (k0 * e - k2 * ygp);
+                    wv = k2 * ygn[a];
+                }
+            }
             ydn[a] = yd;
             ywn[a] = st.yw[(long)a * st.ld + i] + wv * T;                   // 719
             west[a] = wv;
-            finite_obs = finite_obs && (yd - yd == 0.0) && (ywn[a] - ywn[a] == 0.0);
+            finite_obs = finite_obs && (yd - yd == 0.0) && (ywn[a] - ywn[a] == 0.0) && (ygn[a] - ygn[a] == 0.0);
         }
         // the carried state (main.cpp:721-724) only advances on finite values: a NaN among the inputs must not poison the
         // instance's observer for the rest of the run.  The estimate itself stays non-finite here, so Wcom_des and with it the
         // QP record are, and the solver kernel flags the instance (WBC_ST_NONFINITE) instead of solving it.
-        if (finite_obs)
+        if (finite_obs) {
             for (int a = 0; a < 6; a++) { st.yd[(long)a * st.ld + i] = ydn[a]; st.yw[(long)a * st.ld + i] = ywn[a]; }
+            if (second)
+                for (int a = 0; a < 6; a++) st.yg[(long)a * st.ld + i] = ygn[a];
+        }
     } else {
         for (int a = 0; a < 6; a++) west[a] = 0.0;
+    }
+    if (st.w3) {
+        // getw3 (estimator_sem.cpp:64-70): w3 = pinv(J)' w, J = JacCOM_lin[:, 0:6] (12 x 6, full column rank whenever the feet span
+        // more than a line), so pinv(J)' = J (J'J)^-1: one 6 x 6 Cholesky.  A non-positive pivot (degenerate foot geometry) gives NaN.
+        double G[36], y[6];
+        for (int a = 0; a < 6; a++)
+            for (int b = 0; b <= a; b++) {
+                double g = 0.0;
+                for (int r = 0; r < 12; r++) g += Jc[r * 6 + a] * Jc[r * 6 + b];
+                G[a * 6 + b] = g; G[b * 6 + a] = g;
+            }
+        chol6(G);
+        for (int a = 0; a < 6; a++) y[a] = finite_obs ? west[a] : 0.0;
+        chol6_solve(G, y);
+        for (int r = 0; r < 12; r++) {
+            double v = 0.0;
+            for (int a = 0; a < 6; a++) v += Jc[r * 6 + a] * y[a];
+            st.w3[(long)r * st.w3_ld + i] = v;
+        }
     }
     for (int a = 0; a < 6; a++) w_out[(long)a * w_ld + i] = finite_obs ? west[a] : 0.0;
 

@@ -36,11 +36,14 @@ struct Params {
     double obs_dt;            // 0.0025            main.cpp:715
     double gravity[3];        // (0,0,-9.8)        main.cpp:855
     double qp_epsx, qp_rho;   // 1e-2, 1e4         lopt.cpp:101
+    double obs_gain2;         // 1                 second entry of the coefficient vector {10, 1} (main.cpp:707-708, estimator_sem.cpp:47-48)
     int qp_outerits;          // 5                 lopt.cpp:101
     int observer_enabled;     // north_star: 1 (the reference ships with the call commented out, main.cpp:1029)
     int fix_swing_rhs;        // 0 keeps the reference's zero swing-equality rhs (main.cpp:1238-1241)
     int qp_literal_kkt;       // 0: reduced multiplier update, literal form as fallback; 1: literal form only (opt.cpp:41803-42032)
     int hold_tau_on_failure;  // 1: a failed instance keeps the last good tau of its index (main.cpp:242; lopt.cpp:114-116 swallows the failure)
+    int obs_order;            // 1: the observer main.cpp runs; 2: second-order recursion through the ygamma state
+    int obs_form;             // 0: main.cpp:716-718, w = (I + kT)^-1 k (...); 1: estimator_sem.cpp:55-57, w = k (...)
 };
 
 struct DevInputs {
