@@ -179,6 +179,12 @@ int wbc_cycle(wbc_ctx* ctx, int n, const wbc_inputs* in, const wbc_outputs* out,
  * wbc_cycle would compute) and changes neither that state nor the records wbc_plant_step reads. */
 int wbc_debug_update(wbc_ctx* ctx, int n, const wbc_inputs* in, const wbc_debug* dbg, unsigned flags);
 
+/* The QP records the front kernel of the last wbc_cycle on this ctx left for the solver (internal layout, wbc_types.h: the
+ * non-redundant content of Q, c, L): recs [n][*doubles_per_record], host pointer; recs == NULL only reports the record size.
+ * Validation only: the tests compare the two front kernels (four lanes per instance, the default; a thread per instance,
+ * WBC_FRONT=thread in the environment when the ctx is created) record by record. */
+int wbc_debug_qp_records(wbc_ctx* ctx, int n, double* recs, int* doubles_per_record);
+
 /* The OPT operator (lopt.h:5-36): n dense QPs of the controller's shape, instance-major:
  *   Q [n][30*30] row-major (lower triangle used, opt.cpp:4962), c [n][30], L [n][nrows*31] row-major,
  *   first neq rows "=", the rest "<=" (lopt.cpp:35-66); x [n][30].  nrows <= 86.

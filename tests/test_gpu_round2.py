@@ -197,3 +197,44 @@ def test_staged_and_monolithic_solver_kernels_agree_bit_for_bit():
         outs.append(np.load(path))
     for k in outs[0].files:
         assert np.array_equal(outs[0][k], outs[1][k]), k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,terrain", [(1, False), (5, True), (1003, True), (4096, False)])
+def test_leg_parallel_front_kernel_matches_the_thread_per_instance_one(n, terrain):
+    """The control cycle's front kernel works four lanes per instance (one per leg, wbc_front_leg.cuh); the thread-per-instance
+    formulation (wbc_front.cuh: what wbc_debug_update, the plant and the host emulation run, and what every stage test checks
+    against the oracle) stays selectable.  Same inputs, both kernels: every field of the QP record, the estimate, the foot-wrench map
+    and the carried observer state agree to rounding, the torques to 1e-7 -- for the second-order observer form too."""
+    import os
+    from wbc_quadruped_dob_b200 import api
+    sc = S.make(n, mode_mix=(0.4, 0.3, 0.3), pushes=True, terrain=terrain, seed=77)
+    rng = np.random.default_rng(3)
+    sc["obs_yd"] = 0.2 * rng.standard_normal((6, n)); sc["obs_yw"] = 0.1 * rng.standard_normal((6, n))
+    yg = 0.05 * rng.standard_normal((6, n))
+    for order in (1, 2):
+        p = api.default_params()
+        p.obs_order, p.obs_gain2 = order, 4.0
+        res = {}
+        for kind in ("leg", "thread"):
+            os.environ["WBC_FRONT"] = kind
+            try:
+                b = api.WbcBatch(max_batch=n, params=p)
+            finally:
+                del os.environ["WBC_FRONT"]
+            b.set_observer_state(sc["obs_yd"], sc["obs_yw"]); b.set_observer_state2(yg)
+            out = b.cycle(sc, want=("status", "x", "w3"))
+            res[kind] = (out, b.qp_records(n), b.get_observer_state(n), b.get_observer_state2(n))
+            b.close()
+        (o1, r1, s1, g1), (o2, r2, s2, g2) = res["leg"], res["thread"]
+        used = 574                                    # the record's last two doubles are padding
+        scale = np.maximum(1.0, np.abs(r2[:, :used]).max(axis=0, keepdims=True))
+        assert np.max(np.abs(r1[:, :used] - r2[:, :used]) / scale) < 1e-11, order
+        assert np.max(np.abs(o1["w"] - o2["w"])) < 1e-11 * (1.0 + np.abs(o2["w"]).max())
+        assert np.max(np.abs(o1["w3"] - o2["w3"])) < 1e-10 * (1.0 + np.abs(o2["w3"]).max())
+        for a, bb in zip(s1 + (g1,), s2 + (g2,)):
+            assert np.max(np.abs(a - bb)) < 1e-11 * (1.0 + np.abs(bb).max())
+        ok = (o1["status"] == 0) & (o2["status"] == 0)
+        assert np.array_equal(o1["status"] == 0, o2["status"] == 0)
+        # the solver amplifies last-bit differences of its input on the odd instance (SURVEY.md Appendix F): 1e-8 seen in 1003
+        assert np.max(np.abs(o1["tau"][:, ok] - o2["tau"][:, ok]) / (1.0 + np.abs(o2["tau"][:, ok]))) < 1e-7

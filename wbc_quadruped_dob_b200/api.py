@@ -79,7 +79,7 @@ class WbcError(RuntimeError):
 _lib = None
 
 EXPORTS = ["wbc_default_params", "wbc_last_error", "wbc_version", "wbc_create", "wbc_destroy", "wbc_set_params",
-           "wbc_set_observer_state", "wbc_get_observer_state", "wbc_set_observer_state2", "wbc_get_observer_state2", "wbc_cycle", "wbc_debug_update", "wbc_qp_solve",
+           "wbc_set_observer_state", "wbc_get_observer_state", "wbc_set_observer_state2", "wbc_get_observer_state2", "wbc_cycle", "wbc_debug_update", "wbc_debug_qp_records", "wbc_qp_solve",
            "wbc_plant_step", "wbc_plant_dynamics_step", "wbc_last_timing", "wbc_last_solve_cycles", "wbc_last_launches", "wbc_solver_shape", "wbc_stage_profile", "wbc_host_alloc",
            "wbc_host_free",
            "wbc_set_trajectory", "wbc_sample_trajectory",
@@ -110,6 +110,7 @@ def load():
     lib.wbc_set_params.argtypes = [C.c_void_p, C.POINTER(Params)]
     lib.wbc_set_observer_state.argtypes = [C.c_void_p, C.c_int, _dp, _dp, C.c_long]
     lib.wbc_get_observer_state.argtypes = [C.c_void_p, C.c_int, _dp, _dp, C.c_long]
+    lib.wbc_debug_qp_records.argtypes = [C.c_void_p, C.c_int, _dp, C.POINTER(C.c_int)]
     lib.wbc_set_observer_state2.argtypes = [C.c_void_p, C.c_int, _dp, C.c_long]
     lib.wbc_get_observer_state2.argtypes = [C.c_void_p, C.c_int, _dp, C.c_long]
     lib.wbc_cycle.argtypes = [C.c_void_p, C.c_int, C.POINTER(_Inputs), C.POINTER(_Outputs), C.c_void_p, C.c_uint]
@@ -352,6 +353,14 @@ class WbcBatch:
         o.ld = out_ld
         flags = DEVICE_PTRS | (0 if sync else NO_SYNC) | (FIFO_DISPATCH if self.fifo_dispatch else 0)
         _check(self.lib.wbc_cycle(self.h, n, C.byref(ins), C.byref(o), stream, flags), "wbc_cycle")
+
+    def qp_records(self, n):
+        """The QP records of the last cycle [n, doubles per record] (wbc_debug_qp_records; validation only)."""
+        k = C.c_int(0)
+        _check(self.lib.wbc_debug_qp_records(self.h, 0, None, C.byref(k)), "wbc_debug_qp_records")
+        out = np.zeros((n, k.value))
+        _check(self.lib.wbc_debug_qp_records(self.h, n, out.ctypes.data_as(_dp), None), "wbc_debug_qp_records")
+        return out
 
     def debug_update(self, sc, n=None):
         """update() intermediates (wbc_debug_update) for stage-by-stage validation."""

@@ -462,7 +462,9 @@ __device__ __noinline__ void qqp_stats(int nic, double rho, double exbA, double 
     if (l < NMAIN) {
 #pragma unroll 1
         for (int j = l; j < NMAIN; j++) {
-            const double v = H[l * LDH + j], vv = fabs(v);
+            // H[l][j] read as H[j][l] (generate_ex_model writes both with the same value): the lanes then walk a row of H side by
+            // side instead of 30 rows at the same bank (that was a 16-way conflict, a third of the kernel's replays)
+            const double v = H[j * LDH + l], vv = fabs(v);
             const double k = ((double)l == v) ? 1.0 : 2.0;
             s1 += vv * k; s2 += vv * vv * k;
         }

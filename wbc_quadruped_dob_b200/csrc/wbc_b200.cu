@@ -19,6 +19,7 @@
 #include "qp_warp.cuh"
 #include "wbc_assemble.cuh"
 #include "wbc_front.cuh"
+#include "wbc_front_leg.cuh"
 #include "wbc_traj.cuh"
 #include "wbc_types.h"
 
@@ -87,6 +88,45 @@ __global__ void __launch_bounds__(64) wbc_front_kernel(Params P, DevInputs in, F
     }
     if (i >= n) return;
     front_cycle(P, in, st, i, recs + i * QPREC_DOUBLES, w_out, w_ld, has_dbg ? &dbg : nullptr);
+}
+
+// Four lanes per instance (wbc_front_leg.cuh): the control cycle's front kernel.  Same prelude as wbc_front_kernel (the dispatch
+// order of the solve launch that follows and the staged solver's queue reset ride along, indexed by thread).
+__global__ void __launch_bounds__(128) wbc_front_leg_kernel(Params P, DevInputs in, FrontState st, int n, double* __restrict__ recs,
+                                                            double* __restrict__ w_out, long w_ld, DispatchOrder ord, StageReset sr)
+{
+    __shared__ int base[ORD_NB];
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (sr.ctl) {
+        const long nth = (long)gridDim.x * blockDim.x;
+        for (long k = t; k < sr.nctl; k += nth) sr.ctl[k] = (k == sr.free_tail_index || k == sr.free_avail_index) ? sr.nslots : 0;
+        for (long k = t; k < 3L * sr.rsize; k += nth) sr.ring[k] = (k >= 2L * sr.rsize && k - 2L * sr.rsize < sr.nslots) ? (int)(k - 2L * sr.rsize) : -1;
+    }
+    if (ord.cost) {
+        if (threadIdx.x < 32) {
+            const int l = threadIdx.x;
+            int h[8], sum = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) { h[k] = ord.hist[ORD_NB - 1 - (8 * l + k)]; sum += h[k]; }
+            int incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (l >= o) incl += u; }
+            int run = incl - sum;
+#pragma unroll
+            for (int k = 0; k < 8; k++) { base[ORD_NB - 1 - (8 * l + k)] = run; run += h[k]; }
+        }
+        __syncthreads();
+        if (t < n) {
+            const int b = cost_bucket(ord.cost[t]);
+            ord.order[base[b] + atomicAdd(ord.cursor + b, 1)] = (int)t;
+        }
+    }
+    const long first = (t & ~31L) >> 2;              // first instance of this warp
+    if (first >= n) return;
+    long i = t >> 2;
+    const bool valid = i < n;
+    if (!valid) i = n - 1;                            // lanes past the batch compute along (the shuffles need them) and store nothing
+    wbc::front_cycle_leg(P, in, st, i, valid, (int)(t & 3), recs + i * QPREC_DOUBLES, w_out, w_ld);
 }
 
 struct SolveOut {
@@ -619,6 +659,7 @@ struct wbc_ctx {
     int sq_rsize;
     int staged;          // 0: wbc_solve_kernel, 1: wbc_solve_staged_kernel, 2 (default): by batch size (staged from staged_min_n instances)
     int staged_min_n;
+    int front_leg;       // 1 (default): wbc_front_leg_kernel, four lanes per instance; 0: wbc_front_kernel, a thread per instance (WBC_FRONT=thread)
     int last_staged;     // which kernel the last wbc_cycle launched
     int m_period, m_group;   // SM roles of the staged solver
     unsigned long long* prof;   // [nblocks][12] per-warp profile of the last staged launch (WBC_STAGE_PROF=1)
@@ -740,15 +781,17 @@ int wbc_create(wbc_ctx** out, int device, int max_batch, const wbc_params* param
     // Measured on B200 (profiles/README.md, round 2): the staged kernel is 19 % faster at 65 536 instances (37.1 against 44.1 ms) and
     // slower at 4 096 (4.0 against 3.3 ms: a solve is eleven hand-overs and the batch is only 2.3 solves per warp), so the choice
     // goes by batch size; WBC_SOLVER = mono | staged forces one, WBC_STAGED_MIN_N moves the threshold.
-    c->staged = 2; c->staged_min_n = 12288; c->m_period = (0 << 16) | (2 << 8) | 5; c->m_group = 2;       // of every 5 SM pairs: 2 POST/SETUP, 3 QQP
+    c->staged = 2; c->staged_min_n = 12288; c->m_period = (3 << 16) | (7 << 8) | 25; c->m_group = 2;     // of every 25 SM pairs: 3 SETUP, 7 POST, 15 QQP (0.5 % over 2 POST/SETUP in 5)
     if (const char* ev = getenv("WBC_SOLVER")) c->staged = strcmp(ev, "staged") == 0 ? 1 : (strcmp(ev, "mono") == 0 ? 0 : 2);
     if (const char* ev = getenv("WBC_STAGED_MIN_N")) c->staged_min_n = atoi(ev);
+    c->front_leg = 1;
+    if (const char* ev = getenv("WBC_FRONT")) c->front_leg = strcmp(ev, "thread") != 0;
     if (const char* ev = getenv("WBC_STAGE_ROLES")) {        // "nS,nP/den"
         int a = 0, b = 2, d = 5;
         if (sscanf(ev, "%d,%d/%d", &a, &b, &d) == 3 && d > 0 && d < 256 && a >= 0 && b >= 0 && a + b <= d) c->m_period = (a << 16) | (b << 8) | d;
     }
     if (const char* ev = getenv("WBC_STAGE_M_GROUP")) c->m_group = atoi(ev) > 0 ? atoi(ev) : 1;
-    double slots_per_warp = 1.5;
+    double slots_per_warp = 2.0;     // measured at 65 536 instances: 1.0 -> 42.7 ms, 1.5 -> 39.2, 2.0 -> 39.1, 3.0 -> 38.9 (profiles/README.md)
     if (const char* ev = getenv("WBC_STAGE_SLOTS_PER_WARP")) slots_per_warp = atof(ev) >= 1.0 ? atof(ev) : 1.0;
     const long want_slots = (long)((double)nteams * slots_per_warp + 0.5);
     c->nslots = (int)(want_slots < (long)max_batch ? want_slots : (nteams > max_batch ? nteams : max_batch));
@@ -1011,7 +1054,13 @@ int wbc_cycle(wbc_ctx* c, int n, const wbc_inputs* in, const wbc_outputs* out, v
         sr.free_avail_index = (int)(offsetof(StageCtl, avail) / sizeof(int)) + SQ_FREE * 32;
         sr.ring = c->sq_ring; sr.rsize = c->sq_rsize; sr.nslots = c->nslots;
     }
-    wbc_front_kernel<<<(n + fthreads - 1) / fthreads, fthreads, 0, s>>>(c->params, din, st, n, c->recs, w_ptr, w_ld, nodbg, 0, ord, sr);
+    if (c->front_leg) {
+        // four lanes per instance; 64-thread CTAs (16 instances) keep a small batch spread over every SM
+        const int lt = (4L * n >= (long)c->sm_count * 128 * 4) ? 128 : 64;
+        wbc_front_leg_kernel<<<(unsigned)((4L * n + lt - 1) / lt), lt, 0, s>>>(c->params, din, st, n, c->recs, w_ptr, w_ld, ord, sr);
+    } else {
+        wbc_front_kernel<<<(n + fthreads - 1) / fthreads, fthreads, 0, s>>>(c->params, din, st, n, c->recs, w_ptr, w_ld, nodbg, 0, ord, sr);
+    }
     CU(cudaEventRecord(c->ev1, s));
     // Resident solver warps for this batch.  Large batches take every warp that fits (12 per SM); a batch of a few thousand is
     // only two or three solves per warp, where the step ends with its longest solve and every solve runs slower the more
@@ -1359,6 +1408,19 @@ int wbc_debug_update(wbc_ctx* c, int n, const wbc_inputs* in, const wbc_debug* d
     cudaFree(rtmp);
     c->launches = 1;
     if (e != cudaSuccess) return fail(WBC_ECUDA, "wbc_debug_update: %s", cudaGetErrorString(e));
+    return WBC_OK;
+}
+
+int wbc_debug_qp_records(wbc_ctx* c, int n, double* recs, int* doubles_per_record)
+{
+    if (!c) return fail(WBC_EINVAL, "wbc_debug_qp_records: null ctx");
+    if (doubles_per_record) *doubles_per_record = QPREC_DOUBLES;
+    if (!recs) return WBC_OK;
+    if (n < 0 || n > c->last_n) return fail(WBC_EINVAL, "wbc_debug_qp_records: n exceeds the last wbc_cycle's batch");
+    if (n == 0) return WBC_OK;
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaMemcpy(recs, c->recs, (size_t)n * QPREC_DOUBLES * sizeof(double), cudaMemcpyDeviceToHost));
     return WBC_OK;
 }
 
