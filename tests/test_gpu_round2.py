@@ -204,8 +204,10 @@ def test_staged_and_monolithic_solver_kernels_agree_bit_for_bit():
 def test_leg_parallel_front_kernel_matches_the_thread_per_instance_one(n, terrain):
     """The control cycle's front kernel works four lanes per instance (one per leg, wbc_front_leg.cuh); the thread-per-instance
     formulation (wbc_front.cuh: what wbc_debug_update, the plant and the host emulation run, and what every stage test checks
-    against the oracle) stays selectable.  Same inputs, both kernels: every field of the QP record, the estimate, the foot-wrench map
-    and the carried observer state agree to rounding, the torques to 1e-7 -- for the second-order observer form too."""
+    against the oracle) stays selectable.  The leg-parallel kernel performs the thread-per-instance kernel's additions in the same
+    order (it fetches every link's operands from the lane that owns them); what is left between the two is the compiler's choice
+    of fused multiply-adds.  Same inputs, both kernels: every field of the QP record, the estimate, the foot-wrench map and the
+    carried observer state agree to 1e-11, the torques to 1e-7 -- for the second-order observer form too."""
     import os
     from wbc_quadruped_dob_b200 import api
     sc = S.make(n, mode_mix=(0.4, 0.3, 0.3), pushes=True, terrain=terrain, seed=77)

@@ -94,14 +94,18 @@ WBC_HD M3 axis_rotation(const V3& a, double th)
 // In-place lower Cholesky of a 6x6 SPD matrix (row-major) and solves with it.
 WBC_HD void chol6(double* A)
 {
+#pragma unroll
     for (int j = 0; j < 6; j++) {
         double d = A[j * 6 + j];
+#pragma unroll
         for (int k = 0; k < j; k++) d -= A[j * 6 + k] * A[j * 6 + k];
         d = sqrt(d);
         A[j * 6 + j] = d;
         const double r = 1.0 / d;
+#pragma unroll
         for (int i = j + 1; i < 6; i++) {
             double s = A[i * 6 + j];
+#pragma unroll
             for (int k = 0; k < j; k++) s -= A[i * 6 + k] * A[j * 6 + k];
             A[i * 6 + j] = s * r;
         }
@@ -109,13 +113,17 @@ WBC_HD void chol6(double* A)
 }
 WBC_HD void chol6_solve(const double* L, double* x)
 {
+#pragma unroll
     for (int i = 0; i < 6; i++) {
         double s = x[i];
+#pragma unroll
         for (int k = 0; k < i; k++) s -= L[i * 6 + k] * x[k];
         x[i] = s / L[i * 6 + i];
     }
+#pragma unroll
     for (int i = 5; i >= 0; i--) {
         double s = x[i];
+#pragma unroll
         for (int k = i + 1; k < 6; k++) s -= L[k * 6 + i] * x[k];
         x[i] = s / L[i * 6 + i];
     }

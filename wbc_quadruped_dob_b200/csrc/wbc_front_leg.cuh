@@ -6,12 +6,15 @@
 //   * per leg, in its lane: FK, velocities and bias accelerations of the three links, their Newton-Euler wrenches, the leg's share of
 //     the whole-robot sums (mass moment, rotational inertia about the base origin, base rows of h and g), its three CRBA columns
 //     (Mbj, the 3x3 diagonal block of Mjj), its bias torques, its foot kinematics and foot Jacobian;
-//   * 18 doubles are summed over the four lanes with two butterfly shuffles each (every lane gets the same bits);
+//   * the whole-robot sums run link by link in the thread-per-instance kernel's order, every lane fetching each link's operands
+//     from its owner (shuffles inside the group of four): what is left between the two kernels is the compiler's choice of fused
+//     multiply-adds (agreement 1e-11 on every field of the QP record; butterfly sums were measured 14 us faster at 4096 instances
+//     and moved one robot-cycle of the 47 104 of the rollout parity test from 2e-10 to 1.2e-6 -- the solver amplifies last bits);
 //   * the 6x6 base block is factored by every lane (a few dozen flops; splitting it would cost more shuffles than it saves);
-//     each lane solves for ITS three columns of P = Mb^-1 Mbj; P dq_j is a second, 6-double sum over the lanes;
+//     each lane solves for ITS three columns of P = Mb^-1 Mbj; P dq_j is accumulated in DoF order over the lanes;
 //   * the dense joint block Mjj - Mbj' P and the joint columns of the foot Jacobians need every column of P: the lanes pass their
 //     6x3 blocks round (shuffles inside the group of four), and each lane forms and stores its three rows, one 3x3 block at a time;
-//   * J' Fgrf is a third sum (6 doubles); the observer, Wcom_des and the CoM block are then formed by every lane and stored by lane 0.
+//   * J' Fgrf runs over the twelve foot rows in order (every lane gets every foot's lever arm and force); the observer, Wcom_des and the CoM block are then formed by every lane and stored by lane 0.
 // A thread handles a quarter of the instance's arithmetic and its longest dependent chain is a leg, not the robot: the kernel
 // is 4 x as many warps of a quarter of the length each, which is what a batch of a few thousand (or one) robot needs; nothing
 // lives in local memory.
@@ -22,15 +25,9 @@
 namespace wbc {
 
 constexpr unsigned FL_FULL = 0xffffffffu;
-__device__ __forceinline__ double leg_sum(double v)
-{
-    v += __shfl_xor_sync(FL_FULL, v, 1);
-    v += __shfl_xor_sync(FL_FULL, v, 2);
-    return v;
-}
-__device__ __forceinline__ V3 leg_sum(const V3& a) { return v3(leg_sum(a.x), leg_sum(a.y), leg_sum(a.z)); }
 // the value lane `leg` of this instance's group holds
 __device__ __forceinline__ double leg_get(double v, int leg) { return __shfl_sync(FL_FULL, v, leg, 4); }
+__device__ __forceinline__ V3 leg_get(const V3& a, int leg) { return v3(leg_get(a.x, leg), leg_get(a.y, leg), leg_get(a.z, leg)); }
 __device__ __forceinline__ void st2(double* p, double a, double b) { *reinterpret_cast<double2*>(p) = make_double2(a, b); }
 
 // One lane of one instance.  `i` indexes the SoA arrays (clamped by the caller for lanes past the batch, which compute along and
@@ -57,8 +54,9 @@ __device__ __forceinline__ void front_cycle_leg(const Params& P, const DevInputs
     // ---- this leg: kinematics and Newton-Euler with nu_dot = 0 (front_dynamics, one leg)
     V3 pj[3], z[3], c[3], f[3], n[3];
     S3 Iw[3];
-    V3 mr = v3(0, 0, 0), mvrel = v3(0, 0, 0), ftot = v3(0, 0, 0), ntot = v3(0, 0, 0);
-    double Ibxx = 0.0, Ibyy = 0.0, Ibzz = 0.0, Ibxy = 0.0, Ibxz = 0.0, Ibyz = 0.0;
+    // what the whole-robot sums take from each link (summed below in the thread-per-instance kernel's order: link by link)
+    V3 xdv[3], xcr[3];
+    double xI[3][6];
     M3 Rp = R0;
     V3 pp = v3(0, 0, 0), vp = v0, ap = v3(0, 0, 0), wp = w0, alp = v3(0, 0, 0);
 #pragma unroll
@@ -82,19 +80,17 @@ __device__ __forceinline__ void front_cycle_leg(const Params& P, const DevInputs
         const V3 ac = aj + cross(alk, rho) + cross(wk, wxr);
         Iw[k] = rotate_inertia(Rk, kLinkInertia[leg][k]);
         const double m = kLinkMass[leg][k];
-        mr = mr + m * c[k];
-        mvrel = mvrel + m * (vc - v0);
+        xdv[k] = vc - v0;
         const double r2 = dot(c[k], c[k]);
-        Ibxx += Iw[k].xx + m * (r2 - c[k].x * c[k].x);
-        Ibyy += Iw[k].yy + m * (r2 - c[k].y * c[k].y);
-        Ibzz += Iw[k].zz + m * (r2 - c[k].z * c[k].z);
-        Ibxy += Iw[k].xy - m * c[k].x * c[k].y;
-        Ibxz += Iw[k].xz - m * c[k].x * c[k].z;
-        Ibyz += Iw[k].yz - m * c[k].y * c[k].z;
+        xI[k][0] = Iw[k].xx + m * (r2 - c[k].x * c[k].x);
+        xI[k][1] = Iw[k].yy + m * (r2 - c[k].y * c[k].y);
+        xI[k][2] = Iw[k].zz + m * (r2 - c[k].z * c[k].z);
+        xI[k][3] = Iw[k].xy - m * c[k].x * c[k].y;
+        xI[k][4] = Iw[k].xz - m * c[k].x * c[k].z;
+        xI[k][5] = Iw[k].yz - m * c[k].y * c[k].z;
         f[k] = m * (ac - grav);
         n[k] = mul(Iw[k], alk) + cross(wk, mul(Iw[k], wk));
-        ftot = ftot + f[k];
-        ntot = ntot + n[k] + cross(c[k], f[k]);
+        xcr[k] = cross(c[k], f[k]);
         Rp = Rk; pp = pj[k]; vp = vj; ap = aj; wp = wk; alp = alk;
     }
     // foot frame (fixed to the lower leg) and the foot's Jacobian with respect to the leg's joints
@@ -138,16 +134,31 @@ __device__ __forceinline__ void front_cycle_leg(const Params& P, const DevInputs
         }
     }
 
-    // ---- whole-robot sums: the four legs, then the base body (body + bodytext lumped, CoM at the base origin)
-    mr = leg_sum(mr); mvrel = leg_sum(mvrel);
-    ftot = leg_sum(ftot); ntot = leg_sum(ntot);
-    Ibxx = leg_sum(Ibxx); Ibyy = leg_sum(Ibyy); Ibzz = leg_sum(Ibzz); Ibxy = leg_sum(Ibxy); Ibxz = leg_sum(Ibxz); Ibyz = leg_sum(Ibyz);
+    // ---- whole-robot sums: the base body (body + bodytext lumped, CoM at the base origin), then link by link, leg after leg --
+    // the same chain of additions as front_dynamics: every lane fetches every link's operands from the lane that owns it
+    V3 mr = v3(0, 0, 0), mvrel = v3(0, 0, 0), ftot, ntot;
+    double Ibxx, Ibyy, Ibzz, Ibxy, Ibxz, Ibyz;
     {
         const double Ib6[6] = {kBaseInertia[0], kBaseInertia[1], kBaseInertia[2], 0.0, 0.0, 0.0};
         const S3 Ibw = rotate_inertia(R0, Ib6);
-        Ibxx += Ibw.xx; Ibyy += Ibw.yy; Ibzz += Ibw.zz; Ibxy += Ibw.xy; Ibxz += Ibw.xz; Ibyz += Ibw.yz;
-        ftot = ftot + (-kBaseMass) * grav;
-        ntot = ntot + cross(w0, mul(Ibw, w0));
+        Ibxx = Ibw.xx; Ibyy = Ibw.yy; Ibzz = Ibw.zz; Ibxy = Ibw.xy; Ibxz = Ibw.xz; Ibyz = Ibw.yz;
+        ftot = (-kBaseMass) * grav;
+        ntot = cross(w0, mul(Ibw, w0));
+    }
+#pragma unroll
+    for (int src = 0; src < 4; src++) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const double m = kLinkMass[src][k];
+            const V3 cc = leg_get(c[k], src), dd = leg_get(xdv[k], src), ff = leg_get(f[k], src), nn = leg_get(n[k], src),
+                     cr = leg_get(xcr[k], src);
+            mr = mr + m * cc;
+            mvrel = mvrel + m * dd;
+            Ibxx += leg_get(xI[k][0], src); Ibyy += leg_get(xI[k][1], src); Ibzz += leg_get(xI[k][2], src);
+            Ibxy += leg_get(xI[k][3], src); Ibxz += leg_get(xI[k][4], src); Ibyz += leg_get(xI[k][5], src);
+            ftot = ftot + ff;
+            ntot = ntot + nn + cr;
+        }
     }
     const double mtot = kTotalMass;
     double Mb[36];
@@ -177,7 +188,6 @@ __device__ __forceinline__ void front_cycle_leg(const Params& P, const DevInputs
     for (int k = 0; k < 36; k++) Lc[k] = Mb[k];
     chol6(Lc);
     double P3[6][3];
-    double pv[6] = {0, 0, 0, 0, 0, 0};
 #pragma unroll
     for (int j = 0; j < 3; j++) {
         double col[6];
@@ -185,10 +195,24 @@ __device__ __forceinline__ void front_cycle_leg(const Params& P, const DevInputs
         for (int k = 0; k < 6; k++) col[k] = Mbj3[k][j];
         chol6_solve(Lc, col);
 #pragma unroll
-        for (int k = 0; k < 6; k++) { P3[k][j] = col[k]; pv[k] += col[k] * qd3[j]; }
+        for (int k = 0; k < 6; k++) P3[k][j] = col[k];
+    }
+    // P dq_j, accumulated in DoF order (the four rolls, then pitch and knee leg by leg) like front_cycle's column loop
+    double pv[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int src = 0; src < 4; src++) {
+        const double qd = leg_get(qd3[0], src);
+#pragma unroll
+        for (int k = 0; k < 6; k++) pv[k] += leg_get(P3[k][0], src) * qd;
     }
 #pragma unroll
-    for (int k = 0; k < 6; k++) pv[k] = leg_sum(pv[k]);          // P dq_j
+    for (int src = 0; src < 4; src++)
+#pragma unroll
+        for (int j = 1; j < 3; j++) {
+            const double qd = leg_get(qd3[j], src);
+#pragma unroll
+            for (int k = 0; k < 6; k++) pv[k] += leg_get(P3[k][j], src) * qd;
+        }
     V3 u3;                                            // first three entries of T_inv_dot dq (main.cpp:565-566, 648, 658)
     {
         const V3 mdr = mtot * xbcd;
@@ -200,26 +224,6 @@ __device__ __forceinline__ void front_cycle_leg(const Params& P, const DevInputs
         const V3 zl = v3(zz[0], zz[1], zz[2]), za = v3(zz[3], zz[4], zz[5]);
         const V3 dJs = (-1.0) * cross(xbcd, pva) - (zl - cross(xbc, za));
         u3 = cross(xbcd, w0) - dJs;
-    }
-    // Mc = Xi' Mb Xi  (MassMatrixCOM[0:6,0:6], main.cpp:645)
-    double Mc[36];
-    {
-        double MX[36];
-        const double S[9] = {0, -xbc.z, xbc.y, xbc.z, 0, -xbc.x, -xbc.y, xbc.x, 0};
-#pragma unroll
-        for (int r = 0; r < 6; r++)
-#pragma unroll
-            for (int cc = 0; cc < 3; cc++) {
-                MX[r * 6 + cc] = Mb[r * 6 + cc];
-                MX[r * 6 + 3 + cc] = Mb[r * 6 + 3 + cc] + Mb[r * 6] * S[cc] + Mb[r * 6 + 1] * S[3 + cc] + Mb[r * 6 + 2] * S[6 + cc];
-            }
-#pragma unroll
-        for (int cc = 0; cc < 6; cc++) {
-            Mc[0 * 6 + cc] = MX[0 * 6 + cc]; Mc[1 * 6 + cc] = MX[1 * 6 + cc]; Mc[2 * 6 + cc] = MX[2 * 6 + cc];
-#pragma unroll
-            for (int r = 0; r < 3; r++)
-                Mc[(3 + r) * 6 + cc] = MX[(3 + r) * 6 + cc] + S[0 * 3 + r] * MX[0 * 6 + cc] + S[1 * 3 + r] * MX[1 * 6 + cc] + S[2 * 3 + r] * MX[2 * 6 + cc];
-        }
     }
     // BiasCOM = T^-T (h + M T_inv_dot dq): base rows (every lane), this leg's joint rows
     double hb2[6], hc6[6], hcj[3];
@@ -289,10 +293,51 @@ __device__ __forceinline__ void front_cycle_leg(const Params& P, const DevInputs
     const bool swing = (mode == MODE_SWING_BR_FL && (sf == 0 || sf == 2)) || (mode == MODE_SWING_BL_FR && (sf == 1 || sf == 3));
     V3 fw = v3(0, 0, 0);
     if (!swing) fw = mul(footR, v3(LD1(in.foot_force, 3 * sf), LD1(in.foot_force, 3 * sf + 1), LD1(in.foot_force, 3 * sf + 2)));
+    // every foot's lever arm and force, by stacked foot, so that J' Fgrf (and J'J below) run over the twelve rows in order in every lane
+    V3 rcA[4], fwA[4];
+#pragma unroll
+    for (int sfi = 0; sfi < 4; sfi++) {
+        const int lg = (sfi < 2) ? 1 - sfi : sfi;      // kFootLeg
+        rcA[sfi] = leg_get(rc, lg);
+        fwA[sfi] = leg_get(fw, lg);
+    }
     double fc6[6];
 #pragma unroll
-    for (int a = 0; a < 6; a++) fc6[a] = leg_sum(Jc3[0][a] * fw.x + Jc3[1][a] * fw.y + Jc3[2][a] * fw.z);
+    for (int a = 0; a < 6; a++) {
+        double fc = 0.0;
+#pragma unroll
+        for (int sfi = 0; sfi < 4; sfi++) {
+            const V3 r = rcA[sfi];
+            const double nSa[9] = {0, r.z, -r.y, -r.z, 0, r.x, r.y, -r.x, 0};
+#pragma unroll
+            for (int ax = 0; ax < 3; ax++) {
+                const double j = (a < 3) ? ((ax == a) ? 1.0 : 0.0) : nSa[ax * 3 + (a - 3)];
+                fc += j * comp(fwA[sfi], ax);
+            }
+        }
+        fc6[a] = fc;
+    }
 
+    // Mc = Xi' Mb Xi  (MassMatrixCOM[0:6,0:6], main.cpp:645) -- formed here, after the blocks above have released their registers
+    double Mc[36];
+    {
+        double MX[36];
+        const double S[9] = {0, -xbc.z, xbc.y, xbc.z, 0, -xbc.x, -xbc.y, xbc.x, 0};
+#pragma unroll
+        for (int r = 0; r < 6; r++)
+#pragma unroll
+            for (int cc = 0; cc < 3; cc++) {
+                MX[r * 6 + cc] = Mb[r * 6 + cc];
+                MX[r * 6 + 3 + cc] = Mb[r * 6 + 3 + cc] + Mb[r * 6] * S[cc] + Mb[r * 6 + 1] * S[3 + cc] + Mb[r * 6 + 2] * S[6 + cc];
+            }
+#pragma unroll
+        for (int cc = 0; cc < 6; cc++) {
+            Mc[0 * 6 + cc] = MX[0 * 6 + cc]; Mc[1 * 6 + cc] = MX[1 * 6 + cc]; Mc[2 * 6 + cc] = MX[2 * 6 + cc];
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+                Mc[(3 + r) * 6 + cc] = MX[(3 + r) * 6 + cc] + S[0 * 3 + r] * MX[0 * 6 + cc] + S[1 * 3 + r] * MX[1 * 6 + cc] + S[2 * 3 + r] * MX[2 * 6 + cc];
+        }
+    }
     // ---- estimate() (main.cpp:692-725), every lane the same arithmetic; lane 0 stores
     const double comv6[6] = {comv.x, comv.y, comv.z, w0.x, w0.y, w0.z};
     double west[6], rho6[6], dd6[6];
@@ -358,7 +403,18 @@ __device__ __forceinline__ void front_cycle_leg(const Params& P, const DevInputs
         for (int a = 0; a < 6; a++)
 #pragma unroll
             for (int b = 0; b <= a; b++) {
-                const double g = leg_sum(Jc3[0][a] * Jc3[0][b] + Jc3[1][a] * Jc3[1][b] + Jc3[2][a] * Jc3[2][b]);
+                double g = 0.0;
+#pragma unroll
+                for (int sfi = 0; sfi < 4; sfi++) {
+                    const V3 r = rcA[sfi];
+                    const double nSa[9] = {0, r.z, -r.y, -r.z, 0, r.x, r.y, -r.x, 0};
+#pragma unroll
+                    for (int ax = 0; ax < 3; ax++) {
+                        const double ja = (a < 3) ? ((ax == a) ? 1.0 : 0.0) : nSa[ax * 3 + (a - 3)];
+                        const double jb = (b < 3) ? ((ax == b) ? 1.0 : 0.0) : nSa[ax * 3 + (b - 3)];
+                        g += ja * jb;
+                    }
+                }
                 G[a * 6 + b] = g; G[b * 6 + a] = g;
             }
         chol6(G);
