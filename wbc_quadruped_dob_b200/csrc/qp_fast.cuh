@@ -412,7 +412,7 @@ __device__ __noinline__ int step_and_move(double dA, double dB, double exbA, dou
     double* xs = wbc_smem + sl::OFF_XC;
     const double* sp = wbc_smem + sl::OFF_SP;
     const double d1 = sp[4], d2 = sp[5], stpmax = sp[6];
-    double xcA = xs[l < NMAIN ? l : 0], xcB = (l < nic) ? xs[NMAIN + l] : 0.0;
+    double xcA = (l < NMAIN) ? xs[l] : 0.0, xcB = (l < nic) ? xs[NMAIN + l] : 0.0;      // (lanes past the vector read nothing: lane 0 rewrites xs[0] below)
     double stp, a0 = 0.0, a1 = 0.0, a2 = 0.0;
     bool needact;
     int addcnt;
