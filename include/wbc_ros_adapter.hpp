@@ -13,9 +13,10 @@
 //   publish_cmd: torque reorder              main.cpp:768-779      JointMap::command_order
 //
 // The part above the message types is plain C++ (this image has no ROS): it is what tests/cpp/ros_adapter_host.cpp exercises.
-// The node itself (subscribers, publishers, the 400 Hz loop) is the block under WBC_WITH_ROS at the end; it needs roscpp,
-// sensor_msgs, gazebo_msgs, std_msgs, geometry_msgs and has NOT been compiled here -- it is the wiring a maintainer would start
-// from, INTEGRATION.md section 5 walks through it.
+// The node itself (subscribers, publishers, one step of the control loop) is the block under WBC_WITH_ROS at the end; it needs
+// roscpp, sensor_msgs, gazebo_msgs, std_msgs, geometry_msgs.  It has NOT been compiled against ROS here; tests/cpp/ros_node_host.cpp
+// compiles and runs it against a minimal stand-in for those headers (tests/cpp/mock_ros): messages in on the reference's topics,
+// command and estimate out, checked against DogCtrl driven directly.  INTEGRATION.md section 5 walks through it.
 //
 // tf is not vendored in the reference: quaternion -> matrix and getRPY below restate tf/LinearMath/Matrix3x3.h (setRotation,
 // getEulerYPR solution 1) from its published source; SURVEY.md Appendix D records the convention (fixed-axis XYZ,
@@ -173,7 +174,7 @@ struct ContactSample {
 
 #ifdef WBC_WITH_ROS
 // ---------------------------------------------------------------------------------------------------------------------------
-// The node (not compiled in this repository's image: no ROS).  One DogCtrl, the reference's topics, the reference's loop rate.
+// The node (this repository's image has no ROS: exercised against tests/cpp/mock_ros only).  One DogCtrl, the reference's topics.
 #include <gazebo_msgs/ContactsState.h>
 #include <gazebo_msgs/ModelStates.h>
 #include <geometry_msgs/WrenchStamped.h>
@@ -193,10 +194,10 @@ public:
         typedef Topics T;
         joint_sub_ = nh_.subscribe(T::joint_states(), 1, &DogbotNode::joint_cb, this);
         model_sub_ = nh_.subscribe(T::model_states(), 1, &DogbotNode::model_cb, this);
-        bl_sub_ = nh_.subscribe<gazebo_msgs::ContactsState>(T::contact_back_left(), 1, boost::bind(&DogbotNode::contact_cb, this, _1, 1));
-        fl_sub_ = nh_.subscribe<gazebo_msgs::ContactsState>(T::contact_front_left(), 1, boost::bind(&DogbotNode::contact_cb, this, _1, 2));
-        br_sub_ = nh_.subscribe<gazebo_msgs::ContactsState>(T::contact_back_right(), 1, boost::bind(&DogbotNode::contact_cb, this, _1, 0));
-        fr_sub_ = nh_.subscribe<gazebo_msgs::ContactsState>(T::contact_front_right(), 1, boost::bind(&DogbotNode::contact_cb, this, _1, 3));
+        bl_sub_ = nh_.subscribe(T::contact_back_left(), 1, &DogbotNode::eebl_cb, this);        // main.cpp:268-271
+        fl_sub_ = nh_.subscribe(T::contact_front_left(), 1, &DogbotNode::eefl_cb, this);
+        br_sub_ = nh_.subscribe(T::contact_back_right(), 1, &DogbotNode::eebr_cb, this);
+        fr_sub_ = nh_.subscribe(T::contact_front_right(), 1, &DogbotNode::eefr_cb, this);
         cmd_pub_ = nh_.advertise<std_msgs::Float64MultiArray>(T::command(), 1);
         est_pub_ = nh_.advertise<geometry_msgs::WrenchStamped>(T::estimation(), 1);
     }
@@ -244,6 +245,11 @@ private:
             return;
         }
     }
+    // stacked foot order BR, BL, FL, FR (main.cpp:1022-1026)
+    void eebr_cb(const gazebo_msgs::ContactsStateConstPtr& m) { contact_cb(m, 0); }
+    void eebl_cb(const gazebo_msgs::ContactsStateConstPtr& m) { contact_cb(m, 1); }
+    void eefl_cb(const gazebo_msgs::ContactsStateConstPtr& m) { contact_cb(m, 2); }
+    void eefr_cb(const gazebo_msgs::ContactsStateConstPtr& m) { contact_cb(m, 3); }
     void contact_cb(const gazebo_msgs::ContactsStateConstPtr& m, int stacked_foot)
     {
         double f[3] = {0.0, 0.0, 0.0};

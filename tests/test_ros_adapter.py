@@ -93,3 +93,38 @@ def test_model_state_gives_tf_rotation_and_fixed_axis_rpy(exe):
 def test_contact_sample_keeps_the_last_force_when_the_message_is_empty(exe):
     out = subprocess.run([exe, "contact"], capture_output=True, text=True, check=True).stdout.strip().split("\n")
     assert out == ["0 0 0 0", "1 1 2 30", "0 1 2 30", "1 -1 0.5 25"]
+
+
+# ---- the node glue (WBC_WITH_ROS) against the stand-in ROS headers of tests/cpp/mock_ros
+NODE_SRC = os.path.join(util.ROOT, "tests", "cpp", "ros_node_host.cpp")
+NODE_EXE = os.path.join(util.ROOT, "tests", "cpp", "ros_node_host.bin")
+
+
+@pytest.fixture(scope="module")
+def node_exe():
+    from wbc_quadruped_dob_b200 import build as B
+    lib = B.build()
+    inc = os.path.join(util.ROOT, "include")
+    deps = [NODE_SRC, os.path.join(inc, "wbc_ros_adapter.hpp"), os.path.join(inc, "wbc_dogctrl.hpp"), os.path.join(inc, "wbc_b200.h")]
+    if not os.path.exists(NODE_EXE) or any(os.path.getmtime(d) > os.path.getmtime(NODE_EXE) for d in deps):
+        libdir = os.path.dirname(lib)
+        subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-I" + inc, "-I" + os.path.join(util.ROOT, "tests", "cpp", "mock_ros"),
+                        NODE_SRC, "-o", NODE_EXE, "-L" + libdir, "-lwbc_b200", "-Wl,-rpath," + libdir], check=True)
+    return NODE_EXE
+
+
+def test_node_glue_compiles_against_the_stand_in_ros_headers_and_refuses_without_gpu(node_exe):
+    import torch
+    out = subprocess.run([node_exe, "probe"], capture_output=True, text=True, check=True).stdout.strip()
+    assert out == ("ok" if torch.cuda.is_available() else "nodev")
+
+
+@pytest.mark.gpu
+def test_node_step_publishes_the_controllers_torques_in_publish_cmd_order(node_exe):
+    """Messages in on the reference's topics (joint_states in Gazebo's alphabetical order, model_states with an unnormalised
+    quaternion, four contact sensors), one stance step, and the published command is the torque vector of a DogCtrl driven
+    directly with the same numbers, in publish_cmd's reverse message order (main.cpp:768-779); estimation_ee carries w."""
+    out = subprocess.run([node_exe, "run"], capture_output=True, text=True, check=True).stdout.split()
+    vals = dict(zip(out[0::2], out[1::2]))
+    assert float(vals["cmd_err"]) == 0.0 and float(vals["est_err"]) == 0.0, vals
+    assert int(vals["published"]) == 1 and int(vals["status"]) == 0 and float(vals["tau_max"]) > 0.1
