@@ -232,7 +232,8 @@ int wbc_plant_dynamics_step(wbc_ctx* ctx, int n, const wbc_plant_state* st, cons
 /* Device-side timing of the last wbc_cycle on this ctx (CUDA events on the launching stream), ms. */
 int wbc_last_timing(wbc_ctx* ctx, float* front_ms, float* solve_ms);
 /* Per-instance solve duration of the last wbc_cycle on this ctx, in SM clock cycles (clock64 around the instance's
- * set-up + DENSE-AUL solve + torque map; the same figure that orders the next cycle's longest-first dispatch).
+ * set-up + DENSE-AUL solve + torque map; the figure that orders the next cycle's longest-first dispatch -- except for small batches
+ * on the one-warp-per-solve kernel with express lanes, where the order goes by the solve's flop count).
  * cycles [n], host pointer; synchronises the ctx's last launch stream work via a blocking copy. */
 int wbc_last_solve_cycles(wbc_ctx* ctx, int n, unsigned long long* cycles);
 /* Number of kernels launched by the last wbc_cycle / wbc_qp_solve. */

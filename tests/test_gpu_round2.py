@@ -240,3 +240,34 @@ def test_leg_parallel_front_kernel_matches_the_thread_per_instance_one(n, terrai
         assert np.array_equal(o1["status"] == 0, o2["status"] == 0)
         # the solver amplifies last-bit differences of its input on the odd instance: 1e-8 seen in 1003
         assert np.max(np.abs(o1["tau"][:, ok] - o2["tau"][:, ok]) / (1.0 + np.abs(o2["tau"][:, ok]))) < 1e-7
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [2048, 2049, 4096, 5003])
+def test_express_lanes_change_no_result_and_lose_no_instance(n):
+    """Small batches run the one-warp-per-solve kernel with twelve warps per SM and express lanes (a few SM pairs keep four warps and
+    serve the head of the longest-first order; the dispatch cost is then the solve's flop count).  Who solves an instance, and
+    when, must not show in the results: bit-identical to the run without lanes (WBC_EXPRESS=0) over three consecutive cycles
+    (index order, then two longest-first orders), every instance solved exactly once."""
+    import os
+    sc = S.make(n, mode_mix=(0.5, 0.25, 0.25), pushes=True, terrain=False, seed=91)
+    res = {}
+    for x in ("0", "9,4,1", "5,2,1.5"):
+        os.environ["WBC_EXPRESS"] = x
+        try:
+            b = api.WbcBatch(max_batch=n)
+        finally:
+            del os.environ["WBC_EXPRESS"]
+        b.set_observer_state(sc["obs_yd"], sc["obs_yw"])
+        outs = []
+        for cyc in range(3):
+            o = b.cycle(sc, want=("x", "status", "qp_info"))
+            assert (b.last_solve_cycles(n) > 0).all()          # every instance was timed, i.e. solved, this cycle
+            outs.append(o)
+        res[x] = outs
+        b.close()
+    for x in ("9,4,1", "5,2,1.5"):
+        for a, r in zip(res[x], res["0"]):
+            for k in ("tau", "w", "x", "status"):
+                assert np.array_equal(a[k], r[k]), (x, k)
+            assert np.array_equal(a["qp_info"][:6], r["qp_info"][:6])

@@ -49,7 +49,9 @@ struct DispatchOrder {
     const int* hist;          // [ORD_NB] histogram of bucket(cost) over the n instances
     int* cursor;              // [ORD_NB] zeroed
     int* order;               // [n] out: instance index per ticket
+    int* lanes;               // express-lane block of the solve launch that follows (ExpressLanes below), zeroed here; may be NULL
 };
+constexpr int LANES_INTS = 2 + 256;           // head ticket counter, tail ticket counter, arrivals per SM
 __device__ __forceinline__ int cost_bucket(unsigned cost) { const unsigned b = cost >> 6; return b < ORD_NB ? (int)b : ORD_NB - 1; }
 
 // (stage_reset: the staged solver's queue block and rings, reset here for the solve launch that follows; see StageCtl below)
@@ -65,6 +67,10 @@ __global__ void __launch_bounds__(64) wbc_front_kernel(Params P, DevInputs in, F
         const long nth = (long)gridDim.x * blockDim.x;
         for (long k = i; k < sr.nctl; k += nth) sr.ctl[k] = (k == sr.free_tail_index || k == sr.free_avail_index) ? sr.nslots : 0;
         for (long k = i; k < 3L * sr.rsize; k += nth) sr.ring[k] = (k >= 2L * sr.rsize && k - 2L * sr.rsize < sr.nslots) ? (int)(k - 2L * sr.rsize) : -1;
+    }
+    if (ord.lanes) {
+        const long nth = (long)gridDim.x * blockDim.x;
+        for (long k = i; k < LANES_INTS; k += nth) ord.lanes[k] = 0;
     }
     if (ord.cost) {
         // base[b] = number of instances in costlier buckets: lane l scans buckets 255-8l .. 248-8l
@@ -101,6 +107,10 @@ __global__ void __launch_bounds__(128) wbc_front_leg_kernel(Params P, DevInputs 
         const long nth = (long)gridDim.x * blockDim.x;
         for (long k = t; k < sr.nctl; k += nth) sr.ctl[k] = (k == sr.free_tail_index || k == sr.free_avail_index) ? sr.nslots : 0;
         for (long k = t; k < 3L * sr.rsize; k += nth) sr.ring[k] = (k >= 2L * sr.rsize && k - 2L * sr.rsize < sr.nslots) ? (int)(k - 2L * sr.rsize) : -1;
+    }
+    if (ord.lanes) {
+        const long nth = (long)gridDim.x * blockDim.x;
+        for (long k = t; k < LANES_INTS; k += nth) ord.lanes[k] = 0;
     }
     if (ord.cost) {
         if (threadIdx.x < 32) {
@@ -152,23 +162,65 @@ __device__ __forceinline__ int next_instance(int* queue)
     return __shfl_sync(0xffffffffu, i, 0);
 }
 
+// Express lanes.  A batch of a few thousand instances is two or three solves per resident warp, and its step ends with its LONGEST
+// solve: measured at 4 096 standing instances with twelve warps per SM, the sum of all solve latencies is 2.62 ms per warp but the
+// longest solve alone takes 3.28 ms (with eight warps per SM: 2.88 and 2.45 -- which is why eight used to win).  A solve runs
+// almost twice as fast on an SM it shares with three warps instead of eleven.  So a few SM pairs keep only `keep` of their warps
+// (the others leave at once), and those express warps serve the `head` longest solves of the dispatch order, which everybody else
+// skips; either side continues in the other's range when its own is used up, so no ticket is left behind.
+struct ExpressLanes {
+    int* lanes;        // [0] head tickets drawn, [1] tail tickets drawn, [2 + smid] arrivals on SM smid
+    int head;          // tickets [0, head) are the express range
+    int period, keep;  // every period-th SM pair is express and keeps `keep` warps per SM; period 0: off
+    unsigned* cycles;  // [n] the solve's duration (2^10 cycles) when the dispatch cost is not the duration (express lanes on)
+};
+__device__ __forceinline__ int next_instance_lanes(const ExpressLanes& xl, bool express, int n)
+{
+    int t = 0;
+    if ((threadIdx.x & 31) == 0) {
+        if (express) {
+            t = atomicAdd(xl.lanes, 1);
+            if (t >= xl.head) t = xl.head + atomicAdd(xl.lanes + 1, 1);
+        } else {
+            t = xl.head + atomicAdd(xl.lanes + 1, 1);
+            if (t >= n) { t = atomicAdd(xl.lanes, 1); if (t >= xl.head) t = n; }
+        }
+    }
+    return __shfl_sync(0xffffffffu, t, 0);
+}
+
 __global__ void __launch_bounds__(SOLVE_T) wbc_solve_kernel(Params P, int n, const double* __restrict__ recs, SolveOut out,
                                                             double* __restrict__ scratch_base, double* __restrict__ kkt_base, int* __restrict__ queue,
                                                             const int* __restrict__ order, unsigned* __restrict__ cost,
-                                                            int* __restrict__ hist_next)
+                                                            int* __restrict__ hist_next, ExpressLanes xl)
 {
     Work w;
     w.g = scratch_base + (long)blockIdx.x * gl::TOTAL;
     w.kkt = kkt_base + (long)blockIdx.x * gl::KKT_DOUBLES;
     w.sm = nullptr;
     const WarpEx ex;
+    // Express lanes (small batches): on every `period`-th SM pair only the first `keep` warps to arrive stay, and they serve the
+    // head of the longest-first order; everybody else starts behind the head.  See ExpressLanes.
+    bool express = false;
+    if (xl.period > 0) {
+        int verdict = 0;                                  // 0 regular, 1 express, 2 leave
+        if (ex.lane() == 0) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            if (((smid >> 1) % (unsigned)xl.period) == (unsigned)(xl.period >> 1) && smid < 256u)
+                verdict = atomicAdd(xl.lanes + 2 + smid, 1) < xl.keep ? 1 : 2;
+        }
+        verdict = __shfl_sync(0xffffffffu, verdict, 0);
+        if (verdict == 2) return;
+        express = verdict == 1;
+    }
     Settings cfg;
     cfg.epsx = P.qp_epsx; cfg.rho = P.qp_rho; cfg.outerits = P.qp_outerits; cfg.kkt_mode = P.qp_literal_kkt ? 0 : 1;
     // every value later read from shared memory is finite (out-of-range lanes read neighbours and drop the result)
     for (int k = ex.lane(); k < sl::TOTAL; k += SOLVE_T) WBC_SM(w)[k] = 0.0;
     ex.sync();
     for (;;) {
-        const int ticket = next_instance(queue);
+        const int ticket = xl.period > 0 ? next_instance_lanes(xl, express, n) : next_instance(queue);
         if (ticket >= n) break;
         const int i = order ? order[ticket] : ticket;
         const long long t0 = clock64();
@@ -233,7 +285,11 @@ __global__ void __launch_bounds__(SOLVE_T) wbc_solve_kernel(Params P, int n, con
         if (ex.lane() == 0) {
             write_info(st, i, out.ld, out.status, out.qp_info, out.qp_flops);
             const unsigned long long dt = (unsigned long long)(clock64() - t0) >> 10;
-            const unsigned cu = dt > 0xffffffffull ? 0xffffffffu : (unsigned)dt;
+            unsigned cu = dt > 0xffffffffull ? 0xffffffffu : (unsigned)dt;
+            // With express lanes a solve's duration depends on where it ran (an express warp is almost twice as fast), and a cost
+            // that does would make the order oscillate: rank by the solve's instrumented flop count instead (correlation with the
+            // duration 0.97; the literal multiplier update, which the count does not see, is a flat surcharge).  Same unit: 2^10 cycles.
+            if (xl.period > 0) { xl.cycles[i] = cu; cu = (unsigned)(st.flops * (1.0 / 512.0)) + ((st.flags & 8) ? 2000u : 0u); }
             cost[i] = cu;
             atomicAdd(hist_next + cost_bucket(cu), 1);
         }
@@ -659,6 +715,11 @@ struct wbc_ctx {
     int sq_rsize;
     int staged;          // 0: wbc_solve_kernel, 1: wbc_solve_staged_kernel, 2 (default): by batch size (staged from staged_min_n instances)
     int staged_min_n;
+    unsigned* cycles;    // [max_batch] solve durations of the last cycle when express lanes were on (the cost array then ranks by flop count)
+    int cycles_valid;
+    int* lanes;          // [LANES_INTS] express-lane counters of the solve launch (zeroed by the front kernel)
+    int xl_period, xl_keep, xl_min_n;    // express lanes: every xl_period-th SM pair keeps xl_keep warps per SM; batches from xl_min_n instances
+    double xl_head_mult; // express range of the dispatch order = xl_head_mult x the number of express warps
     int front_leg;       // 1 (default): wbc_front_leg_kernel, four lanes per instance; 0: wbc_front_kernel, a thread per instance (WBC_FRONT=thread)
     int last_staged;     // which kernel the last wbc_cycle launched
     int m_period, m_group;   // SM roles of the staged solver
@@ -716,7 +777,7 @@ int wbc_destroy(wbc_ctx* c)
 {
     if (!c) return WBC_OK;
     cudaSetDevice(c->device);
-    cudaFree(c->recs); cudaFree(c->yd); cudaFree(c->yw); cudaFree(c->yg); cudaFree(c->w_dev); cudaFree(c->tau_prev); cudaFree(c->scratch); cudaFree(c->kkt); cudaFree(c->sq_ctl); cudaFree(c->sq_ring); cudaFree(c->prof); cudaFree(c->queue); cudaFree(c->cost); cudaFree(c->order);
+    cudaFree(c->recs); cudaFree(c->yd); cudaFree(c->yw); cudaFree(c->yg); cudaFree(c->w_dev); cudaFree(c->tau_prev); cudaFree(c->scratch); cudaFree(c->kkt); cudaFree(c->sq_ctl); cudaFree(c->sq_ring); cudaFree(c->prof); cudaFree(c->queue); cudaFree(c->lanes); cudaFree(c->cost); cudaFree(c->cycles); cudaFree(c->order);
     cudaFree(c->traj_dur); cudaFree(c->traj_nodes); cudaFree(c->traj_s); cudaFree(c->traj_t);
     cudaFree(c->d_in); cudaFree(c->d_out); cudaFree(c->d_mode); cudaFree(c->d_iout); cudaFree(c->d_dense);
     if (c->h_pin) cudaFreeHost(c->h_pin);
@@ -785,6 +846,16 @@ int wbc_create(wbc_ctx** out, int device, int max_batch, const wbc_params* param
     if (const char* ev = getenv("WBC_SOLVER")) c->staged = strcmp(ev, "staged") == 0 ? 1 : (strcmp(ev, "mono") == 0 ? 0 : 2);
     if (const char* ev = getenv("WBC_STAGED_MIN_N")) c->staged_min_n = atoi(ev);
     c->front_leg = 1;
+    // express lanes (ExpressLanes): WBC_EXPRESS = "period,keep,head multiplier,min n"; period 0 switches them off
+    c->xl_period = 9; c->xl_keep = 4; c->xl_head_mult = 1.0; c->xl_min_n = 2048;
+    if (const char* ev = getenv("WBC_EXPRESS")) {
+        int a = 9, b = 4, d = 2048; double m = 2.0;
+        const int got = sscanf(ev, "%d,%d,%lf,%d", &a, &b, &m, &d);
+        if (got >= 1 && a >= 0 && a < 75) c->xl_period = a;
+        if (got >= 2 && b >= 1 && b <= 12) c->xl_keep = b;
+        if (got >= 3 && m >= 0.0) c->xl_head_mult = m;
+        if (got >= 4 && d >= 0) c->xl_min_n = d;
+    }
     if (const char* ev = getenv("WBC_FRONT")) c->front_leg = strcmp(ev, "thread") != 0;
     if (const char* ev = getenv("WBC_STAGE_ROLES")) {        // "nS,nP/den"
         int a = 0, b = 2, d = 5;
@@ -804,8 +875,11 @@ int wbc_create(wbc_ctx** out, int device, int max_batch, const wbc_params* param
     TRY(cudaMalloc(&c->sq_ring, (size_t)3 * c->sq_rsize * sizeof(int)));
     if (getenv("WBC_STAGE_PROF")) { TRY(cudaMalloc(&c->prof, (size_t)nteams * 12 * sizeof(unsigned long long))); TRY(cudaMemset(c->prof, 0, (size_t)nteams * 12 * sizeof(unsigned long long))); }
     TRY(cudaMalloc(&c->queue, (1 + 3 * ORD_NB) * sizeof(int)));
+    TRY(cudaMalloc(&c->lanes, LANES_INTS * sizeof(int)));
+    TRY(cudaMemset(c->lanes, 0, LANES_INTS * sizeof(int)));
     TRY(cudaMemset(c->queue, 0, (1 + 3 * ORD_NB) * sizeof(int)));
     TRY(cudaMalloc(&c->cost, nb * sizeof(unsigned)));
+    TRY(cudaMalloc(&c->cycles, nb * sizeof(unsigned)));
     TRY(cudaMalloc(&c->order, nb * sizeof(int)));
     TRY(cudaMalloc(&c->d_in, nb * (kInDoublesNoTerrain + 41) * sizeof(double)));
     TRY(cudaMalloc(&c->d_out, nb * kOutDoubles * sizeof(double)));
@@ -1041,6 +1115,10 @@ int wbc_cycle(wbc_ctx* c, int n, const wbc_inputs* in, const wbc_outputs* out, v
     const bool ordered = !(flags & WBC_FIFO_DISPATCH) && c->order_n == n && n > 1;
     DispatchOrder ord;
     ord.cost = ordered ? c->cost : nullptr; ord.hist = hist_prev; ord.cursor = counter + 1; ord.order = c->order;
+    // express lanes for the one-warp-per-solve kernel on a batch of a few solves per warp (see ExpressLanes)
+    const bool staged_sel = c->staged == 1 || (c->staged == 2 && n >= c->staged_min_n);
+    const bool express = !staged_sel && c->xl_period > 0 && !c->occ_forced && c->occ_per_sm >= 12 && n >= c->xl_min_n;
+    ord.lanes = express ? c->lanes : nullptr;
     // one memset: counter, cursors and the histogram this cycle fills (A lies just before the counter, B just after the cursors)
     CU(cudaMemsetAsync((c->hist_sel ^ 1) == 0 ? c->queue : counter, 0, (1 + 2 * ORD_NB) * sizeof(int), s));
     CU(cudaEventRecord(c->ev0, s));
@@ -1062,14 +1140,27 @@ int wbc_cycle(wbc_ctx* c, int n, const wbc_inputs* in, const wbc_outputs* out, v
         wbc_front_kernel<<<(n + fthreads - 1) / fthreads, fthreads, 0, s>>>(c->params, din, st, n, c->recs, w_ptr, w_ld, nodbg, 0, ord, sr);
     }
     CU(cudaEventRecord(c->ev1, s));
-    // Resident solver warps for this batch.  Large batches take every warp that fits (12 per SM); a batch of a few thousand is
-    // only two or three solves per warp, where the step ends with its longest solve and every solve runs slower the more
-    // warps share the SM's instruction supply: measured at 4 096 instances, 8 warps per SM beat 12 by 3 % (profiles/README.md).
+    // Resident solver warps for this batch.  Large batches take every warp that fits (12 per SM).  A batch of a few thousand is
+    // only two or three solves per warp: its step ends with its longest solve, and every solve runs slower the more warps share
+    // the SM's instruction supply.  From xl_min_n instances: 12 warps per SM with express lanes for the longest solves
+    // (ExpressLanes; 3.05 ms against 3.25 at 4 096 instances).  Below, or with the lanes switched off: 8 warps per SM, which
+    // beat a plain 12 by 3 % at 4 096 instances (profiles/README.md).
     int nblocks = c->nblocks;
     int smem = c->solve_smem;
     const bool staged = c->staged == 1 || (c->staged == 2 && n >= c->staged_min_n);
     c->last_staged = staged ? 1 : 0;
-    if (!staged && c->occ_per_sm > 8 && !c->occ_forced) {
+    ExpressLanes xl;
+    xl.lanes = c->lanes; xl.head = 0; xl.period = 0; xl.keep = c->xl_keep; xl.cycles = c->cycles;
+    c->cycles_valid = 0;
+    if (express) {
+        // every resident warp (12 per SM); the express SM pairs keep xl_keep warps per SM and serve the head of the order
+        int nexp = 0;
+        for (int sm = 0; sm < c->sm_count; sm++) nexp += ((sm >> 1) % c->xl_period) == (c->xl_period >> 1);
+        xl.period = c->xl_period;
+        c->cycles_valid = 1;
+        xl.head = (int)(c->xl_head_mult * nexp * c->xl_keep + 0.5);
+        if (xl.head > n) xl.head = n;
+    } else if (!staged && c->occ_per_sm > 8 && !c->occ_forced) {
         int per_sm = (int)((double)n / (3.4 * c->sm_count));
         per_sm = per_sm < 8 ? 8 : (per_sm > c->occ_per_sm ? c->occ_per_sm : per_sm);
         if (per_sm < c->occ_per_sm) {
@@ -1088,7 +1179,7 @@ int wbc_cycle(wbc_ctx* c, int n, const wbc_inputs* in, const wbc_outputs* out, v
                                                                       c->cost, hist_next, c->m_period, c->m_group, c->prof);
     } else {
         wbc_solve_kernel<<<nblocks, c->threads, smem, s>>>(c->params, n, c->recs, so, c->scratch, c->kkt, counter, ordered ? c->order : nullptr,
-                                                               c->cost, hist_next);
+                                                               c->cost, hist_next, xl);
     }
     CU(cudaEventRecord(c->ev2, s));
     CU(cudaGetLastError());
@@ -1309,7 +1400,7 @@ int wbc_last_solve_cycles(wbc_ctx* c, int n, unsigned long long* cycles)
     CU(cudaDeviceSynchronize());
     unsigned* h = (unsigned*)malloc((size_t)n * sizeof(unsigned));
     if (!h) return fail(WBC_ENOMEM, "out of host memory");
-    const cudaError_t e = cudaMemcpy(h, c->cost, (size_t)n * sizeof(unsigned), cudaMemcpyDeviceToHost);
+    const cudaError_t e = cudaMemcpy(h, c->cycles_valid ? c->cycles : c->cost, (size_t)n * sizeof(unsigned), cudaMemcpyDeviceToHost);
     if (e == cudaSuccess)
         for (int i = 0; i < n; i++) cycles[i] = (unsigned long long)h[i] << 10;     // stored >> 10
     free(h);
@@ -1394,7 +1485,7 @@ int wbc_debug_update(wbc_ctx* c, int n, const wbc_inputs* in, const wbc_debug* d
         FrontState st;
         st.yd = ytmp; st.yw = ytmp + 6L * n; st.yg = ytmp + 18L * n; st.ld = n; st.w3 = nullptr; st.w3_ld = 0;
         const int fthreads = front_threads(c, n);
-        wbc_front_kernel<<<(n + fthreads - 1) / fthreads, fthreads, 0, s>>>(c->params, din, st, n, rtmp, ytmp + 12L * n, n, dd, 1, DispatchOrder{nullptr, nullptr, nullptr, nullptr}, StageReset{nullptr, 0, 0, 0, nullptr, 0, 0});
+        wbc_front_kernel<<<(n + fthreads - 1) / fthreads, fthreads, 0, s>>>(c->params, din, st, n, rtmp, ytmp + 12L * n, n, dd, 1, DispatchOrder{nullptr, nullptr, nullptr, nullptr, nullptr}, StageReset{nullptr, 0, 0, 0, nullptr, 0, 0});
         e = cudaStreamSynchronize(s);
         if (e == cudaSuccess) e = cudaGetLastError();
     }
