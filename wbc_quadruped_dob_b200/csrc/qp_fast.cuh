@@ -461,12 +461,13 @@ __device__ __noinline__ void qqp_stats(int nic, double rho, double exbA, double 
     double s1 = 0.0, s2 = 0.0;
     if (l < NMAIN) {
 #pragma unroll 1
-        for (int j = l; j < NMAIN; j++) {
-            // H[l][j] read as H[j][l] (generate_ex_model writes both with the same value): the lanes then walk a row of H side by
-            // side instead of 30 rows at the same bank (that was a 16-way conflict, a third of the kernel's replays)
+        for (int j = 0; j < NMAIN; j++) {
+            // the upper triangle of row l, read as H[j][l] (generate_ex_model writes both with the same value) with every lane on
+            // the same j: the lanes walk a row of H side by side.  (Row l from its diagonal on -- lane l at H[l][l + t] or at
+            // H[l + t][l] -- puts all thirty lanes on one bank: that was a 16-way conflict, a quarter of the kernel's replays.)
             const double v = H[j * LDH + l], vv = fabs(v);
             const double k = ((double)l == v) ? 1.0 : 2.0;
-            s1 += vv * k; s2 += vv * vv * k;
+            if (j >= l) { s1 += vv * k; s2 += vv * vv * k; }
         }
 #pragma unroll 1
         for (int kk = 0; kk < nic; kk++) {
