@@ -121,3 +121,51 @@ def test_kernel_kinematics_reproduce_the_logged_link_frames(gpu_batch):
              foot_pos=np.abs(fp - ref["foot_pos"]).max(), foot_vel=np.abs(fv - ref["foot_vel"]).max())
     print("kernel vs Gazebo log over %d states: %s" % (n, {k: "%.2e" % v for k, v in e.items()}))
     assert e["foot_pos"] < 1e-4 and e["com"] < 1e-4 and e["foot_vel"] < 5e-3 and e["com_vel"] < 1e-3
+
+
+def _model_tables():
+    """Masses, centres of mass and inertia tensors of the kernels' lumped bodies, parsed from csrc/dogbot_model.h (what the CUDA
+    code compiles in), in leg order BL, BR, FL, FR x (hip, upperleg, lowerleg + foot)."""
+    import re
+    txt = open(os.path.join(util.ROOT, "wbc_quadruped_dob_b200", "csrc", "dogbot_model.h")).read()
+
+    def table(name, shape):
+        m = re.search(name + r"[^=]*=\s*\{(.*?)\};", txt, re.S)
+        body = re.sub(r"//[^\n]*", "", m.group(1))
+        vals = [float(v) for v in re.findall(r"-?\d+\.?\d*(?:[eE][-+]?\d+)?", body)]
+        return np.array(vals).reshape(shape)
+    return (table("kLinkMass", (4, 3)), table("kLinkCom", (4, 3, 3)), table("kLinkInertia", (4, 3, 6)),
+            float(re.search(r"kBaseMass\s*=\s*([0-9.eE+-]+)", txt).group(1)), table("kBaseInertia", (3,)))
+
+
+def test_inertial_parameters_match_the_sdf_gazebo_built_from_the_urdf():
+    """Masses, centres of mass and inertia tensors compiled into the kernels (dogbot_model.h, generated by tools/gen_model.py from
+    dogbot.urdf) against the inertial blocks of the SDF that Gazebo built from the same URDF and embedded in its log -- a second,
+    independent reading of the file.  Base, hips and upper legs agree to the SDF's print precision.  The lower legs carry the 1 g
+    foot link (fixed joint, urdf:320-325): Gazebo's converter of that vintage lumped it AT THE LOWER LEG'S ORIGIN, the model
+    tables lump it at its joint offset (as iDynTree does for fixed joints): the lumped centre of mass differs by exactly that,
+    1.06 mm in z, and is reproduced here from both conventions."""
+    z = np.load(FIX)
+    names = [str(x) for x in z["link_names"]]
+    mass, com, inertia, base_mass, base_inertia = _model_tables()
+    legs = [str(x) for x in z["legs"]]
+    k = names.index("base_link")
+    assert abs(z["link_mass"][k] - base_mass) < 1e-9
+    assert np.abs(z["link_inertia"][k, :3] - base_inertia).max() < 1e-6 and not z["link_inertia"][k, 3:].any()
+    assert not z["link_com"][:, 3:].any()               # every inertial frame is aligned with its link frame
+    for leg, nm in enumerate(legs):
+        for j, part in enumerate(("hip", "upperleg", "lowerleg")):
+            k = names.index(nm + "_" + part)
+            assert abs(z["link_mass"][k] - mass[leg, j]) < 1e-9, (nm, part)
+            if part != "lowerleg":
+                assert np.abs(z["link_com"][k, :3] - com[leg, j]).max() < 1e-6, (nm, part)
+                assert np.abs(z["link_inertia"][k] - inertia[leg, j]).max() < 1e-8, (nm, part)
+            else:
+                # un-lump: lower leg alone = URDF (0.302 kg at (0, -0.029, -0.1439)); the foot is 1 g
+                m_foot = 0.001
+                m_leg = mass[leg, j] - m_foot
+                c_leg = (mass[leg, j] * com[leg, j] - m_foot * z["foot_offset"][leg]) / m_leg          # the tables' convention
+                c_sdf = z["link_mass"][k] * z["link_com"][k, :3] / m_leg                                # foot at the origin
+                assert np.abs(c_leg - c_sdf).max() < 2e-6, (nm, c_leg, c_sdf)
+                assert np.abs(z["link_com"][k, :3] - com[leg, j]).max() < 1.2e-3                        # the two lumpings, 1 mm apart
+                assert np.abs(z["link_inertia"][k] - inertia[leg, j]).max() < 2e-5

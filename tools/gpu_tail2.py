@@ -16,4 +16,4 @@ for lo, hi in ((0, 64), (64, 128), (128, 256), (256, 512), (512, 1024), (1024, 4
     m = (rank >= lo) & (rank < hi)
     print("  flop rank %4d..%4d: latency mean %.3f max %.3f ms, flops mean %.3g, ms per Mflop %.3f" % (lo, hi, ms[m].mean(), ms[m].max(), fl[m].mean(), (ms[m] / fl[m]).mean() * 1e6))
 top = np.argsort(-ms)[:12]
-for i in top: print("  long: %.3f ms flops %.3g rank %d nchol %d" % (ms[i], fl[i], rank[i], out["qp_info"][0][i]))
+for i in top: print("  long: %.3f ms flops %.3g rank %d nchol %d outer %d qqp %d nicwork %d kktdim %d flags %d reused %d  (ms per Mflop %.3f)" % ((ms[i], fl[i], rank[i]) + tuple(int(out["qp_info"][k][i]) for k in (0, 1, 2, 3, 4, 5, 6)) + (ms[i] / fl[i] * 1e6,)))
