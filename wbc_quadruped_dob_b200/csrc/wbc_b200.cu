@@ -173,6 +173,7 @@ struct ExpressLanes {
     int head;          // tickets [0, head) are the express range
     int period, keep;  // every period-th SM pair is express and keeps `keep` warps per SM; period 0: off
     unsigned* cycles;  // [n] the solve's duration (2^10 cycles) when the dispatch cost is not the duration (express lanes on)
+    unsigned long long* prof;   // [grid][12] per-warp timeline (WBC_STAGE_PROF=1), else NULL
 };
 __device__ __forceinline__ int next_instance_lanes(const ExpressLanes& xl, bool express, int n)
 {
@@ -211,7 +212,10 @@ __global__ void __launch_bounds__(SOLVE_T) wbc_solve_kernel(Params P, int n, con
                 verdict = atomicAdd(xl.lanes + 2 + smid, 1) < xl.keep ? 1 : 2;
         }
         verdict = __shfl_sync(0xffffffffu, verdict, 0);
-        if (verdict == 2) return;
+        if (verdict == 2) {
+            if (xl.prof && ex.lane() < 12) xl.prof[(long)blockIdx.x * 12 + ex.lane()] = 0ull;      // no stale row from an earlier launch
+            return;
+        }
         express = verdict == 1;
     }
     Settings cfg;
@@ -219,6 +223,8 @@ __global__ void __launch_bounds__(SOLVE_T) wbc_solve_kernel(Params P, int n, con
     // every value later read from shared memory is finite (out-of-range lanes read neighbours and drop the result)
     for (int k = ex.lane(); k < sl::TOTAL; k += SOLVE_T) WBC_SM(w)[k] = 0.0;
     ex.sync();
+    unsigned long long pr_busy = 0, pr_jobs = 0, pr_first = 0, pr_last = 0, pr_t0 = 0, pr_longest = 0;
+    if (xl.prof) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(pr_t0));
     for (;;) {
         const int ticket = xl.period > 0 ? next_instance_lanes(xl, express, n) : next_instance(queue);
         if (ticket >= n) break;
@@ -289,11 +295,27 @@ __global__ void __launch_bounds__(SOLVE_T) wbc_solve_kernel(Params P, int n, con
             // With express lanes a solve's duration depends on where it ran (an express warp is almost twice as fast), and a cost
             // that does would make the order oscillate: rank by the solve's instrumented flop count instead (correlation with the
             // duration 0.97; the literal multiplier update, which the count does not see, is a flat surcharge).  Same unit: 2^10 cycles.
+            if (xl.prof) {
+                const unsigned long long d = (unsigned long long)(clock64() - t0);
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                pr_busy += d; pr_jobs++; pr_last = now; if (d > pr_longest) pr_longest = d;
+                if (pr_jobs == 1) pr_first = now - (unsigned long long)((double)d / 1.965);      // start of the first solve, ns
+            }
             if (xl.period > 0) { xl.cycles[i] = cu; cu = (unsigned)(st.flops * (1.0 / 512.0)) + ((st.flags & 8) ? 2000u : 0u); }
             cost[i] = cu;
             atomicAdd(hist_next + cost_bucket(cu), 1);
         }
         ex.sync();
+    }
+    if (xl.prof && ex.lane() == 0) {
+        // per-warp timeline: busy cycles, solves, [kernel entry, first solve start, last solve end, exit] (globaltimer, ns), longest solve, express flag, SM
+        unsigned long long now; unsigned smid;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        unsigned long long* p = xl.prof + (long)blockIdx.x * 12;
+        p[0] = pr_busy; p[1] = pr_jobs; p[2] = pr_t0; p[3] = pr_first; p[4] = pr_last; p[5] = now; p[6] = pr_longest; p[7] = express ? 1 : 0; p[8] = smid;
+        p[9] = 0; p[10] = 0; p[11] = 0;
     }
 }
 
@@ -718,7 +740,7 @@ struct wbc_ctx {
     unsigned* cycles;    // [max_batch] solve durations of the last cycle when express lanes were on (the cost array then ranks by flop count)
     int cycles_valid;
     int* lanes;          // [LANES_INTS] express-lane counters of the solve launch (zeroed by the front kernel)
-    int xl_period, xl_keep, xl_min_n;    // express lanes: every xl_period-th SM pair keeps xl_keep warps per SM; batches from xl_min_n instances
+    int xl_period, xl_keep, xl_min_n, xl_warps;    // express lanes: every xl_period-th SM pair keeps xl_keep warps per SM; batches from xl_min_n instances
     double xl_head_mult; // express range of the dispatch order = xl_head_mult x the number of express warps
     int front_leg;       // 1 (default): wbc_front_leg_kernel, four lanes per instance; 0: wbc_front_kernel, a thread per instance (WBC_FRONT=thread)
     int last_staged;     // which kernel the last wbc_cycle launched
@@ -847,10 +869,11 @@ int wbc_create(wbc_ctx** out, int device, int max_batch, const wbc_params* param
     if (const char* ev = getenv("WBC_STAGED_MIN_N")) c->staged_min_n = atoi(ev);
     c->front_leg = 1;
     // express lanes (ExpressLanes): WBC_EXPRESS = "period,keep,head multiplier,min n"; period 0 switches them off
-    c->xl_period = 9; c->xl_keep = 4; c->xl_head_mult = 1.0; c->xl_min_n = 2048;
+    c->xl_period = 9; c->xl_keep = 4; c->xl_head_mult = 1.0; c->xl_min_n = 2048; c->xl_warps = 12;
     if (const char* ev = getenv("WBC_EXPRESS")) {
-        int a = 9, b = 4, d = 2048; double m = 2.0;
-        const int got = sscanf(ev, "%d,%d,%lf,%d", &a, &b, &m, &d);
+        int a = 9, b = 4, d = 2048, wps = 12; double m = 2.0;
+        const int got = sscanf(ev, "%d,%d,%lf,%d,%d", &a, &b, &m, &d, &wps);
+        if (got >= 5 && wps >= 4 && wps <= 12) c->xl_warps = wps;
         if (got >= 1 && a >= 0 && a < 75) c->xl_period = a;
         if (got >= 2 && b >= 1 && b <= 12) c->xl_keep = b;
         if (got >= 3 && m >= 0.0) c->xl_head_mult = m;
@@ -1150,7 +1173,7 @@ int wbc_cycle(wbc_ctx* c, int n, const wbc_inputs* in, const wbc_outputs* out, v
     const bool staged = c->staged == 1 || (c->staged == 2 && n >= c->staged_min_n);
     c->last_staged = staged ? 1 : 0;
     ExpressLanes xl;
-    xl.lanes = c->lanes; xl.head = 0; xl.period = 0; xl.keep = c->xl_keep; xl.cycles = c->cycles;
+    xl.lanes = c->lanes; xl.head = 0; xl.period = 0; xl.keep = c->xl_keep; xl.cycles = c->cycles; xl.prof = c->prof;
     c->cycles_valid = 0;
     if (express) {
         // every resident warp (12 per SM); the express SM pairs keep xl_keep warps per SM and serve the head of the order
@@ -1160,6 +1183,10 @@ int wbc_cycle(wbc_ctx* c, int n, const wbc_inputs* in, const wbc_outputs* out, v
         c->cycles_valid = 1;
         xl.head = (int)(c->xl_head_mult * nexp * c->xl_keep + 0.5);
         if (xl.head > n) xl.head = n;
+        if (c->xl_warps < c->occ_per_sm) {         // fewer warps on the regular SMs (padded shared-memory request, as below)
+            nblocks = c->xl_warps * c->sm_count;
+            smem = (((228 * 1024) / c->xl_warps - 1024) / 16) * 16;
+        }
     } else if (!staged && c->occ_per_sm > 8 && !c->occ_forced) {
         int per_sm = (int)((double)n / (3.4 * c->sm_count));
         per_sm = per_sm < 8 ? 8 : (per_sm > c->occ_per_sm ? c->occ_per_sm : per_sm);
