@@ -174,6 +174,7 @@ struct ExpressLanes {
     int period, keep;  // every period-th SM pair is express and keeps `keep` warps per SM; period 0: off
     unsigned* cycles;  // [n] the solve's duration (2^10 cycles) when the dispatch cost is not the duration (express lanes on)
     unsigned long long* prof;   // [grid][12] per-warp timeline (WBC_STAGE_PROF=1), else NULL
+    float time_scale;  // 0: rank by flop count; > 0: rank by duration, an express warp's multiplied by this
 };
 __device__ __forceinline__ int next_instance_lanes(const ExpressLanes& xl, bool express, int n)
 {
@@ -302,7 +303,11 @@ __global__ void __launch_bounds__(SOLVE_T) wbc_solve_kernel(Params P, int n, con
                 pr_busy += d; pr_jobs++; pr_last = now; if (d > pr_longest) pr_longest = d;
                 if (pr_jobs == 1) pr_first = now - (unsigned long long)((double)d / 1.965);      // start of the first solve, ns
             }
-            if (xl.period > 0) { xl.cycles[i] = cu; cu = (unsigned)(st.flops * (1.0 / 512.0)) + ((st.flags & 8) ? 2000u : 0u); }
+            if (xl.period > 0) {
+                xl.cycles[i] = cu;
+                if (xl.time_scale > 0.0f) cu = express ? (unsigned)((float)cu * xl.time_scale) : cu;
+                else cu = (unsigned)(st.flops * (1.0 / 512.0)) + ((st.flags & 8) ? 2000u : 0u);
+            }
             cost[i] = cu;
             atomicAdd(hist_next + cost_bucket(cu), 1);
         }
@@ -740,7 +745,8 @@ struct wbc_ctx {
     unsigned* cycles;    // [max_batch] solve durations of the last cycle when express lanes were on (the cost array then ranks by flop count)
     int cycles_valid;
     int* lanes;          // [LANES_INTS] express-lane counters of the solve launch (zeroed by the front kernel)
-    int xl_period, xl_keep, xl_min_n, xl_warps;    // express lanes: every xl_period-th SM pair keeps xl_keep warps per SM; batches from xl_min_n instances
+    int xl_period, xl_keep, xl_min_n, xl_warps;
+    float xl_time_scale;    // express lanes: every xl_period-th SM pair keeps xl_keep warps per SM; batches from xl_min_n instances
     double xl_head_mult; // express range of the dispatch order = xl_head_mult x the number of express warps
     int front_leg;       // 1 (default): wbc_front_leg_kernel, four lanes per instance; 0: wbc_front_kernel, a thread per instance (WBC_FRONT=thread)
     int last_staged;     // which kernel the last wbc_cycle launched
@@ -869,10 +875,11 @@ int wbc_create(wbc_ctx** out, int device, int max_batch, const wbc_params* param
     if (const char* ev = getenv("WBC_STAGED_MIN_N")) c->staged_min_n = atoi(ev);
     c->front_leg = 1;
     // express lanes (ExpressLanes): WBC_EXPRESS = "period,keep,head multiplier,min n"; period 0 switches them off
-    c->xl_period = 9; c->xl_keep = 4; c->xl_head_mult = 1.0; c->xl_min_n = 2048; c->xl_warps = 12;
+    c->xl_period = 9; c->xl_keep = 4; c->xl_head_mult = 1.0; c->xl_min_n = 2048; c->xl_warps = 12; c->xl_time_scale = 0.0f;
     if (const char* ev = getenv("WBC_EXPRESS")) {
-        int a = 9, b = 4, d = 2048, wps = 12; double m = 2.0;
-        const int got = sscanf(ev, "%d,%d,%lf,%d,%d", &a, &b, &m, &d, &wps);
+        int a = 9, b = 4, d = 2048, wps = 12; double m = 2.0, ts = 0.0;
+        const int got = sscanf(ev, "%d,%d,%lf,%d,%d,%lf", &a, &b, &m, &d, &wps, &ts);
+        if (got >= 6 && ts >= 0.0) c->xl_time_scale = (float)ts;
         if (got >= 5 && wps >= 4 && wps <= 12) c->xl_warps = wps;
         if (got >= 1 && a >= 0 && a < 75) c->xl_period = a;
         if (got >= 2 && b >= 1 && b <= 12) c->xl_keep = b;
@@ -1173,7 +1180,7 @@ int wbc_cycle(wbc_ctx* c, int n, const wbc_inputs* in, const wbc_outputs* out, v
     const bool staged = c->staged == 1 || (c->staged == 2 && n >= c->staged_min_n);
     c->last_staged = staged ? 1 : 0;
     ExpressLanes xl;
-    xl.lanes = c->lanes; xl.head = 0; xl.period = 0; xl.keep = c->xl_keep; xl.cycles = c->cycles; xl.prof = c->prof;
+    xl.lanes = c->lanes; xl.head = 0; xl.period = 0; xl.keep = c->xl_keep; xl.cycles = c->cycles; xl.prof = c->prof; xl.time_scale = c->xl_time_scale;
     c->cycles_valid = 0;
     if (express) {
         // every resident warp (12 per SM); the express SM pairs keep xl_keep warps per SM and serve the head of the order
