@@ -77,10 +77,26 @@ def gazebo_scenario():
         foot_p[:, sf] = p[nm] + off
         foot_v[:, sf] = v[nm] + np.cross(w[nm], off)
         foot_R[:, sf] = R[nm]
+    # kinetic energy, linear momentum and angular momentum about the base origin of the LOGGED motion: every link's logged twist
+    # with the SDF's mass, centre of mass and inertia tensor -- no model of ours involved
+    T = np.zeros(n); Pl = np.zeros((n, 3)); La = np.zeros((n, 3))
+    for nm in names:
+        k = li[nm]
+        m = z["link_mass"][k]
+        rc = np.einsum("nij,j->ni", R[nm], z["link_com"][k, 0:3])
+        vc = v[nm] + np.cross(w[nm], rc)
+        ixx, iyy, izz, ixy, ixz, iyz = z["link_inertia"][k]
+        Il = np.array([[ixx, ixy, ixz], [ixy, iyy, iyz], [ixz, iyz, izz]])
+        Iw = np.einsum("nij,jk,nlk->nil", R[nm], Il, R[nm])
+        Iww = np.einsum("nij,nj->ni", Iw, w[nm])
+        T += 0.5 * m * np.einsum("ni,ni->n", vc, vc) + 0.5 * np.einsum("ni,ni->n", w[nm], Iww)
+        Pl += m * vc
+        La += Iww + np.cross(p[nm] + rc - p["base_link"], m * vc)
     keep = hinge_err < 3e-5                              # states in which every hinge is a hinge to print precision
     assert hinge_err.max() < 1e-3
     sc = {k: (np.ascontiguousarray(v_[..., keep]) if isinstance(v_, np.ndarray) else v_) for k, v_ in sc.items()}
-    return sc, dict(com=com[keep], com_vel=comv[keep], foot_pos=foot_p[keep], foot_vel=foot_v[keep], foot_R=foot_R[keep], mass=M, q=q[:, keep])
+    return sc, dict(com=com[keep], com_vel=comv[keep], foot_pos=foot_p[keep], foot_vel=foot_v[keep], foot_R=foot_R[keep], mass=M, q=q[:, keep],
+                    kinetic=T[keep], lin_mom=Pl[keep], ang_mom=La[keep])
 
 
 def test_fixture_is_a_moving_robot():
@@ -169,3 +185,40 @@ def test_inertial_parameters_match_the_sdf_gazebo_built_from_the_urdf():
                 assert np.abs(c_leg - c_sdf).max() < 2e-6, (nm, c_leg, c_sdf)
                 assert np.abs(z["link_com"][k, :3] - com[leg, j]).max() < 1.2e-3                        # the two lumpings, 1 mm apart
                 assert np.abs(z["link_inertia"][k] - inertia[leg, j]).max() < 2e-5
+
+
+def _energy_and_momentum_errors(M_of, sc, ref):
+    """nu' M nu / 2 and the base rows of M nu (linear momentum; angular momentum about the base origin -- MIXED representation)
+    against the kinetic energy and momenta of the logged link twists."""
+    n = sc["mode"].shape[0]
+    eT, eP, eL, Tmax = 0.0, 0.0, 0.0, 0.0
+    for i in range(n):
+        M = M_of(i)
+        nu = np.concatenate([sc["base_vel"][:, i], sc["dq"][:, i]])
+        Mnu = M @ nu
+        T = 0.5 * nu @ Mnu
+        eT = max(eT, abs(T - ref["kinetic"][i]) / max(ref["kinetic"][i], 1e-3))
+        eP = max(eP, np.abs(Mnu[0:3] - ref["lin_mom"][i]).max())
+        eL = max(eL, np.abs(Mnu[3:6] - ref["ang_mom"][i]).max())
+        Tmax = max(Tmax, T)
+    return eT, eP, eL, Tmax
+
+
+def test_oracle_mass_matrix_reproduces_the_kinetic_energy_and_momentum_of_the_logged_motion(oracle):
+    """The dynamics are not reference-pinned (no iDynTree), but the mass matrix has to agree with the one artefact that records the
+    robot moving: nu' M nu / 2 is the kinetic energy, and the base rows of M nu the linear momentum and the angular momentum about
+    the base origin, of the thirteen logged link twists weighted with the SDF's inertial data.  To the log's print precision."""
+    sc, ref = gazebo_scenario()
+    eT, eP, eL, Tmax = _energy_and_momentum_errors(lambda i: np.array(oracle.update_only(sc, i).M).reshape(18, 18), sc, ref)
+    print("oracle M vs the logged motion: kinetic energy rel err %.2e (largest %.2f J), linear momentum %.2e kg m/s, angular %.2e kg m2/s" % (eT, Tmax, eP, eL))
+    assert Tmax > 1.0                                    # the drop carries real energy
+    assert eT < 1e-2 and eP < 5e-3 and eL < 2e-3
+
+
+@pytest.mark.gpu
+def test_kernel_mass_matrix_reproduces_the_kinetic_energy_and_momentum_of_the_logged_motion(gpu_batch):
+    sc, ref = gazebo_scenario()
+    dbg = gpu_batch.debug_update(sc)
+    eT, eP, eL, Tmax = _energy_and_momentum_errors(lambda i: dbg["M"][:, i].reshape(18, 18), sc, ref)
+    print("kernel M vs the logged motion: kinetic energy rel err %.2e (largest %.2f J), linear momentum %.2e kg m/s, angular %.2e kg m2/s" % (eT, Tmax, eP, eL))
+    assert eT < 1e-2 and eP < 5e-3 and eL < 2e-3
