@@ -79,7 +79,7 @@ def gazebo_scenario():
         foot_R[:, sf] = R[nm]
     # kinetic energy, linear momentum and angular momentum about the base origin of the LOGGED motion: every link's logged twist
     # with the SDF's mass, centre of mass and inertia tensor -- no model of ours involved
-    T = np.zeros(n); Pl = np.zeros((n, 3)); La = np.zeros((n, 3))
+    T = np.zeros(n); Pl = np.zeros((n, 3)); La = np.zeros((n, 3)); Pg = np.zeros(n)
     for nm in names:
         k = li[nm]
         m = z["link_mass"][k]
@@ -92,11 +92,12 @@ def gazebo_scenario():
         T += 0.5 * m * np.einsum("ni,ni->n", vc, vc) + 0.5 * np.einsum("ni,ni->n", w[nm], Iww)
         Pl += m * vc
         La += Iww + np.cross(p[nm] + rc - p["base_link"], m * vc)
+        Pg += m * (-9.8) * vc[:, 2]                          # power of gravity on this link (gravity (0, 0, -9.8), main.cpp:855)
     keep = hinge_err < 3e-5                              # states in which every hinge is a hinge to print precision
     assert hinge_err.max() < 1e-3
     sc = {k: (np.ascontiguousarray(v_[..., keep]) if isinstance(v_, np.ndarray) else v_) for k, v_ in sc.items()}
     return sc, dict(com=com[keep], com_vel=comv[keep], foot_pos=foot_p[keep], foot_vel=foot_v[keep], foot_R=foot_R[keep], mass=M, q=q[:, keep],
-                    kinetic=T[keep], lin_mom=Pl[keep], ang_mom=La[keep])
+                    kinetic=T[keep], lin_mom=Pl[keep], ang_mom=La[keep], gravity_power=Pg[keep])
 
 
 def test_fixture_is_a_moving_robot():
@@ -222,3 +223,30 @@ def test_kernel_mass_matrix_reproduces_the_kinetic_energy_and_momentum_of_the_lo
     eT, eP, eL, Tmax = _energy_and_momentum_errors(lambda i: dbg["M"][:, i].reshape(18, 18), sc, ref)
     print("kernel M vs the logged motion: kinetic energy rel err %.2e (largest %.2f J), linear momentum %.2e kg m/s, angular %.2e kg m2/s" % (eT, Tmax, eP, eL))
     assert eT < 1e-2 and eP < 5e-3 and eL < 2e-3
+
+
+def _gravity_power_error(g_of, sc, ref):
+    """-g(q)' nu is the power gravity puts into the robot; from the log it is the sum of m grav . v_c over the thirteen links."""
+    n = sc["mode"].shape[0]
+    worst, scale = 0.0, 0.0
+    for i in range(n):
+        nu = np.concatenate([sc["base_vel"][:, i], sc["dq"][:, i]])
+        worst = max(worst, abs(-(g_of(i) @ nu) - ref["gravity_power"][i]))
+        scale = max(scale, abs(ref["gravity_power"][i]))
+    return worst, scale
+
+
+def test_oracle_gravity_forces_reproduce_the_power_of_gravity_in_the_logged_motion(oracle):
+    sc, ref = gazebo_scenario()
+    worst, scale = _gravity_power_error(lambda i: np.array(oracle.update_only(sc, i).g), sc, ref)
+    print("oracle g vs the logged motion: power of gravity abs err %.2e W (largest %.1f W)" % (worst, scale))
+    assert scale > 50.0 and worst < 2e-3 * scale
+
+
+@pytest.mark.gpu
+def test_kernel_gravity_forces_reproduce_the_power_of_gravity_in_the_logged_motion(gpu_batch):
+    sc, ref = gazebo_scenario()
+    dbg = gpu_batch.debug_update(sc)
+    worst, scale = _gravity_power_error(lambda i: dbg["g"][:, i], sc, ref)
+    print("kernel g vs the logged motion: power of gravity abs err %.2e W (largest %.1f W)" % (worst, scale))
+    assert worst < 2e-3 * scale
