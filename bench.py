@@ -502,7 +502,8 @@ def main():
                     also[name] = {k: l2[k] for k in ("value", "unit", "ms_per_step", "p50_ms", "steps", "warmup", "e2e", "stats", "value_fifo", "dispatch_gain") if k in l2}
                     also[name]["workload"] = l2["config"]["workload"]
                     also[name]["instances_per_gpu"] = l2["config"]["instances_per_gpu"]
-                    also[name]["roofline"] = {k: l2["roofline"][k] for k in ("achieved", "peak", "unit", "frac", "kernel_ms", "front_kernel_ms", "flops_per_solve", "algorithmic_bytes_per_launch")}
+                    also[name]["roofline"] = {k: l2["roofline"][k] for k in ("bound", "kernel", "achieved", "peak", "unit", "frac", "traffic", "traffic_source", "kernel_ms", "front_kernel_ms",
+                                                                              "flops_per_solve", "algorithmic_bytes_per_launch", "intermediate_bytes_per_launch") if k in l2["roofline"]}
                     also[name]["clocks"] = l2["clocks"]
             if line is not None:
                 line["also"] = also
