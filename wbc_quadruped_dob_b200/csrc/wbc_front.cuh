@@ -642,28 +642,62 @@ WBC_DEVFN inline void fdyn_step_instance(const Params& P, const FdynIO& io, long
     for (int it = 0; it < nsub; it++) {
         FrontDyn D;
         front_dynamics(P, in, i, D);
-        // M (18 x 18, lower triangle) and its Cholesky factor
-        double L[18 * 18];
-        for (int a = 0; a < 18; a++)
-            for (int b = 0; b <= a; b++) {
-                double v;
-                if (a < 6) v = D.Mb[a * 6 + b];
-                else if (b < 6) v = D.Mbj[b * 12 + (a - 6)];
-                else v = D.Mjj[(a - 6) * 12 + (b - 6)];
-                L[a * 18 + b] = v;
+        // M = [Mb, Mbj; Mbj', Mjj] with Mjj block diagonal (one 3 x 3 block per leg: the legs only couple through the base), so
+        // M^-1 is applied by block elimination: four 3 x 3 Cholesky factors, Z_l = Mjj_l^-1 Mbj_l', the 6 x 6 Schur complement
+        // Sb = Mb - sum_l Mbj_l Z_l (one more 6 x 6 Cholesky) -- instead of a dense 18 x 18 factorisation.
+        double Lj[4][6], Z[4][18];
+        double Sb[36];
+        for (int k = 0; k < 36; k++) Sb[k] = D.Mb[k];
+        for (int leg = 0; leg < 4; leg++) {
+            const int i0 = dof_index(leg, 0), i1 = dof_index(leg, 1), i2 = i1 + 1;
+            double* l = Lj[leg];                       // lower factor: l00, l10, l11, l20, l21, l22 (diagonal entries stored as reciprocals)
+            const double m00 = D.Mjj[i0 * 12 + i0], m10 = D.Mjj[i1 * 12 + i0], m11 = D.Mjj[i1 * 12 + i1];
+            const double m20 = D.Mjj[i2 * 12 + i0], m21 = D.Mjj[i2 * 12 + i1], m22 = D.Mjj[i2 * 12 + i2];
+            const double d0 = sqrt(m00);
+            l[0] = 1.0 / d0; l[1] = m10 * l[0]; l[3] = m20 * l[0];
+            const double d1 = sqrt(m11 - l[1] * l[1]);
+            l[2] = 1.0 / d1; l[4] = (m21 - l[3] * l[1]) * l[2];
+            const double d2 = sqrt(m22 - l[3] * l[3] - l[4] * l[4]);
+            l[5] = 1.0 / d2;
+            for (int k = 0; k < 6; k++) {
+                double y0 = D.Mbj[k * 12 + i0] * l[0];
+                double y1 = (D.Mbj[k * 12 + i1] - l[1] * y0) * l[2];
+                double y2 = (D.Mbj[k * 12 + i2] - l[3] * y0 - l[4] * y1) * l[5];
+                y2 = y2 * l[5]; y1 = (y1 - l[4] * y2) * l[2]; y0 = (y0 - l[1] * y1 - l[3] * y2) * l[0];
+                Z[leg][0 * 6 + k] = y0; Z[leg][1 * 6 + k] = y1; Z[leg][2 * 6 + k] = y2;
             }
-        for (int j = 0; j < 18; j++) {
-            double d = L[j * 18 + j];
-            for (int k = 0; k < j; k++) d -= L[j * 18 + k] * L[j * 18 + k];
-            d = sqrt(d);
-            L[j * 18 + j] = d;
-            const double r = 1.0 / d;
-            for (int a = j + 1; a < 18; a++) {
-                double sacc = L[a * 18 + j];
-                for (int k = 0; k < j; k++) sacc -= L[a * 18 + k] * L[j * 18 + k];
-                L[a * 18 + j] = sacc * r;
-            }
+            for (int r = 0; r < 6; r++)
+                for (int c2 = 0; c2 < 6; c2++)
+                    Sb[r * 6 + c2] -= D.Mbj[r * 12 + i0] * Z[leg][0 * 6 + c2] + D.Mbj[r * 12 + i1] * Z[leg][1 * 6 + c2] + D.Mbj[r * 12 + i2] * Z[leg][2 * 6 + c2];
         }
+        chol6(Sb);
+        // x = M^-1 [rb; rj] for a right-hand side whose joint part lives on the legs flagged in `legs` (bit l)
+        auto solveM = [&](const double* rb, const double* rj, unsigned legs, double* xb, double* xj) {
+            double t[6], y[12];
+            for (int k = 0; k < 6; k++) t[k] = rb[k];
+            for (int leg = 0; leg < 4; leg++) {
+                const int i0 = dof_index(leg, 0), i1 = dof_index(leg, 1), i2 = i1 + 1;
+                if (!(legs & (1u << leg))) { y[i0] = y[i1] = y[i2] = 0.0; continue; }
+                const double* l = Lj[leg];
+                double y0 = rj[i0] * l[0];
+                double y1 = (rj[i1] - l[1] * y0) * l[2];
+                double y2 = (rj[i2] - l[3] * y0 - l[4] * y1) * l[5];
+                y2 = y2 * l[5]; y1 = (y1 - l[4] * y2) * l[2]; y0 = (y0 - l[1] * y1 - l[3] * y2) * l[0];
+                y[i0] = y0; y[i1] = y1; y[i2] = y2;
+                for (int r = 0; r < 6; r++) t[r] -= D.Mbj[r * 12 + i0] * y0 + D.Mbj[r * 12 + i1] * y1 + D.Mbj[r * 12 + i2] * y2;
+            }
+            chol6_solve(Sb, t);
+            for (int k = 0; k < 6; k++) xb[k] = t[k];
+            for (int leg = 0; leg < 4; leg++) {
+                const int i0 = dof_index(leg, 0), i1 = dof_index(leg, 1), i2 = i1 + 1;
+                const int id[3] = {i0, i1, i2};
+                for (int a = 0; a < 3; a++) {
+                    double sacc = y[id[a]];
+                    for (int k = 0; k < 6; k++) sacc -= Z[leg][a * 6 + k] * t[k];
+                    xj[id[a]] = sacc;
+                }
+            }
+        };
         // generalised velocity, right-hand side b = S'tau - h + push_gen
         double nu[18], b[18];
         nu[0] = D.v0.x; nu[1] = D.v0.y; nu[2] = D.v0.z; nu[3] = D.w0.x; nu[4] = D.w0.y; nu[5] = D.w0.z;
@@ -673,8 +707,9 @@ WBC_DEVFN inline void fdyn_step_instance(const Params& P, const FdynIO& io, long
         for (int k = 0; k < 6; k++) b[k] = -D.hb[k] + push[k];
         b[3] += tq.x; b[4] += tq.y; b[5] += tq.z;
         for (int k = 0; k < 12; k++) b[6 + k] = -D.hj[k] + tau[k];
-        // stance rows of the linear foot Jacobian (base columns [I, -S(rf)], the leg's three joint columns) and their targets
-        double Js[12 * 18], c[12];
+        // stance rows of the linear foot Jacobian: base columns [I, -S(rf)] (Jb, 6 per row) and the leg's three joint columns (Jl)
+        double Jb[12 * 6], Jl[12 * 3], c[12];
+        int rleg[12];
         int r = 0;
         for (int sf = 0; sf < 4; sf++) {
             if (!stance[sf]) continue;
@@ -682,46 +717,36 @@ WBC_DEVFN inline void fdyn_step_instance(const Params& P, const FdynIO& io, long
             const V3 rf = D.footp[leg];
             const double nSf[9] = {0, rf.z, -rf.y, -rf.z, 0, rf.x, rf.y, -rf.x, 0};
             for (int a = 0; a < 3; a++, r++) {
-                double* row = Js + r * 18;
-                for (int k = 0; k < 18; k++) row[k] = 0.0;
-                row[a] = 1.0;
-                for (int k = 0; k < 3; k++) row[3 + k] = nSf[a * 3 + k];
-                for (int k = 0; k < 3; k++) row[6 + dof_index(leg, k)] = D.Jleg[leg][a * 3 + k];
+                rleg[r] = leg;
+                for (int k = 0; k < 3; k++) { Jb[r * 6 + k] = (k == a) ? 1.0 : 0.0; Jb[r * 6 + 3 + k] = nSf[a * 3 + k]; Jl[r * 3 + k] = D.Jleg[leg][a * 3 + k]; }
                 double jn = 0.0;
-                for (int k = 0; k < 18; k++) jn += row[k] * nu[k];
+                for (int k = 0; k < 6; k++) jn += Jb[r * 6 + k] * nu[k];
+                for (int k = 0; k < 3; k++) jn += Jl[r * 3 + k] * nu[6 + dof_index(leg, k)];
                 c[r] = -comp(D.foota[leg], a) - gamma * jn;
             }
         }
         // a0 = M^-1 b
         double a0[18];
-        for (int a = 0; a < 18; a++) {
-            double sacc = b[a];
-            for (int k = 0; k < a; k++) sacc -= L[a * 18 + k] * a0[k];
-            a0[a] = sacc / L[a * 18 + a];
-        }
-        for (int a = 17; a >= 0; a--) {
-            double sacc = a0[a];
-            for (int k = a + 1; k < 18; k++) sacc -= L[k * 18 + a] * a0[k];
-            a0[a] = sacc / L[a * 18 + a];
-        }
-        // Y = L^-1 Js' (column r of Y in row r of Ym), A = Y'Y, rhs = c - Js a0
-        double Ym[12 * 18], A[12 * 12], f[12];
+        solveM(b, b + 6, 0xfu, a0, a0 + 6);
+        // X = M^-1 Js' (column r in Xb[r], Xj[r]), A = Js X, rhs = c - Js a0
+        double Xb[12 * 6], Xj[12 * 12], A[12 * 12], f[12];
         for (int rr = 0; rr < nc; rr++) {
-            double* y = Ym + rr * 18;
-            for (int a = 0; a < 18; a++) {
-                double sacc = Js[rr * 18 + a];
-                for (int k = 0; k < a; k++) sacc -= L[a * 18 + k] * y[k];
-                y[a] = sacc / L[a * 18 + a];
-            }
+            double rj[12];
+            for (int k = 0; k < 12; k++) rj[k] = 0.0;
+            for (int k = 0; k < 3; k++) rj[dof_index(rleg[rr], k)] = Jl[rr * 3 + k];
+            solveM(Jb + rr * 6, rj, 1u << rleg[rr], Xb + rr * 6, Xj + rr * 12);
         }
         for (int p_ = 0; p_ < nc; p_++) {
+            const int lp = rleg[p_];
             for (int q_ = 0; q_ <= p_; q_++) {
                 double sacc = 0.0;
-                for (int k = 0; k < 18; k++) sacc += Ym[p_ * 18 + k] * Ym[q_ * 18 + k];
+                for (int k = 0; k < 6; k++) sacc += Jb[p_ * 6 + k] * Xb[q_ * 6 + k];
+                for (int k = 0; k < 3; k++) sacc += Jl[p_ * 3 + k] * Xj[q_ * 12 + dof_index(lp, k)];
                 A[p_ * 12 + q_] = sacc;
             }
             double sacc = c[p_];
-            for (int k = 0; k < 18; k++) sacc -= Js[p_ * 18 + k] * a0[k];
+            for (int k = 0; k < 6; k++) sacc -= Jb[p_ * 6 + k] * a0[k];
+            for (int k = 0; k < 3; k++) sacc -= Jl[p_ * 3 + k] * a0[6 + dof_index(lp, k)];
             f[p_] = sacc;
         }
         for (int j = 0; j < nc; j++) {                    // Cholesky of A, in place (lower)
@@ -745,27 +770,17 @@ WBC_DEVFN inline void fdyn_step_instance(const Params& P, const FdynIO& io, long
             for (int k = a + 1; k < nc; k++) sacc -= A[k * 12 + a] * f[k];
             f[a] = sacc / A[a * 12 + a];
         }
-        // nu_dot = a0 + M^-1 Js' f
+        // nu_dot = a0 + M^-1 Js' f = a0 + X f
         double nd[18];
-        for (int a = 0; a < 18; a++) {
-            double sacc = 0.0;
-            for (int rr = 0; rr < nc; rr++) sacc += Js[rr * 18 + a] * f[rr];
-            nd[a] = sacc;
+        for (int a = 0; a < 18; a++) nd[a] = a0[a];
+        for (int rr = 0; rr < nc; rr++) {
+            for (int k = 0; k < 6; k++) nd[k] += Xb[rr * 6 + k] * f[rr];
+            for (int k = 0; k < 12; k++) nd[6 + k] += Xj[rr * 12 + k] * f[rr];
         }
-        for (int a = 0; a < 18; a++) {
-            double sacc = nd[a];
-            for (int k = 0; k < a; k++) sacc -= L[a * 18 + k] * nd[k];
-            nd[a] = sacc / L[a * 18 + a];
-        }
-        for (int a = 17; a >= 0; a--) {
-            double sacc = nd[a];
-            for (int k = a + 1; k < 18; k++) sacc -= L[k * 18 + a] * nd[k];
-            nd[a] = sacc / L[a * 18 + a];
-        }
-        for (int a = 0; a < 18; a++) nd[a] += a0[a];
         for (int rr = 0; rr < nc; rr++) {
             double ja = 0.0;
-            for (int k = 0; k < 18; k++) ja += Js[rr * 18 + k] * nd[k];
+            for (int k = 0; k < 6; k++) ja += Jb[rr * 6 + k] * nd[k];
+            for (int k = 0; k < 3; k++) ja += Jl[rr * 3 + k] * nd[6 + dof_index(rleg[rr], k)];
             worst = fmax(worst, fabs(ja - c[rr]));
         }
         // contact forces in the sensor frames (what the contact sensors report, main.cpp:794-834)
