@@ -205,6 +205,8 @@ def parse_args():
                     help="e2e loop only: the plan's spline tables live in HBM and are sampled on the GPU each step (SURVEY 8f-1); "
                          "the 36 desired-trajectory doubles per instance are not sent from the host")
     ap.add_argument("--fifo", action="store_true", help="index-order work queue (WBC_FIFO_DISPATCH) instead of longest-first")
+    ap.add_argument("--plant", default="momentum", choices=["momentum", "dynamics"],
+                    help="push_sweep: the plant that closes the loop -- the CoM-momentum integrator of SURVEY 8d row 5 (default) or forward dynamics with rigid contacts (SURVEY 8f-2)")
     ap.add_argument("--sweep-cycles", type=int, default=None, help="push_sweep: closed-loop cycles of the rollout (default 400 = 1 s; --steps is ignored)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

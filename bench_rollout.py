@@ -151,9 +151,15 @@ def bench_push_sweep(env, args):
     lo, hi = sharding.shard_range(total, rank, world)
     n = hi - lo
     cycles = args.sweep_cycles or 400
+    dyn_plant = getattr(args, "plant", "momentum") == "dynamics"
     tail = max(1, min(40, cycles // 4))
     sc = S.push_sweep(n=n, start=lo)
     sc.pop("grid", None)
+    if getattr(args, "plant", "momentum") == "dynamics":
+        # the articulated robot really moves: hold the pose it starts in (the momentum plant keeps joints and orientation frozen, so
+        # there the scenario's desired CoM offset only loads the QP)
+        com0, _ = S.forward_kinematics(sc["base_pos"], sc["base_rot"], sc["q"])
+        sc["com_des_pos"] = np.vstack([com0.T, sc["base_rpy"]])
     batch = api.WbcBatch(max_batch=n, device=env.local_rank)
     batch.set_observer_state(sc["obs_yd"], sc["obs_yw"])
     din = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in sc.items() if isinstance(v, np.ndarray)}
@@ -181,7 +187,11 @@ def bench_push_sweep(env, args):
         outs = sout if c == cycles - 1 else dout
         ev[c][0].record(env.stream)
         batch.cycle_device(din, outs, n, n, stream=sp, sync=False)
-        batch.plant_step(din["base_pos"], din["base_vel"], din["push"], foot_force=din["foot_force"], x=outs["x"], n=n, ld=n, stream=sp, sync=False)
+        if dyn_plant:
+            # the articulated robot on rigid contacts under the commanded torques and the push
+            batch.plant_dynamics_step(din, outs["tau"], din["push"], n=n, ld=n, substeps=5, gamma=100.0, stream=sp, sync=False)
+        else:
+            batch.plant_step(din["base_pos"], din["base_vel"], din["push"], foot_force=din["foot_force"], x=outs["x"], n=n, ld=n, stream=sp, sync=False)
         ev[c][1].record(env.stream)
         # metrics of this cycle, on the device, outside the timed bracket
         w = dout["w"]
@@ -231,7 +241,8 @@ def bench_push_sweep(env, args):
                 "ms_per_step": tot_ms / cycles, "p50_ms": float(np.median(step_ms)), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": "push_sweep: %d instances (16 push directions x 8 magnitudes 5..80 N x 8 observer gains x 256 states) over %d GPU(s), "
-                                       "%d closed-loop cycles (%.2f s) through wbc_plant_step, everything resident in HBM" % (total, world, cycles, cycles * 0.0025),
+                                       "%d closed-loop cycles (%.2f s) through %s, everything resident in HBM" % (total, world, cycles, cycles * 0.0025,
+                                                                                                                              "wbc_plant_dynamics_step (forward dynamics, rigid contacts, 5 substeps)" if dyn_plant else "wbc_plant_step"),
                            "instances_per_gpu": n, "global_batch": total, "parallelism": "shard%d" % world, "l2": "not flushed (a rollout keeps its state warm)",
                            "scaling_note": "fixed grid sharded over the ranks (strong scaling); one step = one closed-loop cycle of every instance",
                            "solver_launch": "%d persistent one-warp CTAs (%d per SM), %d B shared memory each" % (grid_ctas, occ, smem)},

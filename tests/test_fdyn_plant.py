@@ -255,3 +255,29 @@ def test_closed_loop_trot_under_pushes_through_the_dynamics_plant(gpu_batch, hav
     assert np.abs(pos - base0).max() < 0.08 and np.abs(rpy - sc["base_rpy"]).max() < 0.15 and np.abs(vel).max() < 1.0
     if have_ref:
         assert checked > 900 and worst_tau < 1e-6
+
+
+def test_oracle_closed_loop_through_the_dynamics_plant_estimates_the_push(oracle, have_ref):
+    """BASELINE config 5 through the forward-dynamics plant (bench.py --workload push_sweep --plant dynamics), on the oracle: robots
+    holding their pose under a constant horizontal push.  The estimate settles on the push in x and y; in z it settles on
+    m (g_acc - |gravity|) = +0.21 N, the reference's two gravity constants (9.81 in estimate(), main.cpp:702; 9.8 in the dynamics,
+    main.cpp:855 -- quirk E1) showing through a plant that, unlike the momentum integrator, does not share the observer's."""
+    sc = S.push_sweep(n=256 * 8 * 2, start=0)
+    idx = np.array([256 * 5, 256 * 5 + 1, 256 * 8 + 256 * 5, 256 * 8 + 256 * 5 + 7])          # gain 50; 5 N and 10 N
+    sub = {k: (v[..., idx] if isinstance(v, np.ndarray) else v) for k, v in sc.items() if k != "grid"}
+    assert (sub["obs_gain"] == 50.0).all()
+    com0, _ = S.forward_kinematics(sub["base_pos"], sub["base_rot"], sub["q"])
+    sub["com_des_pos"] = np.vstack([com0.T, sub["base_rpy"]])
+    push = sub["push"]
+    for c in range(160):
+        res, _ = oracle.run_cycle_batch_gains(sub)
+        assert (res["status"] == 0).all()
+        sub["obs_yd"], sub["obs_yw"] = res["yd"].T.copy(), res["yw"].T.copy()
+        nxt, diag = oracle.fdyn_step(sub, res["tau"].T, push, nsub=5, gamma=100.0)
+        assert diag[:, 1].min() > 0.0
+        for k in ("base_pos", "base_rot", "base_rpy", "base_vel", "q", "dq", "foot_force"):
+            sub[k] = nxt[k]
+    w = res["w"].T
+    assert np.abs(w[:2] - push[:2]).max() < 0.05                               # k = 50: e^-20 of the push is left, plus the robot's sway
+    assert np.abs(w[2] - S.TOTAL_MASS * (9.81 - 9.8)).max() < 0.02
+    assert np.abs(sub["base_pos"] - sc["base_pos"][:, idx]).max() < 0.01
