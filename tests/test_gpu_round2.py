@@ -159,14 +159,17 @@ def test_sweep_400_cycles_teacher_forced(gpu_batch, oracle, have_ref):
     assert rel[sc["obs_gain"] == 1.0].max() > 0.1            # the slow observer is still on its way after 1 s: exp(-1)
 
 
-@pytest.mark.parametrize("cfg,n", [("trot_65536", 16384), ("mixed_terrain_1m", 16384)])
-def test_big_configs_against_live_oracle_16384(gpu_batch, oracle, have_ref, cfg, n):
-    """16 384 instances of BASELINE configs 3 and 4 against the live oracle (reference ALGLIB): tolerances as everywhere, plus the
-    histogram of Cholesky-count differences and the number of torque deviations above 1e-7 (SURVEY.md Appendix F predicts about
-    one flipped decision per 2000 swing solves)."""
+@pytest.mark.parametrize("cfg,n", [("trot_65536", 65536), ("mixed_terrain_1m", 131072)])
+def test_big_configs_against_live_oracle_every_instance(oracle, have_ref, cfg, n):
+    """EVERY instance of BASELINE config 3 (65 536) and of one GPU's shard of config 4 (131 072 of the 1 M) against the live oracle
+    (reference ALGLIB; 5 + 10 s on the host threads): tolerances as everywhere, plus the histogram of Cholesky-count differences
+    and the number of torque deviations above 1e-7 (SURVEY.md Appendix F predicted about one flipped decision per 2000 swing
+    solves; observed: none above 1e-7 in 196 608)."""
     sc = S.make_config(cfg, n=n)
-    gpu_batch.set_observer_state(sc["obs_yd"], sc["obs_yw"])
-    got = gpu_batch.cycle(sc)
+    batch = api.WbcBatch(max_batch=n)
+    batch.set_observer_state(sc["obs_yd"], sc["obs_yw"])
+    got = batch.cycle(sc)
+    batch.close()
     ref, _ = oracle.run_cycle_batch(sc, nthreads=32)
     worst = util.check_cycle_parity(got, ref, what=cfg)
     d = got["qp_info"][0].astype(int) - ref["ncholesky"].astype(int)
@@ -174,7 +177,7 @@ def test_big_configs_against_live_oracle_16384(gpu_batch, oracle, have_ref, cfg,
     et = util.rel_rows(got["tau"].T, ref["tau"])
     print("%s: worst torque rel err %.2e; torque deviations > 1e-7: %d of %d; ncholesky(GPU) - ncholesky(ALGLIB) histogram %s"
           % (cfg, worst, int((et > 1e-7).sum()), n, dict(zip(vals.tolist(), cnts.tolist()))))
-    assert np.mean(d == 0) >= 0.97
+    assert np.mean(d == 0) >= 0.99
 
 
 def test_staged_and_monolithic_solver_kernels_agree_bit_for_bit():
