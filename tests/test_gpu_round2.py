@@ -110,9 +110,9 @@ def test_update_stage_fgrf_and_wcom_des_match_oracle(gpu_batch, oracle, have_ref
 
 
 def test_trot_rollout_matches_oracle_every_cycle(gpu_batch, oracle, have_ref):
-    """256 robots x 184 cycles of the evolving-state herd (contact modes flip, active sets drift, pushes come and go): the
+    """1024 robots x 184 cycles of the evolving-state herd (contact modes flip, active sets drift, pushes come and go): the
     GPU runs free with its observer state in the ctx, the oracle runs free with its own; torques 1e-6, w 1e-9 every cycle."""
-    n, cycles = 256, 184
+    n, cycles = 1024, 184
     gpu_batch.set_observer_state(np.zeros((6, n)), np.zeros((6, n)))
     yd, yw = np.zeros((6, n)), np.zeros((6, n))
     worst, flips, nch_equal = 0.0, 0, []
@@ -121,7 +121,7 @@ def test_trot_rollout_matches_oracle_every_cycle(gpu_batch, oracle, have_ref):
         sc = S.trot_rollout(n, t)
         got = gpu_batch.cycle(sc)
         ref_in = dict(sc, obs_yd=yd, obs_yw=yw)
-        ref, _ = oracle.run_cycle_batch(ref_in, nthreads=16)
+        ref, _ = oracle.run_cycle_batch(ref_in, nthreads=32)
         worst = max(worst, util.check_cycle_parity(got, ref, what="rollout cycle %d" % t))
         yd, yw = np.ascontiguousarray(ref["yd"].T), np.ascontiguousarray(ref["yw"].T)
         nch_equal.append(np.mean(got["qp_info"][0] == ref["ncholesky"]))
