@@ -262,3 +262,32 @@ def test_full_size_properties_config4_shard_131072():
             assert (np.abs((t2 * fv).sum(axis=0)) <= mu * fn + 1e-2).all()
     finally:
         b.close()
+
+
+def test_config4_whole_on_one_gpu_equals_its_shards():
+    """Maximum size: ALL 1 048 576 instances of BASELINE config 4 in one batch on one GPU (the configuration names 8 GPUs; one has the
+    memory for it).  Every instance is solved, and what a rank of the 8-GPU run computes for its shard -- the same instances
+    generated from their offset, solved in a batch of 131 072 -- is bit for bit what the whole batch gives at those indices:
+    sharding changes who computes an instance and with which neighbours, nothing else."""
+    n = 1 << 20
+    sc = S.make_config("mixed_terrain_1m", n=n)
+    b = api.WbcBatch(max_batch=n, device=0)
+    try:
+        got = _run(b, sc)
+        assert (got["status"] == 0).all()
+        assert np.isfinite(got["tau"]).all() and np.isfinite(got["w"]).all()
+        assert np.abs(got["tau"][:, sc["mode"] == 0]).max() <= 60.0 * (1 + 1e-3)
+    finally:
+        b.close()
+    for rank in (0, 5):
+        lo = rank * 131072
+        part = S.make_config("mixed_terrain_1m", n=131072, start=lo)
+        for k in ("q", "base_vel", "terrain", "mode"):
+            assert np.array_equal(part[k], sc[k][..., lo:lo + 131072]), k          # the generator is offset-addressable
+        bs = api.WbcBatch(max_batch=131072, device=0)
+        try:
+            sub = _run(bs, part)
+        finally:
+            bs.close()
+        for k in ("tau", "w", "x"):
+            assert np.array_equal(sub[k], got[k][:, lo:lo + 131072]), (rank, k)
