@@ -54,7 +54,8 @@ extern "C" {
 #define WBC_NO_SYNC 2u           /* (device pointers only) return after enqueueing on the stream */
 #define WBC_FIFO_DISPATCH 4u     /* wbc_cycle: hand instances to the solver warps in index order.  Default: longest solve first,
                                     predicted from each instance's previous cycle on this ctx with the same n (the ctx keeps a
-                                    per-instance duration); the order never changes a result, only when the batch's tail ends. */
+                                    per-instance cost: the solve's duration, or its flop count where small batches run with
+                                    express lanes); the order never changes a result, only when the batch's tail ends. */
 #define WBC_SAMPLED_TRAJ 16u     /* wbc_cycle: com_des_* and sw_des_* come from the last wbc_sample_trajectory(out = NULL) on this ctx;
                                   * those six wbc_inputs pointers are ignored (may be NULL) and are not copied from the host */
 #define WBC_HOST_SLAB 8u         /* (host pointers) the input arrays are carved, in wbc_inputs field order, from ONE page-locked
