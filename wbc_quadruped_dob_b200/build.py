@@ -9,7 +9,12 @@ LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libwbc_b200.so")
 SOURCES = ["wbc_b200.cu"]
 HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [os.path.join("..", "..", "include", "wbc_b200.h")]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+# -maxrregcount: the kernels carry __launch_bounds__, which overrides it for the entry functions (ptxas still reports 168 / 255
+# registers for them); what it caps is the register budget of the separately compiled device functions the solver calls (symv,
+# chol_build30, tri_solve30, the multiplier update ...).  Measured on B200, interleaved A/B of variant builds on one box
+# (profiles/r02_al_maxrregcount_ab.txt): any cap from 112 to 160 takes the 4 096-instance solver kernel from 3.18 to 3.01 ms
+# (+5.5 % solves/s; 96 a little less), the 65 536-instance stage-task kernel is unchanged within +-0.5 %; results bit-identical.
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-maxrregcount=128",
               "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v", "-Wno-deprecated-gpu-targets"]
 
 
