@@ -851,6 +851,13 @@ int wbc_create(wbc_ctx** out, int device, int max_batch, const wbc_params* param
             if (c->solve_smem > 227 * 1024) c->solve_smem = 227 * 1024;
         }
     }
+    // L1 experiment knob: k resident solver warps per SM WITHOUT padding the request -- the shared-memory carve-out is set to what
+    // k CTAs need and the rest of the SM's 256 KB stays L1 (12 CTAs leave 28 KB of it; 8 leave 92 KB, 10 leave 60 KB)
+    int l1_ctas = 0;
+    if (const char* ev = getenv("WBC_SOLVE_L1_CTAS")) {
+        const int k = atoi(ev);
+        if (k >= 1 && k <= SOLVE_CTAS_PER_SM) { l1_ctas = k; per_sm = k; c->occ_forced = 1; c->solve_smem = sl::BYTES; }
+    }
     c->nblocks = c->sm_count * per_sm;
     // one scratch block per resident solver warp a launch can use (a launch never has more CTAs than instances)
     const long nteams = c->nblocks < max_batch ? c->nblocks : max_batch;
@@ -928,6 +935,11 @@ int wbc_create(wbc_ctx** out, int device, int max_batch, const wbc_params* param
     TRY(cudaFuncSetAttribute(wbc_dense_qp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->solve_smem));
     TRY(cudaFuncSetAttribute(wbc_solve_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     TRY(cudaFuncSetAttribute(wbc_dense_qp_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    if (l1_ctas > 0) {
+        const int pct = (int)((100L * l1_ctas * (sl::BYTES + 1024) + 228 * 1024 - 1) / (228 * 1024));
+        TRY(cudaFuncSetAttribute(wbc_solve_staged_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct));
+        TRY(cudaFuncSetAttribute(wbc_solve_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct));
+    }
     if (e == cudaSuccess) {
         // the persistent grid is exactly the resident CTAs: more would queue behind whole solves
         int occ = 0;
@@ -938,6 +950,7 @@ int wbc_create(wbc_ctx** out, int device, int max_batch, const wbc_params* param
         if (e == cudaSuccess && occ >= 1) {
             c->occ_per_sm = occ;
             if (c->nblocks > c->sm_count * occ) c->nblocks = c->sm_count * occ;
+            if (l1_ctas > 0 && l1_ctas < occ) c->occ_per_sm = l1_ctas;
         }
     }
 #undef TRY
