@@ -264,6 +264,24 @@ struct HostEx {
     WBC_HD void copy_wait() const {}
 };
 #if defined(__CUDACC__)
+// Bulk copy global -> shared with cp.async (LDGSTS): every element is in flight at once, one L2 round trip for the
+// whole block instead of one per unrolled group of register-staged loads (ncu: these copies were 10 % of the
+// kernel's stall samples at 0.6 % of its instructions).  8-byte granules: rows have an odd leading dimension.
+__device__ __forceinline__ void warp_copy_start(unsigned dst_shared, const double* __restrict__ src, int n)
+{
+    const int l = threadIdx.x & 31;
+    unsigned d = dst_shared + 8u * l;
+    const double* g = src + l;
+#pragma unroll 4
+    for (int e = l; e < n; e += 32, d += 256u, g += 32)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(g) : "memory");
+}
+// ONE shared, non-inlined copy of that loop for the stage-task kernel: it has 16 call sites (45 instructions each when
+// inlined, 12 KB in all), every one of them in once-per-task code, and once-per-task code is what that kernel's instruction
+// cache misses on (profiles/r02_ar_icache_misses_by_sm.txt).  Measured (profiles/r02_as_shared_copy_ab.txt): -2.7 % on the
+// stage-task kernel at 65 536 instances; the one-warp-per-solve kernel at 4 096 instances LOSES 2.8 % with it, so it keeps
+// the inlined form (WarpEx) and the stage-task kernel runs on WarpExS.
+__device__ __noinline__ void warp_copy_start_ni(unsigned dst_shared, const double* __restrict__ src, int n) { warp_copy_start(dst_shared, src, n); }
 struct WarpEx {
     static constexpr int NL = 32;
     __device__ __forceinline__ int lane() const { return threadIdx.x & 31; }
@@ -274,33 +292,34 @@ struct WarpEx {
     __device__ __forceinline__ unsigned ballot(bool p) const { return __ballot_sync(0xffffffffu, p); }
     __device__ __forceinline__ int popc_below(unsigned m) const { return __popc(m & ((1u << (threadIdx.x & 31)) - 1u)); }
     __device__ __forceinline__ int popc(unsigned m) const { return __popc(m); }
-    // Bulk copy global -> shared with cp.async (LDGSTS): every element is in flight at once, one L2 round trip for the
-    // whole block instead of one per unrolled group of register-staged loads (ncu: these copies were 10 % of the
-    // kernel's stall samples at 0.6 % of its instructions).  8-byte granules: rows have an odd leading dimension.
     __device__ __forceinline__ void copy_in(double* dst, const double* src, int n) const
     {
-        const int l = threadIdx.x & 31;
-        unsigned d = (unsigned)__cvta_generic_to_shared(dst) + 8u * l;
-        const double* g = src + l;
-#pragma unroll 4
-        for (int e = l; e < n; e += 32, d += 256u, g += 32)
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(g) : "memory");
+        warp_copy_start((unsigned)__cvta_generic_to_shared(dst), src, n);
         asm volatile("cp.async.wait_all;" ::: "memory");
         __syncwarp();
     }
+    // several copies in flight at once: copy_start ... copy_start, then one copy_wait
     __device__ __forceinline__ void copy_start(double* dst, const double* src, int n) const
     {
-        const int l = threadIdx.x & 31;
-        unsigned d = (unsigned)__cvta_generic_to_shared(dst) + 8u * l;
-        const double* g = src + l;
-#pragma unroll 4
-        for (int e = l; e < n; e += 32, d += 256u, g += 32)
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(g) : "memory");
+        warp_copy_start((unsigned)__cvta_generic_to_shared(dst), src, n);
     }
     __device__ __forceinline__ void copy_wait() const
     {
         asm volatile("cp.async.wait_all;" ::: "memory");
         __syncwarp();
+    }
+};
+// the stage-task kernel's executor: the same warp, bulk copies through the shared routine
+struct WarpExS : WarpEx {
+    __device__ __forceinline__ void copy_in(double* dst, const double* src, int n) const
+    {
+        warp_copy_start_ni((unsigned)__cvta_generic_to_shared(dst), src, n);
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncwarp();
+    }
+    __device__ __forceinline__ void copy_start(double* dst, const double* src, int n) const
+    {
+        warp_copy_start_ni((unsigned)__cvta_generic_to_shared(dst), src, n);
     }
 };
 #endif
@@ -1953,7 +1972,8 @@ WBC_HD int model_and_qqp(const Ex& ex, const Work& w, int nec, int nicwork, doub
 }
 #if defined(__CUDACC__)
 // device, shared-memory case: the register-resident QQP (the generic one is not instantiated: its vectors do not exist there)
-__device__ __forceinline__ int model_and_qqp_dev(const WarpEx& ex, const Work& w, int nec, int nicwork, double rho, double epsx,
+template <class Ex>
+__device__ __forceinline__ int model_and_qqp_dev(const Ex& ex, const Work& w, int nec, int nicwork, double rho, double epsx,
                                                  int* ncholesky, double* flops, int* reused)
 {
     generate_ex_model<false>(ex, w, nec, nicwork, rho);
@@ -2354,7 +2374,8 @@ WBC_HDN int stage_post_and_model(const Ex& ex, const Work& w, const Settings& cf
 }
 #if defined(__CUDACC__)
 // The QQP task: stage the model (one cp.async round trip), iterate, leave the point in EXXC for stage_store.
-__device__ __forceinline__ void stage_qqp(const WarpEx& ex, const Work& w, SolveState& s)
+template <class Ex>
+__device__ __forceinline__ void stage_qqp(const Ex& ex, const Work& w, SolveState& s)
 {
     const int nic2 = (s.nicwork + 1) & ~1;
     ex.copy_start(W_H(w), w.g + gl::OFF_HQ, NMAIN * LDH);

@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(SOLVE_T) wbc_solve_staged_kernel(Params P, int
     w.g = nullptr;
     w.kkt = kkt_base + (long)blockIdx.x * gl::KKT_DOUBLES;
     w.sm = nullptr;
-    const WarpEx ex;
+    const WarpExS ex;                                              // bulk copies through the shared routine (qp_warp.cuh)
     Settings cfg;
     cfg.epsx = P.qp_epsx; cfg.rho = P.qp_rho; cfg.outerits = P.qp_outerits; cfg.kkt_mode = P.qp_literal_kkt ? 0 : 1;
     for (int k = ex.lane(); k < sl::TOTAL; k += SOLVE_T) WBC_SM(w)[k] = 0.0;
