@@ -19,17 +19,77 @@ namespace fast {
 
 // Code size is a first-order cost here: ncu shows the SM instruction cache hit rate at 60 % and the GPC-level
 // instruction cache at half of its peak request rate when every warp of an SM runs a different phase of a
-// 200 KB kernel.  So loops are not unrolled unless they are the product itself, divisions / square roots /
-// reductions are shared non-inlined helpers, and maxima / arg-minima use the warp REDUX unit on the bit
-// patterns (exact for non-negative doubles).
+// 200 KB kernel.  So loops are not unrolled unless they are the product itself, and maxima / arg-minima use the
+// warp REDUX unit on the bit patterns (exact for non-negative doubles).
+// Which routines are separate functions.  Round 1 made every routine of the QQP a non-inlined function to keep the kernel small (the
+// one-warp-per-solve kernel was instruction-fetch bound with everything inlined).  With SM roles, express lanes and the later diets the
+// balance moved: inlining the routines that have ONE call site (no code growth, no call, no register hand-over at the call) and the
+// small shared helpers (warp sum / max, square root, division: qp_warp.cuh WBC_SMALL_NI) is worth 4.6 % at 4 096 instances, 5 % on the
+// single robot and 5.1 % at 65 536 instances, bit-identical (profiles/r02_aw_inlining_ab.txt).  -DWBC_OUTLINE_<NAME> restores a call,
+// -DWBC_INLINE_<NAME> inlines one of the routines that are still calls (A/B experiments).
+#ifdef WBC_OUTLINE_CHOL_BUILD30
+#define WBC_NI_CHOL_BUILD30 __noinline__
+#else
+#define WBC_NI_CHOL_BUILD30 __forceinline__
+#endif
+#ifdef WBC_OUTLINE_TRI_SOLVE30
+#define WBC_NI_TRI_SOLVE30 __noinline__
+#else
+#define WBC_NI_TRI_SOLVE30 __forceinline__
+#endif
+#ifdef WBC_OUTLINE_RANK1_FIX30
+#define WBC_NI_RANK1_FIX30 __noinline__
+#else
+#define WBC_NI_RANK1_FIX30 __forceinline__
+#endif
+#ifdef WBC_OUTLINE_NEWTON_DIRECTION
+#define WBC_NI_NEWTON_DIRECTION __noinline__
+#else
+#define WBC_NI_NEWTON_DIRECTION __forceinline__
+#endif
+#ifdef WBC_OUTLINE_NEWTON_DIAG
+#define WBC_NI_NEWTON_DIAG __noinline__
+#else
+#define WBC_NI_NEWTON_DIAG __forceinline__
+#endif
+#ifdef WBC_INLINE_EVAL4
+#define WBC_NI_EVAL4 __forceinline__
+#else
+#define WBC_NI_EVAL4 __noinline__
+#endif
+#ifdef WBC_INLINE_QUADRATIC_MODEL
+#define WBC_NI_QUADRATIC_MODEL __forceinline__
+#else
+#define WBC_NI_QUADRATIC_MODEL __noinline__
+#endif
+#ifdef WBC_INLINE_EXPLORE
+#define WBC_NI_EXPLORE __forceinline__
+#else
+#define WBC_NI_EXPLORE __noinline__
+#endif
+#ifdef WBC_INLINE_STEP_AND_MOVE
+#define WBC_NI_STEP_AND_MOVE __forceinline__
+#else
+#define WBC_NI_STEP_AND_MOVE __noinline__
+#endif
+#ifdef WBC_INLINE_SYMV
+#define WBC_NI_SYMV __forceinline__
+#else
+#define WBC_NI_SYMV __noinline__
+#endif
+#ifdef WBC_INLINE_QQP_OPTIMIZE_FAST
+#define WBC_NI_QQP_OPTIMIZE_FAST __forceinline__
+#else
+#define WBC_NI_QQP_OPTIMIZE_FAST __noinline__
+#endif
 constexpr unsigned FULL = 0xffffffffu;
 
 __device__ __forceinline__ double bshfl(double v, int src) { return __shfl_sync(FULL, v, src); }
 __device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
-__device__ __noinline__ double ddiv(double a, double b) { return a / b; }
+__device__ WBC_SMALL_NI double ddiv(double a, double b) { return a / b; }
 __device__ __forceinline__ double dsqrt(double a) { return dsqrt_ni(a); }
 // warp sum, every lane gets the same bits
-__device__ __forceinline__ double wsum(double v) { return warp_sum_ni(v); }      // one shared copy of the butterfly (unrolled inside)
+__device__ __forceinline__ double wsum(double v) { return warp_sum_ni(v); }      // the butterfly (unrolled inside)
 // warp maximum of non-negative doubles (bit patterns order like the values)
 __device__ __forceinline__ double wmax_nn(double v)
 {
@@ -41,7 +101,7 @@ __device__ __forceinline__ double wmax_nn(double v)
 
 // y = E x for the vector mirrored at `x` (shared, 16-byte aligned, entries >= n finite).  Returns slot A / slot B parts.
 // nic2 = nic rounded up to even; rows [nic, nic2) of CI are zero.
-__device__ __noinline__ double2 symv(const double* __restrict__ x, int nic2, double rho)
+__device__ WBC_NI_SYMV double2 symv(const double* __restrict__ x, int nic2, double rho)
 {
     const int l = threadIdx.x & 31;
     const double* H = wbc_smem + sl::OFF_H + l;             // column walk of row l (H symmetric)
@@ -73,7 +133,7 @@ __device__ __noinline__ double2 symv(const double* __restrict__ x, int nic2, dou
 // The candidates are broadcast from shared memory, interleaved four to an entry: the 30 main entries overlay the mirrors
 // of x and d (and the head of EXB), the slack entries overlay EXXC -- all four are dead here (x, exb and the point of the
 // extended model live in registers during a QQP call, d is rewritten before its next use); the CALLER restores the mirror of x.
-__device__ __noinline__ void eval4(double xcA, double xcB, double dA, double dB, double exbA, double exbB, int nic, double rho, double s0,
+__device__ WBC_NI_EVAL4 void eval4(double xcA, double xcB, double dA, double dB, double exbA, double exbB, int nic, double rho, double s0,
                                   double s1, double s2, double s3)
 {
     const int l = threadIdx.x & 31;
@@ -165,7 +225,7 @@ static_assert(sl::Z_DOUBLES >= 480, "pair-interleaved 30 x 30 factor");
 
 // rsB: 1/sqrt(d_k) of slack lane k (0 when the variable is not free); diagA: regularised diagonal of main variable `lane`.
 // Returns false on a non-positive pivot.
-__device__ __noinline__ bool chol_build30(double diagA, double rsB, unsigned fmask)
+__device__ WBC_NI_CHOL_BUILD30 bool chol_build30(double diagA, double rsB, unsigned fmask)
 {
     const int l = threadIdx.x & 31;
     double* Z = wbc_smem + sl::OFF_Z;
@@ -230,7 +290,7 @@ __device__ __noinline__ bool chol_build30(double diagA, double rsB, unsigned fma
 // Two columns per step: both pivot components are broadcast at once and the second one is finished redundantly by every
 // lane (y_{k+1} = (x_{k+1} - U_{k,k+1} y_k) / U_{k+1,k+1}), so the dependent chain is one shuffle per two columns instead
 // of one per column.  The operations on every component are the ones of the one-column sweep, in the same order.
-__device__ __noinline__ void tri_solve30(double* x)
+__device__ WBC_NI_TRI_SOLVE30 void tri_solve30(double* x)
 {
     const int l = threadIdx.x & 31;
     const double* Z = wbc_smem + sl::OFF_Z;
@@ -273,7 +333,7 @@ __device__ __noinline__ void tri_solve30(double* x)
 }
 
 // U'U <- U'U + T_k T_k'  (slack variable k leaves the free set)
-__device__ __noinline__ void rank1_fix30(int k)
+__device__ WBC_NI_RANK1_FIX30 void rank1_fix30(int k)
 {
     const int l = threadIdx.x & 31;
     double* Z = wbc_smem + sl::OFF_Z;
@@ -307,7 +367,7 @@ __device__ __noinline__ void rank1_fix30(int k)
 
 // Newton direction from the gradient (two-slot registers; gB already zeroed on fixed slack variables, winvB = 1/d_k on the
 // free ones and 0 elsewhere).  The direction is written to the mirror `sdc` (main and slack part, pad entry untouched).
-__device__ __noinline__ void newton_direction(double gA, double gB, double winvB, unsigned freemask, int nic)
+__device__ WBC_NI_NEWTON_DIRECTION void newton_direction(double gA, double gB, double winvB, unsigned freemask, int nic)
 {
     const int l = threadIdx.x & 31;
     double* sdc = wbc_smem + sl::OFF_DC;
@@ -354,7 +414,7 @@ __device__ __forceinline__ double red1(double a)
 
 // qqpsolver_quadraticmodel (opt.cpp:30753-30821) on two-slot registers.  d is mirrored at DC.  Returns the packed sign
 // estimates (see estimateparabolicmodel); d1, d2 are left in SP[4..5].
-__device__ __noinline__ int quadratic_model(double dA, double dB, double gA, double gB, double xcA, double xcB, int nic2, double rho,
+__device__ WBC_NI_QUADRATIC_MODEL int quadratic_model(double dA, double dB, double gA, double gB, double xcA, double xcB, int nic2, double rho,
                                             double absasum, double absasum2, double mb)
 {
     const double2 ed = symv(wbc_smem + sl::OFF_DC, nic2, rho);
@@ -377,7 +437,7 @@ __device__ __noinline__ int quadratic_model(double dA, double dB, double gA, dou
 
 // sasexploredirection (opt.cpp:27433-27528) on slot B registers (see sas_explore_direction in qp_warp.cuh).
 // Returns cidx (-1: no blocking bound); the step is left in SP[6].
-__device__ __noinline__ int explore(double xcB, double dB, int candB)
+__device__ WBC_NI_EXPLORE int explore(double xcB, double dB, int candB)
 {
     const int l = threadIdx.x & 31;
     double best = BIGSTEP;
@@ -406,7 +466,7 @@ __device__ __noinline__ int explore(double xcB, double dB, int candB)
 // (step to the bound); 2: the Newton phase's bound step with candidates {4 stpmax, 1, 0.25}.
 // Returns the new cstatus of slot B; SP[7] gets the number of extra model evaluations.  (The trial points of eval4 overlay
 // the mirror of x, which is read before and rewritten after.)
-__device__ __noinline__ int step_and_move(double dA, double dB, double exbA, double exbB, int nic, double rho, int mode, int cidx, int csB)
+__device__ WBC_NI_STEP_AND_MOVE int step_and_move(double dA, double dB, double exbA, double exbB, int nic, double rho, int mode, int cidx, int csB)
 {
     const int l = threadIdx.x & 31;
     double* xs = wbc_smem + sl::OFF_XC;
@@ -492,7 +552,7 @@ __device__ __noinline__ void qqp_stats(int nic, double rho, double exbA, double 
 
 // Diagonal of the constrained-Newton model with its regulariser 1e-9 * sum_j |A_ff[i][j]| over free j (opt.cpp:31150-31167),
 // in two-slot form; fixed variables get 1.  fmask: ballot of the free slack variables.
-__device__ __noinline__ double2 newton_diag(int nic, double rho, unsigned fmask)
+__device__ WBC_NI_NEWTON_DIAG double2 newton_diag(int nic, double rho, unsigned fmask)
 {
     const int l = threadIdx.x & 31;
     const double* H = wbc_smem + sl::OFF_H;
@@ -522,7 +582,7 @@ __device__ __noinline__ double2 newton_diag(int nic, double rho, unsigned fmask)
 
 // One QQP solve from the point exxc (in/out) on the model (H, CI, rho, exb).  Returns the QQP termination type.
 // pre_stats: the model's (absasum, absasum2, max|exb|) when the caller has them already (stage tasks), else NULL.
-__device__ __noinline__ int qqp_optimize_fast(const Work w, int nic, double rho, double epsx, int maxouterits, int* ncholesky, double* flops_io, int* reused_io,
+__device__ WBC_NI_QQP_OPTIMIZE_FAST int qqp_optimize_fast(const Work w, int nic, double rho, double epsx, int maxouterits, int* ncholesky, double* flops_io, int* reused_io,
                                               const double* pre_stats)
 {
     const int l = threadIdx.x & 31;

@@ -40,6 +40,13 @@
 #define WBC_HD __host__ __device__ __forceinline__
 #define WBC_HDN __host__ __device__
 #define WBC_HDNI __host__ __device__ __noinline__
+// the small shared helpers (warp sum / max, square root, division): inlined (qp_fast.cuh, "Which routines are separate functions");
+// -DWBC_SMALL_OUTLINE makes them calls again
+#ifdef WBC_SMALL_OUTLINE
+#define WBC_SMALL_NI __noinline__
+#else
+#define WBC_SMALL_NI __forceinline__
+#endif
 #else
 #define WBC_HD inline
 #define WBC_HDN
@@ -324,16 +331,16 @@ struct WarpExS : WarpEx {
 };
 #endif
 // all-reduce by butterflies: every lane ends with bit-identical results (IEEE add / max are commutative).
-// On the device the butterfly is one shared, rolled, non-inlined routine: the solver is instruction-fetch bound
+// On the device the butterfly is one routine (WBC_SMALL_NI: inlined since round 2, a call before): the solver is instruction-fetch bound
 // (DESIGN.md 4.2), and an inlined 5-step double-precision butterfly is 25 instructions at each of ~60 call sites.
 #if defined(__CUDACC__)
-__device__ __noinline__ double warp_sum_ni(double v)
+__device__ WBC_SMALL_NI double warp_sum_ni(double v)
 {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
-__device__ __noinline__ double warp_max_ni(double v)
+__device__ WBC_SMALL_NI double warp_max_ni(double v)
 {
 #pragma unroll 1
     for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -411,8 +418,8 @@ WBC_HD void generaterotation(double f, double g, double& cs, double& sn, double&
     if (fabs(f) > fabs(g) && cs < 0.0) { cs = -cs; sn = -sn; r = -r; }
 }
 #if defined(__CUDACC__)
-// one shared copy of the double-precision square root (an inlined one is ~30 instructions; code size is what this solver pays for)
-__device__ __noinline__ double dsqrt_ni(double a) { return sqrt(a); }
+// the double-precision square root (WBC_SMALL_NI: inlined since round 2; as a shared call it saved ~30 instructions per site)
+__device__ WBC_SMALL_NI double dsqrt_ni(double a) { return sqrt(a); }
 #endif
 WBC_HD double sqrt_shared(double a)
 {
