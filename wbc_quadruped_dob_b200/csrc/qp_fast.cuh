@@ -21,12 +21,14 @@ namespace fast {
 // instruction cache at half of its peak request rate when every warp of an SM runs a different phase of a
 // 200 KB kernel.  So loops are not unrolled unless they are the product itself, and maxima / arg-minima use the
 // warp REDUX unit on the bit patterns (exact for non-negative doubles).
-// Which routines are separate functions.  Round 1 made every routine of the QQP a non-inlined function to keep the kernel small (the
-// one-warp-per-solve kernel was instruction-fetch bound with everything inlined).  With SM roles, express lanes and the later diets the
-// balance moved: inlining the routines that have ONE call site (no code growth, no call, no register hand-over at the call) and the
-// small shared helpers (warp sum / max, square root, division: qp_warp.cuh WBC_SMALL_NI) is worth 4.6 % at 4 096 instances, 5 % on the
-// single robot and 5.1 % at 65 536 instances, bit-identical (profiles/r02_aw_inlining_ab.txt).  -DWBC_OUTLINE_<NAME> restores a call,
-// -DWBC_INLINE_<NAME> inlines one of the routines that are still calls (A/B experiments).
+// Which routines are separate functions.  Round 1 made every routine of the solver a non-inlined function to keep the kernel small (the
+// one-warp-per-solve kernel was instruction-fetch bound with everything inlined, and its hot code was twice today's).  With SM roles,
+// express lanes and the later diets the balance moved, and a call is expensive in a 168-register kernel (live values handed over or
+// spilled at every call, no scheduling across it).  Measured in three rounds of interleaved A/B builds, all bit-identical
+// (profiles/r02_aw_inlining_ab.txt): everything on the QQP path inlined except the product `symv` (five call sites; inlined it is
+// +0.3 % / -1 %), plus the small helpers and the model / working-set / multiplier-update / set-up routines of qp_warp.cuh
+// (WBC_SMALL_NI, WBC_HDNI_G, WBC_HDNI_M):  4 096 instances 3.02 -> 2.44 ms, 65 536 instances 37.7 -> 32.3 ms.
+// -DWBC_OUTLINE_<NAME> restores a call, -DWBC_INLINE_SYMV inlines the product (A/B experiments).
 #ifdef WBC_OUTLINE_CHOL_BUILD30
 #define WBC_NI_CHOL_BUILD30 __noinline__
 #else
@@ -52,35 +54,35 @@ namespace fast {
 #else
 #define WBC_NI_NEWTON_DIAG __forceinline__
 #endif
-#ifdef WBC_INLINE_EVAL4
-#define WBC_NI_EVAL4 __forceinline__
-#else
+#ifdef WBC_OUTLINE_EVAL4
 #define WBC_NI_EVAL4 __noinline__
-#endif
-#ifdef WBC_INLINE_QUADRATIC_MODEL
-#define WBC_NI_QUADRATIC_MODEL __forceinline__
 #else
+#define WBC_NI_EVAL4 __forceinline__
+#endif
+#ifdef WBC_OUTLINE_QUADRATIC_MODEL
 #define WBC_NI_QUADRATIC_MODEL __noinline__
-#endif
-#ifdef WBC_INLINE_EXPLORE
-#define WBC_NI_EXPLORE __forceinline__
 #else
+#define WBC_NI_QUADRATIC_MODEL __forceinline__
+#endif
+#ifdef WBC_OUTLINE_EXPLORE
 #define WBC_NI_EXPLORE __noinline__
-#endif
-#ifdef WBC_INLINE_STEP_AND_MOVE
-#define WBC_NI_STEP_AND_MOVE __forceinline__
 #else
+#define WBC_NI_EXPLORE __forceinline__
+#endif
+#ifdef WBC_OUTLINE_STEP_AND_MOVE
 #define WBC_NI_STEP_AND_MOVE __noinline__
+#else
+#define WBC_NI_STEP_AND_MOVE __forceinline__
+#endif
+#ifdef WBC_OUTLINE_QQP_OPTIMIZE_FAST
+#define WBC_NI_QQP_OPTIMIZE_FAST __noinline__
+#else
+#define WBC_NI_QQP_OPTIMIZE_FAST __forceinline__
 #endif
 #ifdef WBC_INLINE_SYMV
 #define WBC_NI_SYMV __forceinline__
 #else
 #define WBC_NI_SYMV __noinline__
-#endif
-#ifdef WBC_INLINE_QQP_OPTIMIZE_FAST
-#define WBC_NI_QQP_OPTIMIZE_FAST __forceinline__
-#else
-#define WBC_NI_QQP_OPTIMIZE_FAST __noinline__
 #endif
 constexpr unsigned FULL = 0xffffffffu;
 

@@ -40,6 +40,29 @@
 #define WBC_HD __host__ __device__ __forceinline__
 #define WBC_HDN __host__ __device__
 #define WBC_HDNI __host__ __device__ __noinline__
+// groups of routines that are inlined on the device since round 2 (qp_fast.cuh, "Which routines are separate functions");
+// -DWBC_OUTLINE_G / _M / _PARAB / _TSW make a group calls again.  G: generate_ex_model, update_working_set, inequality_violations,
+// feasibility_error; M: update_lagrange_multipliers_reduced, setup_problem; PARAB: estimateparabolicmodel; TSW: tri_solve_warp32.
+#ifdef WBC_OUTLINE_G
+#define WBC_HDNI_G WBC_HDNI
+#else
+#define WBC_HDNI_G __host__ __device__ __forceinline__
+#endif
+#ifdef WBC_OUTLINE_M
+#define WBC_HDNI_M WBC_HDNI
+#else
+#define WBC_HDNI_M __host__ __device__ __forceinline__
+#endif
+#ifdef WBC_OUTLINE_PARAB
+#define WBC_HDNI_PARAB WBC_HDNI
+#else
+#define WBC_HDNI_PARAB __host__ __device__ __forceinline__
+#endif
+#ifdef WBC_OUTLINE_TSW
+#define WBC_NI_TSW __noinline__
+#else
+#define WBC_NI_TSW __forceinline__
+#endif
 // the small shared helpers (warp sum / max, square root, division): inlined (qp_fast.cuh, "Which routines are separate functions");
 // -DWBC_SMALL_OUTLINE makes them calls again
 #ifdef WBC_SMALL_OUTLINE
@@ -51,6 +74,9 @@
 #define WBC_HD inline
 #define WBC_HDN
 #define WBC_HDNI
+#define WBC_HDNI_G
+#define WBC_HDNI_M
+#define WBC_HDNI_PARAB
 #endif
 
 namespace wbcqp {
@@ -430,7 +456,7 @@ WBC_HD double sqrt_shared(double a)
 #endif
 }
 // returns (d1est + 1) * 4 + (d2est + 1)
-WBC_HDNI int estimateparabolicmodel(double absasum, double absasum2, double mx, double mb, double md, double d1, double d2)
+WBC_HDNI_PARAB int estimateparabolicmodel(double absasum, double absasum2, double mx, double mb, double md, double d1, double d2)
 { // opt.cpp:23071-23131
     const double eps = 4 * MACHEPS;
     const double sq2 = sqrt_shared(absasum2);
@@ -627,7 +653,7 @@ WBC_HD void tri_solve_regs(const Ex& ex, const double* Z, int n, const double* z
 #if defined(__CUDACC__)
 // Device, n <= 32: one component per lane, both sweeps (same operations on the same operands as tri_solve_regs, without
 // its slot bookkeeping).  Dependent pivots (zrinv = 0) yield a zero component.
-__device__ __noinline__ void tri_solve_warp32(const double* Z, int n, const double* zrinv, double* x)
+__device__ WBC_NI_TSW void tri_solve_warp32(const double* Z, int n, const double* zrinv, double* x)
 {
     const int l = threadIdx.x & 31;
     const double* r0 = Z + zoff(l < n ? l : 0);
@@ -1359,7 +1385,7 @@ WBC_HD void tri_index_lower(int e, int& c, int& r)
 }
 
 template <class Ex>
-WBC_HDNI bool update_lagrange_multipliers_reduced(const Ex ex, const Work w, int nec, int nic, double pivtol, int* flags_io, double* flops_io)
+WBC_HDNI_M bool update_lagrange_multipliers_reduced(const Ex ex, const Work w, int nec, int nic, double pivtol, int* flags_io, double* flops_io)
 {
     const int ktotal = nec + nic;
     // Workspace (the QQP is not running, so everything but EXXC and the ints is free):
@@ -1660,7 +1686,7 @@ WBC_HD void tri_advance30(int& i, int& j, int step)
 }
 
 template <bool SPILL, class Ex>
-WBC_HDNI void generate_ex_model(const Ex ex, const Work w, int nec, int nic, double rho)
+WBC_HDNI_G void generate_ex_model(const Ex ex, const Work w, int nec, int nic, double rho)
 {
     const int n = NMAIN + nic, kw = nec + nic;
     double* H = W_H(w);
@@ -1743,7 +1769,7 @@ WBC_HDNI void generate_ex_model(const Ex ex, const Work w, int nec, int nic, dou
 // (arg-max by butterfly, ties to the lowest index like the reference's strict '>' scan).
 // Results: iscr[1] = new nicwork, iscr[2] = extended flag.
 template <class Ex>
-WBC_HDNI void update_working_set(const Ex ex, const Work w, int nec, int nictotal, int nicwork, int allowevict)
+WBC_HDNI_G void update_working_set(const Ex ex, const Work w, int nec, int nictotal, int nicwork, int allowevict)
 {
     const int l = ex.lane();
     double* nicerr = W_NICERR(w);
@@ -1826,7 +1852,7 @@ WBC_HDNI void update_working_set(const Ex ex, const Work w, int nec, int nictota
 // (42374-42446), selectinitialworkingset (42474-42523).  On entry: Q (lower triangle used, opt.cpp:4962/18959) in the H
 // array (ld 31), c in exb[0..30), L rows in the global C array.  Returns 0, or -9 for a non-positive diagonal.
 template <class Ex>
-WBC_HDNI int setup_problem(const Ex ex, const Work w, int nrows, int* pd_out, int dup0s, int dup0c, int dup1s, int dup1c)
+WBC_HDNI_M int setup_problem(const Ex ex, const Work w, int nrows, int* pd_out, int dup0s, int dup0c, int dup1s, int dup1c)
 {
     double* As = W_H(w);
     double* sc = W_SC(w);
@@ -2003,7 +2029,7 @@ WBC_HD const double* stage_rows(const Ex& ex, const Work& w, int row0, int nr)
 }
 // violations of all inequality rows w.r.t. the main variables only (opt.cpp:41330-41335)
 template <class Ex>
-WBC_HDNI void inequality_violations(const Ex ex, const Work w, int nec, int nictotal)
+WBC_HDNI_G void inequality_violations(const Ex ex, const Work w, int nec, int nictotal)
 {
     double* nicerr = W_NICERR(w);
     const double* exxc = W_EXXC(w);
@@ -2024,7 +2050,7 @@ WBC_HDNI void inequality_violations(const Ex ex, const Work w, int nec, int nict
 }
 // feasibility error over the working rows and the multiplier hand-over (opt.cpp:41444-41476); returns sum of squares
 template <class Ex>
-WBC_HDNI double feasibility_error(const Ex ex, const Work w, int nec, int kwork)
+WBC_HDNI_G double feasibility_error(const Ex ex, const Work w, int nec, int kwork)
 {
     const double* exxc = W_EXXC(w);
     double* nulc = W_NULC(w);
