@@ -874,10 +874,12 @@ int wbc_create(wbc_ctx** out, int device, int max_batch, const wbc_params* param
     TRY(cudaMemset(c->tau_prev, 0, nb * 12 * sizeof(double)));
     // Which solver kernel.  wbc_solve_kernel: one warp per solve.  wbc_solve_staged_kernel: stage tasks with SM roles -- the QQP
     // iteration (its hot code fits an SM's instruction cache) on three SM pairs of five, everything else on the other two.
-    // Measured on B200 (profiles/README.md, round 2): the staged kernel is 19 % faster at 65 536 instances (37.1 against 44.1 ms) and
+    // Measured on B200 (profiles/README.md, round 2): the staged kernel was 19 % faster at 65 536 instances (37.1 against 44.1 ms) and
     // slower at 4 096 (4.0 against 3.3 ms: a solve is eleven hand-overs and the batch is only 2.3 solves per warp), so the choice
-    // goes by batch size; WBC_SOLVER = mono | staged forces one, WBC_STAGED_MIN_N moves the threshold.
-    c->staged = 2; c->staged_min_n = 12288; c->m_period = (3 << 16) | (7 << 8) | 25; c->m_group = 2;     // of every 25 SM pairs: 3 SETUP, 7 POST, 15 QQP (0.5 % over 2 POST/SETUP in 5)
+    // goes by batch size; WBC_SOLVER = mono | staged forces one, WBC_STAGED_MIN_N moves the threshold.  After the inlining of the
+    // round's last step the one-warp-per-solve kernel gained more than the staged one and the crossover moved from 12 288 to
+    // ~49 152 instances (profiles/r02_az_crossover.txt: 24 576: 13.33 against 13.98 ms, 49 152: 25.05 / 24.99, 65 536: 33.03 / 32.33).
+    c->staged = 2; c->staged_min_n = 49152; c->m_period = (3 << 16) | (7 << 8) | 25; c->m_group = 2;     // of every 25 SM pairs: 3 SETUP, 7 POST, 15 QQP (0.5 % over 2 POST/SETUP in 5)
     if (const char* ev = getenv("WBC_SOLVER")) c->staged = strcmp(ev, "staged") == 0 ? 1 : (strcmp(ev, "mono") == 0 ? 0 : 2);
     if (const char* ev = getenv("WBC_STAGED_MIN_N")) c->staged_min_n = atoi(ev);
     c->front_leg = 1;
