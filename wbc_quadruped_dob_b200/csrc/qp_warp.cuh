@@ -9,9 +9,10 @@
 // per SM).  The design is driven by what ncu showed on the earlier CTA-per-instance version (profiles/):
 // the path is bound by instruction issue and instruction fetch, not by the FP64 pipe or by memory --
 // so every uniform scalar decision is executed once (one warp), there are no block barriers or
-// cross-warp reductions, the hot code is a handful of small non-inlined routines that fit the
-// instruction cache, and nothing is passed to them by reference (no local-memory traffic): storage is
-// addressed as constant offsets from the CTA's shared-memory base and from one global scratch pointer.
+// cross-warp reductions, and nothing is passed between routines by reference (no local-memory traffic):
+// storage is addressed as constant offsets from the CTA's shared-memory base and from one global scratch
+// pointer.  Which routines are calls and which are inlined was decided by measurement, twice: round 1 made
+// all of them calls (code size), round 2's last step inlined all but the product (qp_fast.cuh).
 // `HostEx` (one lane) lets the same source be compiled by g++ for CPU-side unit tests
 // (tests/host_emu); the shipped library only instantiates `WarpEx`.
 //
