@@ -1,5 +1,6 @@
-# A/B of compile-flag variants on top of -maxrregcount=128 (A), interleaved on one box:
-# G = -extra-device-vectorization, H = -Xptxas -dlcm=cg, I = -restrict.  WBC_B200_LIB selects the library.
+# A/B of variant builds, interleaved on one box (WBC_B200_LIB selects the library): VARIANTS names the libraries under lib/variants/, CMPVARIANTS the ones
+# whose outputs are compared bit for bit with the stored dump, OUT the result file.  Defaults = the first use: compile flags on top of -maxrregcount=128 (A),
+# G = -extra-device-vectorization, H = -Xptxas -dlcm=cg, I = -restrict.
 for rep in 1 2; do
   for v in ${VARIANTS:-A G H I}; do
     L=$PWD/wbc_quadruped_dob_b200/lib/variants/libwbc_b200_$v.so
